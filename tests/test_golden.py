@@ -1,0 +1,175 @@
+"""CPU oracle vs golden vectors produced by executing the reference's own sources
+(oracle/make_golden.py over oracle/jaxshim).  Integer / byte results: bit-exact.
+Network outputs: 1e-5 (the goldens come from numpy BLAS matmul, the oracle from
+the fp32 FMA-chain contract; north_star tolerance for fp32 is 1e-5 relative)."""
+import os
+
+import numpy as np
+import pytest
+
+from e_alphazero_b200 import _abi
+from oracle import oracle as O
+
+RTOL = 1e-5
+ATOL = 2e-6
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+@pytest.mark.parametrize("N", [4, 10, 30])
+def test_deepsea_trajectories(golden_dir, N):
+    g = load(golden_dir, "deepsea.npz")
+    env = O.Env.deepsea(N, g[f"N{N}_action_map"])
+    actions = g[f"N{N}_actions"]
+    E, T = actions.shape
+    st = O.env_init(env, E)
+    for t in range(T + 1):
+        assert (st["step_count"] == g[f"N{N}_step_count"][:, t]).all()
+        assert (st["col"] == g[f"N{N}_col"][:, t]).all()
+        assert (st["terminated"] == g[f"N{N}_terminated"][:, t]).all()
+        assert (st["rewards"][:, 0] == g[f"N{N}_rewards"][:, t]).all()
+        obs = O.env_observe(env, st)
+        assert (obs.sum(1) == 1).all()
+        assert (obs.argmax(1) == g[f"N{N}_obs_index"][:, t]).all()
+        if t < T:
+            st = O.env_step(env, st, actions[:, t])
+
+
+def test_subleq_trajectories(golden_dir):
+    g = load(golden_dir, "subleq_env.npz")
+    n = int(g["num_cases"])
+    assert n >= 60
+    for i in range(n):
+        ws, binary, rf, task = (int(g[f"c{i}_{k}"]) for k in ("ws", "binary", "reward_fn", "task"))
+        env = O.Env.subleq(ws, bool(binary), rf)
+        st = O.env_init(env, 1, [task])
+        acts = g[f"c{i}_actions"]
+        for t in range(len(acts) + 1):
+            ctx = f"case {i} ws={ws} task={task} t={t}"
+            assert st["step_count"][0] == g[f"c{i}__step_count"][t], ctx
+            assert st["solved"][0] == g[f"c{i}__solved"][t], ctx
+            assert st["terminated"][0] == g[f"c{i}_terminated"][t], ctx
+            assert (st["memory"][0] == g[f"c{i}__memory_state"][t]).all(), ctx
+            assert (st["input_after"][0] == g[f"c{i}__example_input_after"][t]).all(), ctx
+            assert (st["output_after"][0] == g[f"c{i}__example_output_after"][t]).all(), ctx
+            assert st["rewards"][0, 0] == g[f"c{i}_rewards"][t, 0], ctx
+            assert (O.env_observe(env, st)[0] == g[f"c{i}_observation"][t]).all(), ctx
+            tin, tout = O.subleq_test_cases(task, ws)
+            assert (tin == g[f"c{i}_test_in"][t]).all() and (tout == g[f"c{i}_test_out"][t]).all(), ctx
+            assert (tin[0] == g[f"c{i}__example_input"][t]).all() and (tout[0] == g[f"c{i}__example_output"][t]).all()
+            if t < len(acts):
+                st = O.env_step(env, st, [acts[t]])
+
+
+def test_subleq_simulate(golden_dir):
+    g = load(golden_dir, "subleq_simulate.npz")
+    outcomes = set()
+    for i in range(len(g["ws"])):
+        ws = int(g["ws"][i])
+        r = O.subleq_simulate(ws, g["memory"][i][:ws], g["tin"][i], g["tout"][i])
+        assert (r["input_after"] == g["in_after"][i]).all(), i
+        assert (r["output_after"] == g["out_after"][i]).all(), i
+        assert [r["bytes_used"], r["cycles_used"], int(r["correct"])] == g["bcc"][i].tolist(), i
+        outcomes.add((r["cycles_used"] >= 200, r["correct"]))
+    assert (True, False) in outcomes and (False, False) in outcomes  # both timeouts and early errors are covered
+
+
+def test_subleq_tables_and_encoders(golden_dir):
+    g = load(golden_dir, "subleq_tables.npz")
+    for ws in (16, 100, 256):
+        for task in range(1, 8):
+            tin, tout = O.subleq_test_cases(task, ws)
+            assert (tin == g[f"ws{ws}_t{task}_in"]).all() and (tout == g[f"ws{ws}_t{task}_out"]).all()
+    # docstring examples subleq.py:30-41 / 67-78 via the observation of a crafted state
+    env = O.Env.subleq(16, True)
+    st = O.env_init(env, 1, [1])
+    st["memory"][0, :5] = [1, 3, 5, -1 % 16, 0]
+    st["output_after"][0, 0] = 16
+    obs = O.env_observe(env, st)[0].reshape(48, 5)
+    assert (obs[:4] == g["binary_ws16"][:4]).all() and (obs[16 + 24] == g["binary_ws16"][4]).all()
+
+
+def test_xxhash(golden_dir):
+    g = load(golden_dir, "xxhash.npz")
+    for i in range(int(g["num"])):
+        idx = O.xxhash_indices(g[f"h{i}_x"], int(g[f"h{i}_bits"]))
+        assert (idx == g[f"h{i}_idx"]).all(), i
+    x = g["lk_x"]
+    bset = np.zeros(1 << 21, np.uint8)
+    assert (O.hash_lookup(x, bset) == g["lk_seen0"]).all()
+    O.hash_update(x[:8], bset)
+    assert (O.hash_lookup(x, bset) == g["lk_seen1"]).all()
+    nz = np.flatnonzero(bset)
+    assert (nz == g["lk_set_nonzero"]).all() and (bset[nz] == g["lk_set_values"]).all()
+    # SURVEY Appendix C known answers
+    z = np.zeros((1, 100), np.float32)
+    assert O.xxhash_indices(z, 32)[0] == 0xE0BE2238 and O.xxhash_indices(z)[0] == 14728738
+    with pytest.raises(ValueError):
+        O.xxhash_indices(np.zeros((1, 25), np.float32))  # hashes.py:210
+
+
+def _net_from_golden(g, tag, A, D, hash_io):
+    w = [[g[f"{tag}_w{h * 3 + l}"] for l in range(3)] for h in range(4)]
+    b = [[g[f"{tag}_b{h * 3 + l}"] for l in range(3)] for h in range(4)]
+    bset = np.zeros(1 << 21, np.uint8)
+    bset[g[f"{tag}_set_idx"]] = g[f"{tag}_set_val"]
+    return O.FcNet(D, 256, A, w, b, bset, 24, hash_io)
+
+
+@pytest.mark.parametrize("tag", ["ds10", "sub16"])
+def test_fc_network_and_recurrent_fn(golden_dir, tag):
+    g = load(golden_dir, "fcnet.npz")
+    if tag == "ds10":
+        env, A, hash_io, gamma = O.Env.deepsea(10, g["ds10_action_map"]), 2, 0, 0.997
+    else:
+        env, A, hash_io, gamma = O.Env.subleq(16, True), 16, 1, 0.97
+    obs = g[f"{tag}_obs"]
+    net = _net_from_golden(g, tag, A, obs.shape[1], hash_io)
+    out = O.mlp_forward(net, obs, env.hash_dim(hash_io))
+    assert out["novelty"].tolist() == g[f"{tag}_novelty"].tolist()  # exact: 0/1 from the bitset
+    assert 0 < out["novelty"].sum() < len(obs)
+    for k, gk in (("exploit_logits", "exploit"), ("explore_logits", "explore"), ("value", "value"), ("ube", "ube")):
+        np.testing.assert_allclose(out[k], g[f"{tag}_{gk}"], rtol=RTOL, atol=ATOL, err_msg=k)
+    # rebuild the states and run one search-free recurrent step through the oracle's search glue:
+    B = len(obs)
+    st = O.alloc_state(env, B)
+    st["terminated"][:] = g[f"{tag}_terminated"]
+    st["rewards"][:] = g[f"{tag}_rewards"]
+    if tag == "ds10":
+        st["step_count"][:], st["col"][:] = g["ds10_step_count"], g["ds10_col"]
+    else:
+        st["step_count"][:], st["task"][:], st["solved"][:] = g["sub16__step_count"], g["sub16__task"], g["sub16__solved"]
+        st["memory"][:], st["input_after"][:], st["output_after"][:] = (g["sub16__memory_state"], g["sub16__example_input_after"],
+                                                                        g["sub16__example_output_after"])
+    assert (O.env_observe(env, st) == obs).all()
+    for expl in (0, 1):
+        p = f"{tag}_rf{expl}_"
+        act = g[p + "action"]
+        # A 1-simulation search whose root prior forces `act`: node 1 then holds the recurrent_fn output.
+        prior = np.full((B, A), -50.0, np.float32)
+        prior[np.arange(B), act] = 0.0
+        cfg = _abi.default_search_config(num_simulations=1, discount=gamma, exploration=expl, gumbel_scale=0.0)
+        root = dict(prior_logits=prior, value=np.zeros(B, np.float32), value_epistemic_variance=np.zeros(B, np.float32),
+                    beta=np.zeros(B, np.float32), embedding=st, gumbel=np.zeros((B, A), np.float32))
+        t = O.search(cfg, env, net, root)
+        assert (t["children_index"][np.arange(B), 0, act] == 1).all()
+        assert (t["children_rewards"][np.arange(B), 0, act] == g[p + "reward"]).all()
+        assert (t["children_discounts"][np.arange(B), 0, act] == g[p + "discount"]).all()
+        assert (t["children_rewards_epistemic_variance"] == 0).all() and (g[p + "reward_epistemic_variance"] == 0).all()
+        np.testing.assert_allclose(t["children_prior_logits"][:, 1], g[p + "prior_logits"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(t["raw_values"][:, 1], g[p + "value"], rtol=RTOL, atol=ATOL)
+        np.testing.assert_allclose(t["raw_values_epistemic_variance"][:, 1], g[p + "value_epistemic_variance"], rtol=RTOL, atol=ATOL)
+        nxt = O.env_step(env, st, act)
+        assert (nxt["terminated"] == g[p + "terminated"]).all() and (nxt["step_count"] == g[p + "step_count"]).all()
+        assert (O.env_observe(env, nxt) == g[p + "obs"]).all()
+        assert g[p + "terminated"].any() and not g[p + "terminated"].all()
+
+
+def test_mask_invalid_actions(golden_dir):
+    g = load(golden_dir, "fcnet.npz")
+    lg, inv = g["mask_logits"], g["mask_invalid"]
+    exp = g["mask_out"]
+    got = np.where(inv > 0, np.float32(np.finfo(np.float32).min), lg - lg.max(1, keepdims=True))
+    assert (got == exp).all()
