@@ -72,6 +72,7 @@ class EazFcParams(C.Structure):
         ("binary_set", _p),
         ("hash_bits", C.c_int32),
         ("hash_io", C.c_int32),
+        ("word_size", C.c_int32),
         ("max_u", C.c_float),
         ("novelty_scale", C.c_float),
     ]

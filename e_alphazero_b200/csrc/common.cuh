@@ -1,0 +1,336 @@
+// common.cuh -- shared device code of libeaz_b200: error plumbing, the compact
+// in-tree env-state encodings, the DeepSea / Subleq transitions, the XXHash
+// variant, and the lane-group reductions whose order is the contract with the
+// CPU oracle (oracle/eaz_oracle.c: orc_tree_sum).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/eaz_b200.h"
+#include "../../include/eaz_math.h"
+
+namespace eaz {
+
+// ---------------------------------------------------------------- errors
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define EAZ_CHECK_ARG(cond, ...)      \
+  do {                                \
+    if (!(cond)) {                    \
+      ::eaz::set_error(__VA_ARGS__);  \
+      return EAZ_ERR_INVALID_ARG;     \
+    }                                 \
+  } while (0)
+
+#define EAZ_CHECK_LAUNCH(what)                                   \
+  do {                                                           \
+    cudaError_t e__ = cudaGetLastError();                        \
+    if (e__ != cudaSuccess) return ::eaz::cuda_fail(e__, what);  \
+  } while (0)
+
+static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------- env description (by value into kernels)
+struct EnvDesc {
+  int kind;
+  int size;                   // DeepSea N
+  const uint8_t* action_map;  // device, may be null
+  int ws;                     // Subleq word size
+  int binary;
+  int reward_fn;
+  int obs_cols;   // N | bit width | ws+1
+  int obs_dim;    // flattened observation length
+  int num_actions;
+  int compact_bytes;
+};
+
+inline int binary_width(int ws) {  // envs/subleq.py:59-60
+  int x = ws - 1, n = 0;
+  while (x > 0) { n++; x >>= 1; }
+  return n + 1;
+}
+
+int make_env_desc(const eaz_env* env, EnvDesc* d);  // validates like the reference asserts
+
+// Pointers of an eaz_state, by value.
+struct StateSoA {
+  int32_t* step_count;
+  float* rewards;
+  uint8_t* terminated;
+  uint8_t* truncated;
+  uint8_t* observation;
+  int32_t* col;
+  int32_t* memory;
+  int32_t* task;
+  uint8_t* solved;
+  int32_t* input_after;
+  int32_t* output_after;
+};
+inline StateSoA soa_of(const eaz_state* s) {
+  return StateSoA{s->step_count, s->rewards, s->terminated, s->truncated, s->observation, s->col,
+                  s->memory, s->task, s->solved, s->input_after, s->output_after};
+}
+
+// ---------------------------------------------------------------- compact states
+// DeepSea: one u32 -- bits 0..11 _step_count, 12..23 _horizontal_position,
+// 24 terminated, 25 truncated.
+// Subleq: [u16 in_after[8]] [u16 out_after[8]] [u16 step_count] [u8 task]
+// [u8 flags: 1 terminated, 2 truncated, 4 solved] [4 reserved] [u8 memory[ws]]
+// padded to a multiple of 8 bytes (40 + roundup8(ws)).
+#define EAZ_DS_STEP(v) ((int)((v)&0xfffu))
+#define EAZ_DS_COL(v) ((int)(((v) >> 12) & 0xfffu))
+#define EAZ_DS_TERM(v) ((int)(((v) >> 24) & 1u))
+#define EAZ_DS_TRUNC(v) ((int)(((v) >> 25) & 1u))
+__host__ __device__ inline uint32_t ds_pack(int step, int col, int term, int trunc) {
+  return ((uint32_t)step & 0xfffu) | (((uint32_t)col & 0xfffu) << 12) | ((uint32_t)(term != 0) << 24) |
+         ((uint32_t)(trunc != 0) << 25);
+}
+
+#define EAZ_SQ_HDR 40
+#define EAZ_SQ_FLAG_TERM 1
+#define EAZ_SQ_FLAG_TRUNC 2
+#define EAZ_SQ_FLAG_SOLVED 4
+
+// pgx.Env.step around DeepSea._step (deep_sea.py:59-81).  Returns the new
+// packed state; *reward receives rewards[0].
+__device__ __forceinline__ uint32_t deepsea_step(uint32_t s, int action, int N, const uint8_t* __restrict__ amap,
+                                                 float* reward) {
+  if (EAZ_DS_TERM(s) | EAZ_DS_TRUNC(s)) {  // absorbing: same state, zero rewards (pgx core.py Env.step)
+    *reward = 0.0f;
+    return s;
+  }
+  const int step = EAZ_DS_STEP(s) + 1;  // _step_count incremented before _step
+  int col = EAZ_DS_COL(s);
+  int row = min(max(step - 1, 0), N - 1);
+  const int flip = amap ? (amap[row * N + min(col, N - 1)] != 0) : 0;  // :62
+  const int shift = ((action == 0) != (flip != 0)) ? -1 : 1;          // :63
+  col = min(max(col + shift, 0), N - 1);                               // :64
+  const int term = step >= N - 1;                                      // :72
+  *reward = (term && col == N - 1) ? 1.0f : 0.0f;                      // :74-78
+  return ds_pack(step, col, term, 0);
+}
+
+// Observation cell of a DeepSea state (deep_sea.py:56,68-70).
+__device__ __forceinline__ int deepsea_obs_index(uint32_t s, int N) {
+  return min(EAZ_DS_STEP(s), N - 1) * N + EAZ_DS_COL(s);
+}
+
+// ---------------------------------------------------------------- Subleq test cases (subleq.py:398-501)
+struct SubleqVec {
+  int8_t len;
+  int8_t v[8];
+};
+// [task 0..5][test 0..2]; the sixth row is the last lax.switch branch (MULTIPLICATION).
+static __constant__ SubleqVec c_sq_in[6][3] = {
+    {{7, {1, 2, 3, 4, 5, 6, 7, 0}}, {8, {5, 4, 4, 5, 1, 2, 3, 1}}, {8, {1, 1, 6, 2, 4, 4, 5, 3}}},
+    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}},
+    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}},
+    {{6, {1, 1, 5, 4, 0, -3, 0, 0}}, {6, {2, 3, 0, 0, -1, -2, 0, 0}}, {8, {1, 2, 3, 4, 4, 3, 2, 1}}},
+    {{6, {1, 1, 5, 4, 0, -3, 0, 0}}, {6, {2, 3, 0, 0, -1, -2, 0, 0}}, {8, {1, 2, 3, 4, 4, 3, 2, 1}}},
+    {{6, {1, 2, 2, 3, -7, 4, 0, 0}}, {6, {-1, -5, 5, 2, 0, 1, 0, 0}}, {6, {0, 0, 1, 1, -3, 3, 0, 0}}},
+};
+static __constant__ SubleqVec c_sq_out[6][3] = {
+    {{7, {-1, -2, -3, -4, -5, -6, -7, 0}}, {8, {-5, -4, -4, -5, -1, -2, -3, -1}}, {8, {-1, -1, -6, -2, -4, -4, -5, -3}}},
+    {{8, {4, 3, 2, 1, 0, -1, -2, -3}}, {7, {-1, -2, -3, -4, -5, -6, -7, 0}}, {5, {0, 1, -2, 3, -4, 0, 0, 0}}},
+    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}},
+    {{3, {0, 1, 3, 0, 0, 0, 0, 0}}, {3, {-1, 0, 1, 0, 0, 0, 0, 0}}, {4, {-1, -1, 1, 1, 0, 0, 0, 0}}},
+    {{3, {2, 9, -3, 0, 0, 0, 0, 0}}, {3, {5, 0, -3, 0, 0, 0, 0, 0}}, {4, {3, 7, 7, 3, 0, 0, 0, 0}}},
+    {{3, {2, 6, -28, 0, 0, 0, 0, 0}}, {3, {5, 10, 0, 0, 0, 0, 0, 0}}, {3, {0, 1, -9, 0, 0, 0, 0, 0}}},
+};
+
+__host__ __device__ inline int floormod(int x, int m) {
+  int r = x % m;
+  return r < 0 ? r + m : r;
+}
+__device__ __forceinline__ int sq_task_row(int task) { return min(max(task - 1, 0), 5); }  // lax.switch clamps
+// element i of test k: x % ws, padded with ws (subleq.py:402-404)
+__device__ __forceinline__ int sq_test_in(int trow, int k, int i, int ws) {
+  return i < c_sq_in[trow][k].len ? floormod(c_sq_in[trow][k].v[i], ws) : ws;
+}
+__device__ __forceinline__ int sq_test_out(int trow, int k, int i, int ws) {
+  return i < c_sq_out[trow][k].len ? floormod(c_sq_out[trow][k].v[i], ws) : ws;
+}
+
+// One simulate() call (subleq.py:156-395) on a byte memory image living in
+// shared or local memory.  `mem` is modified.  Returns correct / fills results.
+struct SubleqSim {
+  int in[8];
+  int out[8];
+  int bytes_used;
+  int cycles;
+  int correct;
+};
+template <typename MemT>
+__device__ __forceinline__ void subleq_simulate(int ws, MemT* mem, int trow, int k, SubleqSim& r) {
+  const int AMAX = ws - 4, AIN = ws - 3, AOUT = ws - 2;
+  int tout[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r.in[i] = sq_test_in(trow, k, i, ws);
+    tout[i] = sq_test_out(trow, k, i, ws);
+    r.out[i] = ws;  // :382
+  }
+  int out_cur = 0, cur = 0, bytes = 0, cycles = 0, halt = 0, err = 0;
+  while (!err && !halt && cycles < EAZ_SUBLEQ_MAX_CYCLES) {  // :297-299
+    cycles += 1;
+    if (cur + 2 >= ws) {  // :364-370
+      err = 1;
+      break;
+    }
+    bytes = max(bytes, cur + 3);  // :311
+    const int a = mem[cur], b = mem[cur + 1], c = mem[cur + 2];
+    int va = 0, vb = 0, acc = 0, e = 0;
+    if (a <= AMAX) va = mem[a];
+    else if (a == AIN) { if (r.in[0] >= ws) e = 1; else { va = r.in[0]; acc = 1; } }
+    if (b <= AMAX) vb = mem[b];
+    else if (b == AIN) { if (r.in[0] >= ws) e = 1; else { vb = r.in[0]; acc = 1; } }
+    const int value = floormod(va - vb, ws);  // :322
+    int modified = 0;
+    if (a <= AMAX) mem[a] = (MemT)value;
+    else if (a == AOUT) {
+      if (out_cur >= 8) e = 1;
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) if (i == out_cur) r.out[i] = value;
+        out_cur += 1;
+        modified = 1;
+      }
+    }
+    const int jump = (value == 0) || (2 * value >= ws);  // :329
+    cur = jump ? c : cur + 3;
+    if (acc) {  // :333-338
+#pragma unroll
+      for (int i = 0; i < 7; ++i) r.in[i] = r.in[i + 1];
+      r.in[7] = ws;
+    }
+    int all_eq = 1, last_ok = 1;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      all_eq &= (r.out[i] == tout[i]);
+      if (i == out_cur - 1) last_ok = (r.out[i] == tout[i]);
+    }
+    halt = ((((jump ? 1 : 0) & c) > AMAX) ? 1 : 0) | all_eq;  // :340-345, precedence as written
+    err = e | (modified && !last_ok);                         // :346-350
+  }
+  int all_eq = 1;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) all_eq &= (r.out[i] == tout[i]);
+  r.bytes_used = bytes;
+  r.cycles = cycles;
+  r.correct = (!err) && all_eq;  // :394
+}
+
+__device__ __forceinline__ float subleq_reward(int reward_fn, int solved, int bytes_used) {
+  if (reward_fn == EAZ_SUBLEQ_REWARD_LOWEST_BYTES) return __fdiv_rn((float)solved, (float)(1 + bytes_used));  // :540-542
+  return (float)solved;                                                                                      // :535-537
+}
+
+// ---------------------------------------------------------------- XXHash variant (network/hashes.py:162-229)
+#define EAZ_XX_P1 0x9E3779B1u
+#define EAZ_XX_P2 0x85EBCA77u
+#define EAZ_XX_P3 0xC2B2AE3Du
+#define EAZ_XX_ONE 0x3F800000u  // bit pattern of 1.0f
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, int n) { return __funnelshift_l(x, x, n); }
+__device__ __forceinline__ uint32_t xx_init(int lane) {
+  return lane == 0 ? 1u + EAZ_XX_P1 + EAZ_XX_P2 : lane == 1 ? 1u + EAZ_XX_P2 : lane == 2 ? 1u : 1u - EAZ_XX_P1;  // :217-220
+}
+__device__ __forceinline__ uint32_t xx_round(uint32_t acc, uint32_t word) {
+  return rotl32(acc + word * EAZ_XX_P2, 13) * EAZ_XX_P1;  // :176-181
+}
+__device__ __forceinline__ uint32_t xx_finish(uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, int L, int bits) {
+  uint32_t h = rotl32(a0, 1) + rotl32(a1, 7) + rotl32(a2, 12) + rotl32(a3, 18);  // :187
+  h += (uint32_t)L;                                                              // :226
+  h ^= h >> 15; h *= EAZ_XX_P2; h ^= h >> 13; h *= EAZ_XX_P3; h ^= h >> 16;      // :190-197
+  return bits >= 32 ? h : (h >> (32 - bits));                                    // :229
+}
+
+// ---------------------------------------------------------------- lane groups
+// G lanes per tree, action a in lane a % G, slot a / G.  Sums: slots ascending
+// from 0.0f per lane, then xor-butterfly with strides 1,2,..,G/2.
+template <int G>
+__device__ __forceinline__ float group_sum(float v) {
+#pragma unroll
+  for (int s = 1; s < G; s <<= 1) v = __fadd_rn(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ int group_sum_i(int v) {
+#pragma unroll
+  for (int s = 1; s < G; s <<= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
+  return v;
+}
+template <int G>
+__device__ __forceinline__ int group_max_i(int v) {
+#pragma unroll
+  for (int s = 1; s < G; s <<= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float group_max(float v) {
+#pragma unroll
+  for (int s = 1; s < G; s <<= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+template <int G>
+__device__ __forceinline__ float group_min(float v) {
+#pragma unroll
+  for (int s = 1; s < G; s <<= 1) v = fminf(v, __shfl_xor_sync(0xffffffffu, v, s));
+  return v;
+}
+// argmax with lowest index among maxima (jnp.argmax)
+template <int G>
+__device__ __forceinline__ int group_argmax(float v, int idx) {
+#pragma unroll
+  for (int s = 1; s < G; s <<= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, v, s);
+    const int oi = __shfl_xor_sync(0xffffffffu, idx, s);
+    if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
+  }
+  return idx;
+}
+
+}  // namespace eaz
+
+// ---------------------------------------------------------------- Subleq step, block-cooperative
+// A block of 3*EAZ_SQ_EPB threads advances EAZ_SQ_EPB envs: thread (e,k) runs
+// test case k of env e (run_tests, subleq.py:504-532, vmaps the 3 tests).
+#define EAZ_SQ_EPB 32
+#define EAZ_SQ_IMG 264  // >= 256 + slack, multiple of 8
+namespace eaz {
+struct SqShared {
+  uint8_t img[3 * EAZ_SQ_EPB][EAZ_SQ_IMG];  // per-(env,test) scratch memory image
+  uint8_t base[EAZ_SQ_EPB][EAZ_SQ_IMG];     // program after writing the action
+  int16_t in_after[EAZ_SQ_EPB][8];
+  int16_t out_after[EAZ_SQ_EPB][8];
+  int correct[EAZ_SQ_EPB][3];
+  int bytes[EAZ_SQ_EPB][3];
+  int run[EAZ_SQ_EPB];   // 1 = execute the program for this env
+  int trow[EAZ_SQ_EPB];  // row of the test-case table
+};
+
+// All 3*EPB threads call this after base/run/trow are filled and synced.
+// On return (after its trailing __syncthreads) in_after/out_after/correct/bytes hold the results.
+__device__ __forceinline__ void sq_run_tests_block(SqShared& sh, int ws) {
+  const int e = threadIdx.x / 3, k = threadIdx.x % 3;
+  if (sh.run[e]) {
+    uint8_t* img = sh.img[threadIdx.x];
+    const uint8_t* base = sh.base[e];
+    for (int i = 0; i < ws; i += 8) *reinterpret_cast<uint2*>(img + i) = *reinterpret_cast<const uint2*>(base + i);
+    SubleqSim r;
+    subleq_simulate<uint8_t>(ws, img, sh.trow[e], k, r);
+    sh.correct[e][k] = r.correct;
+    sh.bytes[e][k] = r.bytes_used;
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        sh.in_after[e][i] = (int16_t)r.in[i];
+        sh.out_after[e][i] = (int16_t)r.out[i];
+      }
+    }
+  }
+  __syncthreads();
+}
+}  // namespace eaz

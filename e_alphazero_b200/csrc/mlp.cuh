@@ -1,0 +1,40 @@
+// mlp.cuh -- launch interface of the FC network kernels (mlp.cu), shared with search.cu.
+#pragma once
+#include "common.cuh"
+
+namespace eaz {
+
+struct NetDesc {
+  int D, H, A;
+  const float* w[4][3];
+  const float* b[4][3];
+  const uint8_t* bset;
+  int hash_bits, hash_io, hash_dim;
+  float max_u, novelty_scale;
+};
+int make_net_desc(const eaz_fc_params* net, const EnvDesc* env, NetDesc* d);
+
+// Where the observation of row b comes from.
+struct MlpSource {
+  const uint8_t* dense;       // bool [B,D] or null
+  const uint8_t* compact;     // compact env states or null
+  const int32_t* node_index;  // optional [B]: row b's state is compact[(node_index[b]*B + b)*S]; null: compact[b*S]
+  const uint8_t* ds_seen;     // optional DeepSea per-cell "seen" table [D] (replaces hashing the one-hot row)
+};
+
+struct MlpOutputs {
+  float* logits[2];  // [B,A] for EAZ_HEAD_EXPLOIT / EAZ_HEAD_EXPLORE
+  float* value;      // [B]
+  float* ube;        // [B]
+  float* novelty;    // [B]
+};
+
+// heads_mask: bit h set = evaluate head h.  mode: EAZ_MLP_EXACT | EAZ_MLP_TENSOR.
+int launch_mlp(const NetDesc& net, const EnvDesc& env, const MlpSource& src, int B, int heads_mask, const MlpOutputs& out, int mode,
+               cudaStream_t stream);
+int mlp_num_launches(int mode);
+
+// DeepSea: seen[cell] for every one-hot observation (one hash per grid cell).
+int launch_deepsea_seen_table(const NetDesc& net, const EnvDesc& env, uint8_t* seen, cudaStream_t stream);
+
+}  // namespace eaz

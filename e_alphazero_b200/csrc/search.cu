@@ -1,0 +1,798 @@
+// search.cu -- emctx.epistemic_gumbel_muzero_policy for B independent trees
+// (call sites: selfplay.py:107-117, reanalyze.py:77-85, evaluate.py:36-45) with
+// the recurrent_fn of context.py:109-157 fused in.  Algorithm: mctx search.py /
+// action_selection.py / qtransforms.py / seq_halving.py / policies.py plus the
+// epistemic extension of SURVEY.md Appendix A (assumptions = EAZ_FLAG_*).
+//
+// Data layout (workspace): the tree is a struct of arrays, NODE-major:
+//   node arrays  [N][B]      visits, raw/node value, raw/node variance, link{parent,action}
+//   edge arrays  [N][B][A]   child index, prior logit, visits, reward, discount, value, value variance
+//   states       [N][B][S]   compact env state per node
+// so that everything written for the node expanded in simulation i (the same
+// node index i+1 for every tree) and everything read at the root is contiguous
+// across the batch.  G = min(32, pow2(A)) lanes cooperate on one tree: lane g owns
+// actions g, g+G, ...; all reductions over actions are warp shuffles in the
+// fixed order shared with the oracle (common.cuh).
+//
+// Per simulation: select (+ fused DeepSea step | Subleq step kernel) -> network
+// -> expand + backward.  Everything is enqueued on the caller's stream with no
+// host synchronisation, so a whole search is CUDA-graph capturable.
+#include "mlp.cuh"
+
+namespace eaz {
+
+struct Tree {
+  int B, N, A, S;
+  int32_t* node_visits;
+  float *raw_values, *node_values, *raw_var, *node_var;
+  int2* link;
+  int32_t *children_index, *children_visits;
+  float *prior, *rewards, *discounts, *values, *values_var;
+  uint8_t* states;
+  // scratch
+  float *gumbel, *net_logits, *net_value, *net_ube, *reward;
+  int32_t *parent, *action, *leaf;
+  int32_t* table;
+  uint8_t* ds_seen;
+};
+
+struct Layout {
+  size_t off[32];
+  size_t total;
+  size_t zero_begin, zero_end, ones_begin, ones_end;
+};
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, Layout* L) {
+  const size_t nb = (size_t)N * B, nba = nb * A;
+  size_t o = 0;
+  int i = 0;
+  auto put = [&](size_t bytes) { L->off[i++] = o; o = align_up(o + bytes); };
+  L->zero_begin = o;
+  put(nb * 4);   // 0 node_visits
+  put(nb * 4);   // 1 raw_values
+  put(nb * 4);   // 2 node_values
+  put(nb * 4);   // 3 raw_var
+  put(nb * 4);   // 4 node_var
+  put(nba * 4);  // 5 children_visits
+  put(nba * 4);  // 6 prior
+  put(nba * 4);  // 7 rewards
+  put(nba * 4);  // 8 discounts
+  put(nba * 4);  // 9 values
+  put(nba * 4);  // 10 values_var
+  put(nb * S);   // 11 states
+  L->zero_end = o;
+  L->ones_begin = o;
+  put(nb * 8);   // 12 link
+  put(nba * 4);  // 13 children_index
+  L->ones_end = o;
+  put((size_t)B * A * 4);  // 14 gumbel
+  put((size_t)B * A * 4);  // 15 net_logits
+  put((size_t)B * 4);      // 16 net_value
+  put((size_t)B * 4);      // 17 net_ube
+  put((size_t)B * 4);      // 18 reward
+  put((size_t)B * 4);      // 19 parent
+  put((size_t)B * 4);      // 20 action
+  put((size_t)B * 4);      // 21 leaf
+  put((size_t)table_len * 4);  // 22 table
+  put((size_t)obs_dim);        // 23 ds_seen
+  L->total = o;
+}
+
+static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
+  uint8_t* p = (uint8_t*)ws;
+  Tree t;
+  t.B = B; t.N = N; t.A = A; t.S = S;
+  t.node_visits = (int32_t*)(p + L.off[0]);
+  t.raw_values = (float*)(p + L.off[1]);
+  t.node_values = (float*)(p + L.off[2]);
+  t.raw_var = (float*)(p + L.off[3]);
+  t.node_var = (float*)(p + L.off[4]);
+  t.children_visits = (int32_t*)(p + L.off[5]);
+  t.prior = (float*)(p + L.off[6]);
+  t.rewards = (float*)(p + L.off[7]);
+  t.discounts = (float*)(p + L.off[8]);
+  t.values = (float*)(p + L.off[9]);
+  t.values_var = (float*)(p + L.off[10]);
+  t.states = p + L.off[11];
+  t.link = (int2*)(p + L.off[12]);
+  t.children_index = (int32_t*)(p + L.off[13]);
+  t.gumbel = (float*)(p + L.off[14]);
+  t.net_logits = (float*)(p + L.off[15]);
+  t.net_value = (float*)(p + L.off[16]);
+  t.net_ube = (float*)(p + L.off[17]);
+  t.reward = (float*)(p + L.off[18]);
+  t.parent = (int32_t*)(p + L.off[19]);
+  t.action = (int32_t*)(p + L.off[20]);
+  t.leaf = (int32_t*)(p + L.off[21]);
+  t.table = (int32_t*)(p + L.off[22]);
+  t.ds_seen = p + L.off[23];
+  return t;
+}
+
+// Search scalars, by value into the kernels.
+struct SearchParams {
+  int n, max_depth, max_considered;
+  float gumbel_scale, discount, value_scale, maxvisit_init, epsilon;
+  int two_players, rescale, mixed, flags;
+};
+
+// ------------------------------------------------------------------ state packing
+__global__ void pack_states_kernel(EnvDesc env, StateSoA s, uint8_t* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int term = s.terminated[b] != 0, trunc = s.truncated ? (s.truncated[b] != 0) : 0;
+  if (env.kind == EAZ_ENV_DEEPSEA) {
+    reinterpret_cast<uint32_t*>(out)[b] = ds_pack(s.step_count[b], s.col[b], term, trunc);
+    return;
+  }
+  const int S = env.compact_bytes, ws = env.ws;
+  uint8_t* o = out + (size_t)b * S;
+  uint16_t* h = reinterpret_cast<uint16_t*>(o);
+  for (int i = 0; i < 8; ++i) {
+    h[i] = (uint16_t)s.input_after[(size_t)b * 8 + i];
+    h[8 + i] = (uint16_t)s.output_after[(size_t)b * 8 + i];
+  }
+  h[16] = (uint16_t)s.step_count[b];
+  o[34] = (uint8_t)s.task[b];
+  o[35] = (uint8_t)((term ? EAZ_SQ_FLAG_TERM : 0) | (trunc ? EAZ_SQ_FLAG_TRUNC : 0) | (s.solved[b] ? EAZ_SQ_FLAG_SOLVED : 0));
+  o[36] = o[37] = o[38] = o[39] = 0;
+  for (int i = 0; i < S - EAZ_SQ_HDR; ++i) o[EAZ_SQ_HDR + i] = i < ws ? (uint8_t)s.memory[(size_t)b * ws + i] : 0;
+}
+
+// ------------------------------------------------------------------ sequential halving table (mctx seq_halving.py)
+__global__ void seq_halving_table_kernel(int max_considered, int n, int32_t* __restrict__ table) {
+  const int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m > max_considered) return;
+  int32_t* seq = table + (size_t)m * n;
+  if (m <= 1) {
+    for (int i = 0; i < n; ++i) seq[i] = i;
+    return;
+  }
+  int log2max = 0;
+  while ((1 << log2max) < m) log2max++;
+  int visits[256];
+  for (int i = 0; i < m; ++i) visits[i] = 0;
+  int nc = m, len = 0;
+  while (len < n) {
+    int extra = max(1, n / (log2max * nc));
+    for (int e = 0; e < extra && len < n; ++e) {
+      for (int i = 0; i < nc && len < n; ++i) seq[len++] = visits[i];
+      for (int i = 0; i < nc; ++i) visits[i] += 1;
+    }
+    nc = max(2, nc / 2);
+  }
+}
+
+// ------------------------------------------------------------------ lane-group helpers
+template <int G, int J>
+struct Edge {
+  int32_t ci[J], vis[J];
+  float pl[J], rew[J], dis[J], val[J], vvar[J];
+};
+
+template <int G, int J>
+__device__ __forceinline__ void load_edges(const Tree& t, size_t node_slot, int gl, bool active, Edge<G, J>& e) {
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int a = gl + G * j;
+    if (active && a < t.A) {
+      const size_t o = node_slot * t.A + a;
+      e.ci[j] = t.children_index[o];
+      e.vis[j] = t.children_visits[o];
+      e.pl[j] = t.prior[o];
+      e.rew[j] = t.rewards[o];
+      e.dis[j] = t.discounts[o];
+      e.val[j] = t.values[o];
+      e.vvar[j] = t.values_var[o];
+    } else {
+      e.ci[j] = -1; e.vis[j] = 0;
+      e.pl[j] = 0.0f; e.rew[j] = 0.0f; e.dis[j] = 0.0f; e.val[j] = 0.0f; e.vvar[j] = 0.0f;
+    }
+  }
+}
+
+// softmax over the group's actions (jax.nn.softmax: exp(x - max) / sum)
+template <int G, int J>
+__device__ __forceinline__ void group_softmax(const float (&x)[J], const bool (&valid)[J], float (&p)[J]) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < J; ++j) if (valid[j]) m = fmaxf(m, x[j]);
+  m = group_max<G>(m);
+  float s = 0.0f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    p[j] = valid[j] ? eaz_exp(__fsub_rn(x[j], m)) : 0.0f;
+    s = __fadd_rn(s, p[j]);
+  }
+  s = group_sum<G>(s);
+#pragma unroll
+  for (int j = 0; j < J; ++j) p[j] = __fdiv_rn(p[j], s);
+}
+
+// epistemic_qtransform_completed_by_mix_value (mctx qtransforms.py + beta)
+template <int G, int J>
+__device__ __forceinline__ void qtransform(const SearchParams& sp, const Edge<G, J>& e, const bool (&valid)[J], float raw, float raw_var,
+                                           float beta, bool use_beta, float (&cq)[J], int& sumN, int& maxN) {
+  float q[J];
+  int sn = 0, mn = 0;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    q[j] = __fadd_rn(e.rew[j], __fmul_rn(e.dis[j], e.val[j]));
+    if (use_beta) {
+      const float qv = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(e.dis[j], e.dis[j]), e.vvar[j]));  // reward variance == 0 (context.py:149)
+      q[j] = __fadd_rn(q[j], __fmul_rn(beta, __fsqrt_rn(qv)));
+    }
+    if (valid[j]) { sn += e.vis[j]; mn = max(mn, e.vis[j]); }
+  }
+  sumN = group_sum_i<G>(sn);
+  maxN = group_max_i<G>(mn);
+  if (use_beta && (sp.flags & EAZ_FLAG_BETA_RAW)) raw = __fadd_rn(raw, __fmul_rn(beta, __fsqrt_rn(raw_var)));
+  float value = raw;
+  if (sp.mixed) {  // _compute_mixed_value
+    float p[J];
+    group_softmax<G, J>(e.pl, valid, p);
+    float sP = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      p[j] = eaz_max(EAZ_F32_TINY, p[j]);
+      sP = __fadd_rn(sP, (valid[j] && e.vis[j] > 0) ? p[j] : 0.0f);
+    }
+    sP = group_sum<G>(sP);
+    float wq = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j) wq = __fadd_rn(wq, (valid[j] && e.vis[j] > 0) ? __fdiv_rn(__fmul_rn(p[j], q[j]), sP) : 0.0f);
+    wq = group_sum<G>(wq);
+    value = __fdiv_rn(__fadd_rn(raw, __fmul_rn((float)sumN, wq)), (float)(sumN + 1));
+  }
+  float c[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) c[j] = e.vis[j] > 0 ? q[j] : value;  // _complete_qvalues (reanalyze.py:32-40)
+  if (sp.rescale) {  // _rescale_qvalues
+    float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < J; ++j) if (valid[j]) { lo = fminf(lo, c[j]); hi = fmaxf(hi, c[j]); }
+    lo = group_min<G>(lo);
+    hi = group_max<G>(hi);
+    const float den = eaz_max(__fsub_rn(hi, lo), sp.epsilon);
+#pragma unroll
+    for (int j = 0; j < J; ++j) c[j] = __fdiv_rn(__fsub_rn(c[j], lo), den);
+  }
+  const float scale = __fmul_rn(__fadd_rn(sp.maxvisit_init, (float)maxN), sp.value_scale);
+#pragma unroll
+  for (int j = 0; j < J; ++j) cq[j] = __fmul_rn(scale, c[j]);
+}
+
+// seq_halving.score_considered + masked_argmax
+template <int G, int J>
+__device__ __forceinline__ int root_argmax(const Edge<G, J>& e, const bool (&valid)[J], const float (&gum)[J], const bool (&inval)[J],
+                                           const float (&cq)[J], int considered_visit, int gl) {
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < J; ++j) if (valid[j]) m = fmaxf(m, e.pl[j]);
+  m = group_max<G>(m);
+  float best = -INFINITY;
+  int besti = 1 << 30;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int a = gl + G * j;
+    float s = -INFINITY;
+    if (valid[j]) {
+      const float lg = __fsub_rn(e.pl[j], m);
+      s = eaz_max(-1e9f, __fadd_rn(__fadd_rn(gum[j], lg), cq[j]));
+      s = __fadd_rn(s, e.vis[j] == considered_visit ? 0.0f : -INFINITY);
+      if (inval[j]) s = -INFINITY;
+    }
+    const int ia = valid[j] ? a : (1 << 30);
+    if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
+  }
+  return group_argmax<G>(best, besti);
+}
+
+#define EAZ_GROUP_PROLOGUE()                                               \
+  const int lane = threadIdx.x & 31;                                       \
+  const int gl = lane & (G - 1);                                           \
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;    \
+  const int b = warp_global * (32 / G) + (lane / G);                       \
+  const bool in_range = b < t.B;                                           \
+  bool valid[J];                                                           \
+  _Pragma("unroll") for (int j = 0; j < J; ++j) valid[j] = (gl + G * j) < t.A;
+
+// ------------------------------------------------------------------ root initialisation (A.1 steps 1-2, A.2)
+template <int G, int J>
+__global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp, const float* __restrict__ prior_logits,
+                                                         const float* __restrict__ value, const float* __restrict__ var,
+                                                         const float* __restrict__ gumbel, const uint8_t* __restrict__ invalid) {
+  EAZ_GROUP_PROLOGUE();
+  float lg[J];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    lg[j] = (in_range && valid[j]) ? prior_logits[(size_t)b * t.A + gl + G * j] : 0.0f;
+    if (valid[j]) m = fmaxf(m, lg[j]);
+  }
+  m = group_max<G>(m);
+  if (!in_range) return;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (!valid[j]) continue;
+    const int a = gl + G * j;
+    const bool inv = invalid && invalid[(size_t)b * t.A + a];
+    t.prior[(size_t)b * t.A + a] = inv ? EAZ_F32_MIN : __fsub_rn(lg[j], m);  // _mask_invalid_actions (reanalyze.py:16-29)
+    t.gumbel[(size_t)b * t.A + a] = __fmul_rn(sp.gumbel_scale, gumbel[(size_t)b * t.A + a]);
+  }
+  if (gl == 0) {
+    t.raw_values[b] = t.node_values[b] = value[b];
+    t.raw_var[b] = t.node_var[b] = var[b];
+    t.node_visits[b] = 1;
+  }
+}
+
+// ------------------------------------------------------------------ simulate (A.3) [+ DeepSea transition]
+template <int G, int J>
+__global__ void __launch_bounds__(128) select_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, const float* __restrict__ beta_in,
+                                                      const uint8_t* __restrict__ invalid) {
+  EAZ_GROUP_PROLOGUE();
+  const float beta = (in_range && beta_in) ? beta_in[b] : 0.0f;
+  float gum[J];
+  bool inval[J];
+  int num_valid = 0;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int a = gl + G * j;
+    gum[j] = (in_range && valid[j]) ? t.gumbel[(size_t)b * t.A + a] : 0.0f;
+    inval[j] = (in_range && valid[j] && invalid) ? (invalid[(size_t)b * t.A + a] != 0) : false;
+    num_valid += (valid[j] && !inval[j]) ? 1 : 0;
+  }
+  num_valid = group_sum_i<G>(num_valid);
+  const int num_considered = min(sp.max_considered, num_valid);
+
+  int node = 0, parent = 0, action = 0, next = 0, depth = 0;
+  bool cont = in_range;
+  while (__any_sync(0xffffffffu, cont)) {
+    Edge<G, J> e;
+    const size_t slot = (size_t)node * t.B + b;
+    load_edges<G, J>(t, slot, gl, cont, e);
+    const float raw = cont ? t.raw_values[slot] : 0.0f;
+    const float raw_var = cont ? t.raw_var[slot] : 0.0f;
+    float cq[J];
+    int sumN, maxN, act;
+    if (depth == 0) {  // gumbel_muzero_root_action_selection (uniform: all trees start at the root together)
+      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, true, cq, sumN, maxN);
+      const int considered_visit = cont ? t.table[(size_t)num_considered * sp.n + min(sumN, sp.n - 1)] : 0;
+      act = root_argmax<G, J>(e, valid, gum, inval, cq, considered_visit, gl);
+    } else {  // gumbel_muzero_interior_action_selection
+      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0, cq, sumN, maxN);
+      float x[J], p[J];
+#pragma unroll
+      for (int j = 0; j < J; ++j) x[j] = __fadd_rn(e.pl[j], cq[j]);
+      group_softmax<G, J>(x, valid, p);
+      const float den = (float)(1 + sumN);
+      float best = -INFINITY;
+      int besti = 1 << 30;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float s = valid[j] ? __fsub_rn(p[j], __fdiv_rn((float)e.vis[j], den)) : -INFINITY;
+        const int ia = valid[j] ? gl + G * j : (1 << 30);
+        if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
+      }
+      act = group_argmax<G>(best, besti);
+    }
+    // children_index[node, act]: owned by lane act % G, slot act / G
+    int ci_sel = -1;
+#pragma unroll
+    for (int j = 0; j < J; ++j) if (j == act / G) ci_sel = e.ci[j];
+    const int nxt = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
+    depth += 1;
+    if (cont) {
+      parent = node;
+      action = act;
+      next = nxt;
+      cont = (nxt != -1) && (depth < sp.max_depth);
+      if (cont) node = nxt;
+    }
+  }
+  if (!in_range || gl != 0) return;
+  const int leaf = next == -1 ? sim + 1 : next;  // search.py: node first expanded on simulation i gets index i+1
+  t.parent[b] = parent;
+  t.action[b] = action;
+  t.leaf[b] = leaf;
+  if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
+    uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
+    float reward;
+    st[(size_t)leaf * t.B + b] = deepsea_step(st[(size_t)parent * t.B + b], action, env.size, env.action_map, &reward);
+    t.reward[b] = reward;
+  }
+}
+
+// ------------------------------------------------------------------ Subleq transition on tree states (context.py:127)
+__global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_tree_step_kernel(Tree t, EnvDesc env) {
+  __shared__ SqShared sh;
+  __shared__ int kind[EAZ_SQ_EPB];  // 0 absorbing, 1 terminate now, 2 execute
+  __shared__ __align__(8) uint8_t hdr[EAZ_SQ_EPB][EAZ_SQ_HDR];
+  const int ws = env.ws, S = t.S;
+  const int e = threadIdx.x / 3, k = threadIdx.x % 3;
+  const int b = blockIdx.x * EAZ_SQ_EPB + e;
+  if (k == 0) {
+    int kd = -1, run = 0;
+    if (b < t.B) {
+      const uint8_t* ps = t.states + ((size_t)t.parent[b] * t.B + b) * S;
+      for (int i = 0; i < EAZ_SQ_HDR / 8; ++i) reinterpret_cast<uint2*>(hdr[e])[i] = reinterpret_cast<const uint2*>(ps)[i];
+      for (int i = 0; i < S - EAZ_SQ_HDR; i += 8) *reinterpret_cast<uint2*>(&sh.base[e][i]) = *reinterpret_cast<const uint2*>(ps + EAZ_SQ_HDR + i);
+      uint16_t* h = reinterpret_cast<uint16_t*>(hdr[e]);
+      const int flags = hdr[e][35];
+      if (flags & (EAZ_SQ_FLAG_TERM | EAZ_SQ_FLAG_TRUNC)) {
+        kd = 0;
+      } else {
+        const int step = h[16] + 1;  // _step_count incremented before _step
+        h[16] = (uint16_t)step;
+        if (step >= ws - 3 || (flags & EAZ_SQ_FLAG_SOLVED)) {  // subleq.py:671-673
+          kd = 1;
+          hdr[e][35] = (uint8_t)(flags | EAZ_SQ_FLAG_TERM);
+        } else {
+          sh.base[e][step - 1] = (uint8_t)t.action[b];  // :654
+          sh.trow[e] = sq_task_row(hdr[e][34]);
+          kd = 2;
+          run = 1;
+        }
+      }
+    }
+    kind[e] = kd;
+    sh.run[e] = run;
+  }
+  __syncthreads();
+  sq_run_tests_block(sh, ws);
+  if (k != 0 || b >= t.B) return;
+  float reward = 0.0f;
+  if (kind[e] == 2) {
+    const int solved = sh.correct[e][0] & sh.correct[e][1] & sh.correct[e][2];
+    const int bytes = max(sh.bytes[e][0], max(sh.bytes[e][1], sh.bytes[e][2]));
+    reward = subleq_reward(env.reward_fn, solved, bytes);
+    uint16_t* h = reinterpret_cast<uint16_t*>(hdr[e]);
+    for (int i = 0; i < 8; ++i) {
+      h[i] = (uint16_t)sh.in_after[e][i];
+      h[8 + i] = (uint16_t)sh.out_after[e][i];
+    }
+    hdr[e][35] = (uint8_t)((hdr[e][35] & ~EAZ_SQ_FLAG_SOLVED) | (solved ? EAZ_SQ_FLAG_SOLVED : 0));
+  }
+  uint8_t* cs = t.states + ((size_t)t.leaf[b] * t.B + b) * S;
+  for (int i = 0; i < EAZ_SQ_HDR / 8; ++i) reinterpret_cast<uint2*>(cs)[i] = reinterpret_cast<const uint2*>(hdr[e])[i];
+  for (int i = 0; i < S - EAZ_SQ_HDR; i += 8) *reinterpret_cast<uint2*>(cs + EAZ_SQ_HDR + i) = *reinterpret_cast<const uint2*>(&sh.base[e][i]);
+  t.reward[b] = reward;
+}
+
+// ------------------------------------------------------------------ expand (A.4, context.py:132-154) + backward (A.5)
+template <int G, int J>
+__global__ void __launch_bounds__(128) expand_backward_kernel(Tree t, SearchParams sp, EnvDesc env) {
+  EAZ_GROUP_PROLOGUE();
+  float lg[J];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    lg[j] = (in_range && valid[j]) ? t.net_logits[(size_t)b * t.A + gl + G * j] : 0.0f;
+    if (valid[j]) m = fmaxf(m, lg[j]);
+  }
+  m = group_max<G>(m);  // context.py:135
+  if (!in_range) return;
+  const int parent = t.parent[b], action = t.action[b], leaf = t.leaf[b];
+  const size_t lslot = (size_t)leaf * t.B + b;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (valid[j]) t.prior[lslot * t.A + gl + G * j] = __fsub_rn(lg[j], m);  // legal_action_mask is all True (:137)
+  if (gl != 0) return;
+
+  int term;
+  if (env.kind == EAZ_ENV_DEEPSEA) term = EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot]);
+  else term = t.states[lslot * t.S + 35] & EAZ_SQ_FLAG_TERM;
+  const float value = term ? 0.0f : t.net_value[b];  // :140
+  const float var = term ? 0.0f : t.net_ube[b];      // :141
+  float disc = sp.discount;
+  if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
+  if (term) disc = 0.0f;                              // :144
+  const float reward = t.reward[b];                   // :139
+  // update_tree_node
+  t.raw_values[lslot] = value;
+  t.node_values[lslot] = value;
+  t.raw_var[lslot] = var;
+  t.node_var[lslot] = var;
+  t.node_visits[lslot] = t.node_visits[lslot] + 1;
+  t.link[lslot] = make_int2(parent, action);
+  const size_t pe0 = ((size_t)parent * t.B + b) * t.A + action;
+  t.children_index[pe0] = leaf;
+  t.rewards[pe0] = reward;
+  t.discounts[pe0] = disc;
+
+  // backward
+  const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
+  float leaf_value = value, leaf_var = std_backup ? __fsqrt_rn(var) : var;
+  float cur_val = value, cur_var = var;
+  int par = parent, act = action;
+  float r = reward, d = disc;
+  while (true) {
+    const size_t pslot = (size_t)par * t.B + b;
+    const size_t pe = pslot * t.A + act;
+    const int2 up = t.link[pslot];  // prefetch the next hop
+    const float count = (float)t.node_visits[pslot];
+    leaf_value = __fadd_rn(r, __fmul_rn(d, leaf_value));
+    const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(t.node_values[pslot], count), leaf_value), __fadd_rn(count, 1.0f));
+    float pvar;
+    if (std_backup) {
+      leaf_var = __fadd_rn(0.0f, __fmul_rn(fabsf(d), leaf_var));
+      const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(t.node_var[pslot]), count), leaf_var), __fadd_rn(count, 1.0f));
+      pvar = __fmul_rn(ps, ps);
+    } else {
+      leaf_var = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(d, d), leaf_var));
+      pvar = __fdiv_rn(__fadd_rn(__fmul_rn(t.node_var[pslot], count), leaf_var), __fadd_rn(count, 1.0f));
+    }
+    t.node_values[pslot] = pv;
+    t.node_var[pslot] = pvar;
+    t.node_visits[pslot] = (int)count + 1;
+    t.values[pe] = cur_val;
+    t.values_var[pe] = cur_var;
+    t.children_visits[pe] = t.children_visits[pe] + 1;
+    cur_val = pv;
+    cur_var = pvar;
+    if (par == 0) break;
+    act = up.y;
+    par = up.x;
+    const size_t ne = ((size_t)par * t.B + b) * t.A + act;
+    r = t.rewards[ne];
+    d = t.discounts[ne];
+  }
+}
+
+// ------------------------------------------------------------------ policy output (A.1 step 4) + epistemic_summary (A.7)
+struct SummaryOut {
+  int32_t* action;
+  float *action_weights, *value, *value_std, *visit_counts, *visit_probs, *qvalues, *qvalues_var;
+};
+
+template <int G, int J>
+__global__ void __launch_bounds__(128) finalize_kernel(Tree t, SearchParams sp, const float* __restrict__ beta_in,
+                                                        const uint8_t* __restrict__ invalid, SummaryOut out) {
+  EAZ_GROUP_PROLOGUE();
+  const float beta = (in_range && beta_in) ? beta_in[b] : 0.0f;
+  float gum[J];
+  bool inval[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int a = gl + G * j;
+    gum[j] = (in_range && valid[j]) ? t.gumbel[(size_t)b * t.A + a] : 0.0f;
+    inval[j] = (in_range && valid[j] && invalid) ? (invalid[(size_t)b * t.A + a] != 0) : false;
+  }
+  Edge<G, J> e;
+  load_edges<G, J>(t, (size_t)b, gl, in_range, e);
+  const float raw = in_range ? t.raw_values[b] : 0.0f, raw_var = in_range ? t.raw_var[b] : 0.0f;
+  float cq[J];
+  int sumN, maxN;
+  qtransform<G, J>(sp, e, valid, raw, raw_var, beta, (sp.flags & EAZ_FLAG_BETA_FINAL) != 0, cq, sumN, maxN);
+  const int act = root_argmax<G, J>(e, valid, gum, inval, cq, maxN, gl);  // considered_visit = max visit count
+  // action_weights = softmax(mask_invalid(root_logits + completed_q))
+  float x[J], p[J];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    x[j] = __fadd_rn(e.pl[j], cq[j]);
+    if (valid[j]) m = fmaxf(m, x[j]);
+  }
+  m = group_max<G>(m);
+#pragma unroll
+  for (int j = 0; j < J; ++j) x[j] = inval[j] ? EAZ_F32_MIN : __fsub_rn(x[j], m);
+  group_softmax<G, J>(x, valid, p);
+  if (!in_range) return;
+  if (gl == 0) {
+    out.action[b] = act;
+    if (out.value) out.value[b] = t.node_values[b];
+    if (out.value_std) out.value_std[b] = __fsqrt_rn(t.node_var[b]);
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (!valid[j]) continue;
+    const size_t o = (size_t)b * t.A + gl + G * j;
+    const float vc = (float)e.vis[j];
+    if (out.action_weights) out.action_weights[o] = p[j];
+    if (out.visit_counts) out.visit_counts[o] = vc;
+    if (out.visit_probs) out.visit_probs[o] = sumN > 0 ? __fdiv_rn(vc, eaz_max((float)sumN, 1.0f)) : __fdiv_rn(1.0f, (float)t.A);
+    if (out.qvalues) out.qvalues[o] = __fadd_rn(e.rew[j], __fmul_rn(e.dis[j], e.val[j]));
+    if (out.qvalues_var) out.qvalues_var[o] = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(e.dis[j], e.dis[j]), e.vvar[j]));
+  }
+}
+
+// ------------------------------------------------------------------ optional tree export: node-major -> emctx [B,N,...]
+struct TreeOut {
+  int32_t *node_visits, *parents, *action_from_parent, *children_index, *children_visits;
+  float *raw_values, *node_values, *raw_var, *node_var;
+  float *prior, *rewards, *discounts, *values, *rewards_var, *values_var;
+  uint8_t* embeddings;
+};
+
+__global__ void export_tree_kernel(Tree t, TreeOut o) {
+  const size_t nb = (size_t)t.N * t.B, nba = nb * t.A;
+  const size_t stride = (size_t)gridDim.x * blockDim.x, tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (size_t i = tid0; i < nb; i += stride) {  // i indexes the OUTPUT [B][N]
+    const size_t b = i / t.N, n = i % t.N, s = n * t.B + b;
+    if (o.node_visits) o.node_visits[i] = t.node_visits[s];
+    if (o.raw_values) o.raw_values[i] = t.raw_values[s];
+    if (o.node_values) o.node_values[i] = t.node_values[s];
+    if (o.raw_var) o.raw_var[i] = t.raw_var[s];
+    if (o.node_var) o.node_var[i] = t.node_var[s];
+    const int2 l = t.link[s];
+    if (o.parents) o.parents[i] = l.x;
+    if (o.action_from_parent) o.action_from_parent[i] = l.y;
+    if (o.embeddings) {
+      const bool live = t.node_visits[s] > 0;
+      for (int k = 0; k < t.S; ++k) o.embeddings[i * t.S + k] = live ? t.states[s * t.S + k] : 0;
+    }
+  }
+  for (size_t i = tid0; i < nba; i += stride) {  // output [B][N][A]
+    const size_t a = i % t.A, bn = i / t.A, b = bn / t.N, n = bn % t.N, s = (n * t.B + b) * t.A + a;
+    if (o.children_index) o.children_index[i] = t.children_index[s];
+    if (o.children_visits) o.children_visits[i] = t.children_visits[s];
+    if (o.prior) o.prior[i] = t.prior[s];
+    if (o.rewards) o.rewards[i] = t.rewards[s];
+    if (o.discounts) o.discounts[i] = t.discounts[s];
+    if (o.values) o.values[i] = t.values[s];
+    if (o.rewards_var) o.rewards_var[i] = 0.0f;  // context.py:149
+    if (o.values_var) o.values_var[i] = t.values_var[s];
+  }
+}
+
+// ------------------------------------------------------------------ host side
+template <int G, int J>
+static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env, const NetDesc& net, const eaz_search_inputs* in,
+                      const SummaryOut& so, int mlp_mode, int exploration, cudaStream_t st) {
+  const int envs_per_block = 4 * (32 / G);
+  const int grid = ceil_div(t.B, envs_per_block);
+  root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->prior_logits, in->value, in->value_epistemic_variance, in->gumbel, in->invalid_actions);
+  EAZ_CHECK_LAUNCH("root_init_kernel");
+  const int lhead = exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;  // context.py:132
+  const int mask = (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead);
+  MlpSource src{nullptr, t.states, t.leaf, env.kind == EAZ_ENV_DEEPSEA ? t.ds_seen : nullptr};
+  MlpOutputs mo{{nullptr, nullptr}, t.net_value, t.net_ube, nullptr};
+  mo.logits[lhead - EAZ_HEAD_EXPLOIT] = t.net_logits;
+  for (int sim = 0; sim < sp.n; ++sim) {
+    select_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env, sim, in->beta, in->invalid_actions);
+    EAZ_CHECK_LAUNCH("select_kernel");
+    if (env.kind == EAZ_ENV_SUBLEQ) {
+      subleq_tree_step_kernel<<<ceil_div(t.B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, 0, st>>>(t, env);
+      EAZ_CHECK_LAUNCH("subleq_tree_step_kernel");
+    }
+    if (int rc = launch_mlp(net, env, src, t.B, mask, mo, mlp_mode, st)) return rc;
+    expand_backward_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env);
+    EAZ_CHECK_LAUNCH("expand_backward_kernel");
+  }
+  finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so);
+  EAZ_CHECK_LAUNCH("finalize_kernel");
+  return 0;
+}
+
+static int check_search(const eaz_search_config* cfg, const eaz_search_inputs* in, const eaz_search_outputs* out, EnvDesc* env, NetDesc* net) {
+  EAZ_CHECK_ARG(cfg && in && out, "search: NULL config / inputs / outputs");
+  EAZ_CHECK_ARG(cfg->batch >= 1, "batch must be >= 1");
+  EAZ_CHECK_ARG(cfg->num_simulations >= 1 && cfg->num_simulations <= 4094, "num_simulations %d outside [1,4094]", cfg->num_simulations);
+  EAZ_CHECK_ARG(cfg->max_num_considered_actions >= 1 && cfg->max_num_considered_actions <= 256, "max_num_considered_actions outside [1,256]");
+  EAZ_CHECK_ARG(cfg->max_depth >= 0, "max_depth must be >= 0 (0 = None)");
+  if (int rc = make_env_desc(in->env, env)) return rc;
+  if (int rc = make_net_desc(in->net, env, net)) return rc;
+  EAZ_CHECK_ARG(in->prior_logits && in->value && in->value_epistemic_variance && in->gumbel && in->embedding,
+                "search inputs: prior_logits / value / value_epistemic_variance / gumbel / embedding must be non-NULL");
+  EAZ_CHECK_ARG(out->action != nullptr, "search outputs: action must be non-NULL");
+  return 0;
+}
+
+}  // namespace eaz
+
+using namespace eaz;
+
+extern "C" {
+
+int eaz_env_compact(const eaz_env* env, const eaz_state* state, uint8_t* out, int32_t B, void* stream) {
+  EnvDesc d;
+  if (int rc = make_env_desc(env, &d)) return rc;
+  EAZ_CHECK_ARG(state && out && B >= 0, "eaz_env_compact: bad arguments");
+  if (B == 0) return 0;
+  pack_states_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(d, soa_of(state), out, B);
+  EAZ_CHECK_LAUNCH("pack_states_kernel");
+  return 0;
+}
+
+int eaz_mlp_forward_states(const eaz_fc_params* net, const eaz_env* env, const eaz_state* state, int32_t B, float* exploit_logits,
+                           float* explore_logits, float* value, float* ube, float* novelty, void* workspace, size_t workspace_bytes,
+                           void* stream) {
+  EnvDesc ed;
+  if (int rc = make_env_desc(env, &ed)) return rc;
+  NetDesc nd;
+  if (int rc = make_net_desc(net, &ed, &nd)) return rc;
+  EAZ_CHECK_ARG(state && B >= 0, "eaz_mlp_forward_states: bad arguments");
+  if (!workspace || workspace_bytes < (size_t)B * ed.compact_bytes || ((uintptr_t)workspace & 15)) {
+    set_error("eaz_mlp_forward_states: workspace must be >= B*compact_bytes = %zu bytes, 16-byte aligned", (size_t)B * ed.compact_bytes);
+    return EAZ_ERR_WORKSPACE;
+  }
+  if (B == 0) return 0;
+  if (int rc = eaz_env_compact(env, state, (uint8_t*)workspace, B, stream)) return rc;
+  MlpSource src{nullptr, (const uint8_t*)workspace, nullptr, nullptr};
+  MlpOutputs out{{exploit_logits, explore_logits}, value, ube, novelty};
+  int mask = 0;
+  if (value) mask |= 1 << EAZ_HEAD_VALUE;
+  if (ube || novelty) mask |= 1 << EAZ_HEAD_UBE;
+  if (exploit_logits) mask |= 1 << EAZ_HEAD_EXPLOIT;
+  if (explore_logits) mask |= 1 << EAZ_HEAD_EXPLORE;
+  return launch_mlp(nd, ed, src, B, mask, out, EAZ_MLP_EXACT, (cudaStream_t)stream);
+}
+
+size_t eaz_search_workspace_bytes(const eaz_search_config* cfg, const eaz_env* env) {
+  EnvDesc d;
+  if (!cfg || make_env_desc(env, &d) || cfg->batch < 1 || cfg->num_simulations < 1) return 0;
+  Layout L;
+  make_layout(cfg->batch, cfg->num_simulations + 1, d.num_actions, d.compact_bytes,
+              (cfg->max_num_considered_actions + 1) * cfg->num_simulations, d.obs_dim, &L);
+  return L.total;
+}
+
+int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env) {
+  EnvDesc d;
+  if (!cfg || make_env_desc(env, &d)) return -1;
+  const int per_sim = 2 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
+  // 2 memsets + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
+  return 2 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + per_sim * cfg->num_simulations + 1;
+}
+
+int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  EnvDesc env;
+  NetDesc net;
+  if (int rc = check_search(cfg, in, out, &env, &net)) return rc;
+  const int B = cfg->batch, n = cfg->num_simulations, N = n + 1, A = env.num_actions, S = env.compact_bytes;
+  Layout L;
+  make_layout(B, N, A, S, (cfg->max_num_considered_actions + 1) * n, env.obs_dim, &L);
+  if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
+    set_error("search workspace must be >= %zu bytes and 256-byte aligned (got %zu)", L.total, workspace_bytes);
+    return EAZ_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  Tree t = make_tree(workspace, L, B, N, A, S);
+  SearchParams sp{n, cfg->max_depth > 0 ? cfg->max_depth : n, cfg->max_num_considered_actions, cfg->gumbel_scale, cfg->discount,
+                  cfg->value_scale, cfg->maxvisit_init, cfg->epsilon, cfg->two_players_game, cfg->rescale_values, cfg->use_mixed_value,
+                  cfg->flags};
+  cudaError_t e = cudaMemsetAsync((uint8_t*)workspace + L.zero_begin, 0, L.zero_end - L.zero_begin, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync((uint8_t*)workspace + L.ones_begin, 0xFF, L.ones_end - L.ones_begin, st);
+  if (e != cudaSuccess) return cuda_fail(e, "search memset");
+  seq_halving_table_kernel<<<ceil_div(cfg->max_num_considered_actions + 1, 32), 32, 0, st>>>(cfg->max_num_considered_actions, n, t.table);
+  EAZ_CHECK_LAUNCH("seq_halving_table_kernel");
+  if (int rc = eaz_env_compact(in->env, in->embedding, t.states, B, stream)) return rc;  // node 0 = roots
+  if (env.kind == EAZ_ENV_DEEPSEA)
+    if (int rc = launch_deepsea_seen_table(net, env, t.ds_seen, st)) return rc;
+
+  SummaryOut so{out->action, out->action_weights, out->value, out->value_epistemic_std, out->visit_counts, out->visit_probs,
+                out->qvalues, out->qvalues_epistemic_variance};
+  int rc;
+#define EAZ_RUN(G, J) rc = run_search<G, J>(t, sp, env, net, in, so, cfg->mlp_mode, cfg->exploration, st)
+  if (A <= 2) EAZ_RUN(2, 1);
+  else if (A <= 4) EAZ_RUN(4, 1);
+  else if (A <= 8) EAZ_RUN(8, 1);
+  else if (A <= 16) EAZ_RUN(16, 1);
+  else if (A <= 32) EAZ_RUN(32, 1);
+  else if (A <= 64) EAZ_RUN(32, 2);
+  else if (A <= 128) EAZ_RUN(32, 4);
+  else EAZ_RUN(32, 8);
+#undef EAZ_RUN
+  if (rc) return rc;
+
+  const bool want_tree = out->node_visits || out->raw_values || out->node_values || out->raw_values_epistemic_variance ||
+                         out->node_values_epistemic_variance || out->parents || out->action_from_parent || out->children_index ||
+                         out->children_prior_logits || out->children_visits || out->children_rewards || out->children_discounts ||
+                         out->children_values || out->children_rewards_epistemic_variance || out->children_values_epistemic_variance ||
+                         out->embeddings;
+  if (want_tree) {
+    TreeOut to{out->node_visits, out->parents, out->action_from_parent, out->children_index, out->children_visits,
+               out->raw_values, out->node_values, out->raw_values_epistemic_variance, out->node_values_epistemic_variance,
+               out->children_prior_logits, out->children_rewards, out->children_discounts, out->children_values,
+               out->children_rewards_epistemic_variance, out->children_values_epistemic_variance, out->embeddings};
+    export_tree_kernel<<<148 * 8, 256, 0, st>>>(t, to);
+    EAZ_CHECK_LAUNCH("export_tree_kernel");
+  }
+  return 0;
+}
+
+}  // extern "C"

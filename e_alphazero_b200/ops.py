@@ -1,0 +1,393 @@
+"""Thin torch-tensor harness over the C ABI (include/eaz_b200.h).
+
+Tensors supply device pointers and the current CUDA stream; all arithmetic runs
+in libeaz_b200.so.  States are dicts of device tensors named like the pgx.State
+leaves (``step_count, rewards, terminated, truncated, col | memory, task, solved,
+input_after, output_after`` and optionally ``observation``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+from . import _abi
+from ._lib import EazError, check, load, require_cuda
+
+_TORCH_DT = None
+
+
+def _dt():
+    global _TORCH_DT
+    if _TORCH_DT is None:
+        import torch
+
+        _TORCH_DT = {"i32": torch.int32, "f32": torch.float32, "u8": torch.uint8}
+    return _TORCH_DT
+
+
+def _ptr(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise EazError("expected a CUDA tensor (the C ABI takes device pointers)")
+    if not t.is_contiguous():
+        raise EazError("expected a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise EazError(f"expected dtype {dtype}, got {t.dtype}")
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    import torch
+
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# --------------------------------------------------------------------------- env
+@dataclass
+class EnvSpec:
+    """Static attributes of the pgx.Env instance (deep_sea.py:37-52, subleq.py:599-621)."""
+
+    kind: int
+    size: int = 0
+    action_map: object = None  # device uint8 [N,N] or None
+    word_size: int = 0
+    binary_encoding: int = 1
+    reward_fn: int = _abi.SUBLEQ_REWARD_SOLVED
+
+    def struct(self) -> _abi.EazEnv:
+        return _abi.EazEnv(self.kind, self.size, _ptr(self.action_map), self.word_size, self.binary_encoding, self.reward_fn)
+
+    def _q(self, fn, *a):
+        s = self.struct()
+        v = getattr(load(), fn)(C.byref(s), *a)
+        if v < 0:
+            check(-1, fn)
+        return v
+
+    @property
+    def num_actions(self):
+        return self._q("eaz_env_num_actions")
+
+    @property
+    def obs_dim(self):
+        return self._q("eaz_env_obs_dim")
+
+    @property
+    def obs_cols(self):
+        return self._q("eaz_env_obs_cols")
+
+    @property
+    def compact_bytes(self):
+        return self._q("eaz_env_compact_bytes")
+
+    def hash_dim(self, hash_io):
+        return self._q("eaz_env_hash_dim", int(hash_io))
+
+    @property
+    def obs_shape(self):
+        if self.kind == _abi.ENV_DEEPSEA:
+            return (self.size, self.size)
+        return (self.word_size + 32, self.obs_cols)
+
+
+def deepsea_spec(size, action_map=None, device="cuda") -> EnvSpec:
+    torch = require_cuda()
+    am = None
+    if action_map is not None:
+        am = torch.as_tensor(action_map).to(device=device, dtype=torch.uint8).reshape(size, size).contiguous()
+    return EnvSpec(_abi.ENV_DEEPSEA, size=size, action_map=am)
+
+
+def subleq_spec(word_size, binary_encoding=True, reward_fn=_abi.SUBLEQ_REWARD_SOLVED) -> EnvSpec:
+    return EnvSpec(_abi.ENV_SUBLEQ, word_size=word_size, binary_encoding=int(binary_encoding), reward_fn=reward_fn)
+
+
+_STATE_SHAPES = {
+    "step_count": ("i32", lambda e: ()),
+    "rewards": ("f32", lambda e: (1,)),
+    "terminated": ("u8", lambda e: ()),
+    "truncated": ("u8", lambda e: ()),
+    "col": ("i32", lambda e: ()),
+    "memory": ("i32", lambda e: (e.word_size,)),
+    "task": ("i32", lambda e: ()),
+    "solved": ("u8", lambda e: ()),
+    "input_after": ("i32", lambda e: (8,)),
+    "output_after": ("i32", lambda e: (8,)),
+}
+DEEPSEA_FIELDS = ["step_count", "rewards", "terminated", "truncated", "col"]
+SUBLEQ_FIELDS = ["step_count", "rewards", "terminated", "truncated", "memory", "task", "solved", "input_after", "output_after"]
+
+
+def state_fields(env: EnvSpec):
+    return DEEPSEA_FIELDS if env.kind == _abi.ENV_DEEPSEA else SUBLEQ_FIELDS
+
+
+def alloc_state(env: EnvSpec, B: int, with_obs=False, device="cuda") -> dict:
+    torch = require_cuda()
+    st = {}
+    for name in state_fields(env):
+        dt, shp = _STATE_SHAPES[name]
+        st[name] = torch.zeros((B,) + shp(env), dtype=_dt()[dt], device=device)
+    if with_obs:
+        st["observation"] = torch.zeros((B, env.obs_dim), dtype=torch.uint8, device=device)
+    return st
+
+
+def state_to_device(env: EnvSpec, st: dict, device="cuda") -> dict:
+    """Upload a host (numpy) state dict."""
+    torch = require_cuda()
+    out = {}
+    for name in state_fields(env):
+        dt, _ = _STATE_SHAPES[name]
+        out[name] = torch.as_tensor(st[name]).to(device=device, dtype=_dt()[dt]).contiguous()
+    return out
+
+
+def state_struct(env: EnvSpec, st: dict) -> _abi.EazState:
+    s = _abi.EazState()
+    for name in state_fields(env):
+        dt, _ = _STATE_SHAPES[name]
+        setattr(s, name, _ptr(st[name], _dt()[dt]))
+    if st.get("observation") is not None:
+        s.observation = _ptr(st["observation"], _dt()["u8"])
+    return s
+
+
+def _batch(st):
+    return st["step_count"].shape[0]
+
+
+def _tasks(task_ids, B, device):
+    torch = require_cuda()
+    if task_ids is None:
+        return None
+    t = torch.as_tensor(task_ids).to(device=device, dtype=torch.int32).contiguous()
+    if t.numel() != B:
+        raise EazError("task_ids must have one entry per env")
+    return t
+
+
+def env_init(env: EnvSpec, B: int, task_ids=None, with_obs=False, device="cuda") -> dict:
+    """vmap(env.init): deep_sea.py:54-57 / subleq.py:623-646 (task ids pre-drawn)."""
+    st = alloc_state(env, B, with_obs, device)
+    t = _tasks(task_ids, B, device)
+    e, s = env.struct(), state_struct(env, st)
+    check(load().eaz_env_init(C.byref(e), _ptr(t), C.byref(s), B, _stream()), "eaz_env_init")
+    return st
+
+
+def env_step_(env: EnvSpec, st: dict, action, auto_reset=False, task_ids=None) -> dict:
+    """In-place vmap(env.step) (or the reference's auto_reset wrapper, selfplay.py:26-75)."""
+    torch = require_cuda()
+    B = _batch(st)
+    a = torch.as_tensor(action).to(device=st["step_count"].device, dtype=torch.int32).contiguous()
+    t = _tasks(task_ids, B, st["step_count"].device)
+    e, s = env.struct(), state_struct(env, st)
+    check(load().eaz_env_step(C.byref(e), C.byref(s), _ptr(a), int(auto_reset), _ptr(t), B, _stream()), "eaz_env_step")
+    return st
+
+
+def env_step(env: EnvSpec, st: dict, action, auto_reset=False, task_ids=None) -> dict:
+    return env_step_(env, {k: v.clone() for k, v in st.items()}, action, auto_reset, task_ids)
+
+
+def env_observe(env: EnvSpec, st: dict):
+    torch = require_cuda()
+    B = _batch(st)
+    obs = torch.empty((B, env.obs_dim), dtype=torch.uint8, device=st["step_count"].device)
+    e, s = env.struct(), state_struct(env, st)
+    check(load().eaz_env_observe(C.byref(e), C.byref(s), _ptr(obs), B, _stream()), "eaz_env_observe")
+    return obs
+
+
+def env_compact(env: EnvSpec, st: dict):
+    torch = require_cuda()
+    B = _batch(st)
+    out = torch.empty((B, env.compact_bytes), dtype=torch.uint8, device=st["step_count"].device)
+    e, s = env.struct(), state_struct(env, st)
+    check(load().eaz_env_compact(C.byref(e), C.byref(s), _ptr(out), B, _stream()), "eaz_env_compact")
+    return out
+
+
+def subleq_test_cases(task: int, ws: int):
+    import numpy as np
+
+    i, o = np.zeros((3, 8), np.int32), np.zeros((3, 8), np.int32)
+    check(load().eaz_subleq_test_cases(int(task), int(ws), i.ctypes.data_as(C.c_void_p), o.ctypes.data_as(C.c_void_p)), "eaz_subleq_test_cases")
+    return i, o
+
+
+# --------------------------------------------------------------------------- hash
+def _rows_f32(x):
+    torch = require_cuda()
+    if x.dtype != torch.float32:
+        x = x.to(torch.float32)
+    return x.reshape(x.shape[0], -1).contiguous()
+
+
+def xxhash_indices(x, bits=24):
+    """XXHash.get_indices (hashes.py:162-229)."""
+    torch = require_cuda()
+    x = _rows_f32(x)
+    out = torch.empty(x.shape[0], dtype=torch.int32, device=x.device)  # uint32 payload
+    check(load().eaz_xxhash_indices(_ptr(x), x.shape[0], x.shape[1], int(bits), _ptr(out), _stream()), "eaz_xxhash_indices")
+    return out
+
+
+def hash_lookup(x, binary_set, bits=24):
+    """BaseHash.__call__ (hashes.py:29-38)."""
+    torch = require_cuda()
+    x = _rows_f32(x)
+    out = torch.empty(x.shape[0], dtype=torch.uint8, device=x.device)
+    check(load().eaz_hash_lookup(_ptr(x), x.shape[0], x.shape[1], int(bits), _ptr(binary_set, torch.uint8), _ptr(out), _stream()), "eaz_hash_lookup")
+    return out
+
+
+def hash_update_(x, binary_set, bits=24):
+    """BaseHash.update (hashes.py:45-50), in place."""
+    torch = require_cuda()
+    x = _rows_f32(x)
+    check(load().eaz_hash_update(_ptr(x), x.shape[0], x.shape[1], int(bits), _ptr(binary_set, torch.uint8), _stream()), "eaz_hash_update")
+    return binary_set
+
+
+# --------------------------------------------------------------------------- network
+@dataclass
+class FcParams:
+    """Device copy of the haiku pytree of EpistemicFullyConnectedAZNet: w[h][l] is [in,out], b[h][l] is [out]
+    (heads: value, ube, exploit, explore = fc_az_net/linear{,_1..11} in call order) + the hash state."""
+
+    in_dim: int
+    hidden: int
+    num_actions: int
+    w: list
+    b: list
+    binary_set: object
+    hash_bits: int = 24
+    hash_io: int = 0
+    word_size: int = 0
+    max_u: float = 1.0
+    novelty_scale: float = 1.0
+
+    @staticmethod
+    def from_numpy(w, b, binary_set, num_actions, hash_bits=24, hash_io=0, word_size=0, max_u=1.0, novelty_scale=1.0, device="cuda"):
+        torch = require_cuda()
+        tw = [[torch.as_tensor(w[h][l]).to(device=device, dtype=torch.float32).contiguous() for l in range(3)] for h in range(4)]
+        tb = [[torch.as_tensor(b[h][l]).to(device=device, dtype=torch.float32).contiguous() for l in range(3)] for h in range(4)]
+        bs = torch.as_tensor(binary_set).to(device=device, dtype=torch.uint8).contiguous()
+        return FcParams(tw[0][0].shape[0], tw[0][0].shape[1], num_actions, tw, tb, bs, hash_bits, hash_io, word_size, max_u, novelty_scale)
+
+    @staticmethod
+    def from_haiku(params: dict, state: dict, num_actions, prefix="fc_az_net", **kw):
+        """params: {'fc_az_net/linear_3': {'w','b'}, ...}; state: {'fc_az_net/xxhash32': {'binary_set'}}."""
+        names = [f"{prefix}/linear" + ("" if i == 0 else f"_{i}") for i in range(12)]
+        w = [[params[names[h * 3 + l]]["w"] for l in range(3)] for h in range(4)]
+        b = [[params[names[h * 3 + l]]["b"] for l in range(3)] for h in range(4)]
+        return FcParams.from_numpy(w, b, state[f"{prefix}/xxhash32"]["binary_set"], num_actions, **kw)
+
+    def struct(self) -> _abi.EazFcParams:
+        import torch
+
+        s = _abi.EazFcParams()
+        s.in_dim, s.hidden, s.num_actions = self.in_dim, self.hidden, self.num_actions
+        for h in range(4):
+            for l in range(3):
+                s.w[h][l] = _ptr(self.w[h][l], torch.float32).value
+                s.b[h][l] = _ptr(self.b[h][l], torch.float32).value
+        s.binary_set = _ptr(self.binary_set, torch.uint8)
+        s.hash_bits, s.hash_io, s.word_size = self.hash_bits, self.hash_io, self.word_size
+        s.max_u, s.novelty_scale = self.max_u, self.novelty_scale
+        return s
+
+
+def _mlp_out(B, A, device):
+    torch = require_cuda()
+    f = lambda *s: torch.empty(s, dtype=torch.float32, device=device)
+    return dict(exploit_logits=f(B, A), explore_logits=f(B, A), value=f(B), ube=f(B), novelty=f(B))
+
+
+def mlp_forward(net: FcParams, observation) -> dict:
+    """forward.apply(params, state, observation, is_training=False) on a bool observation batch."""
+    torch = require_cuda()
+    obs = observation.to(torch.uint8).reshape(observation.shape[0], -1).contiguous()
+    B = obs.shape[0]
+    out = _mlp_out(B, net.num_actions, obs.device)
+    s = net.struct()
+    check(load().eaz_mlp_forward(C.byref(s), _ptr(obs), B, _ptr(out["exploit_logits"]), _ptr(out["explore_logits"]), _ptr(out["value"]),
+                                 _ptr(out["ube"]), _ptr(out["novelty"]), _stream()), "eaz_mlp_forward")
+    return out
+
+
+def mlp_forward_states(net: FcParams, env: EnvSpec, st: dict) -> dict:
+    """Same network, observation derived on the fly from env states."""
+    torch = require_cuda()
+    B = _batch(st)
+    dev = st["step_count"].device
+    out = _mlp_out(B, net.num_actions, dev)
+    ws = torch.empty(max(B * env.compact_bytes, 16), dtype=torch.uint8, device=dev)
+    s, e, ss = net.struct(), env.struct(), state_struct(env, st)
+    check(load().eaz_mlp_forward_states(C.byref(s), C.byref(e), C.byref(ss), B, _ptr(out["exploit_logits"]), _ptr(out["explore_logits"]),
+                                        _ptr(out["value"]), _ptr(out["ube"]), _ptr(out["novelty"]), _ptr(ws), C.c_size_t(ws.numel()),
+                                        _stream()), "eaz_mlp_forward_states")
+    return out
+
+
+# --------------------------------------------------------------------------- search
+def alloc_search_outputs(B, N, A, S, want_tree, device) -> dict:
+    torch = require_cuda()
+    shp = {"B": (B,), "BA": (B, A), "BN": (B, N), "BNA": (B, N, A), "BNS": (B, N, S)}
+    fields = _abi.SEARCH_OUTPUT_FIELDS if want_tree else _abi.SUMMARY_FIELDS
+    return {name: torch.empty(shp[kind], dtype=_dt()[dt], device=device) for name, dt, kind in fields}
+
+
+@dataclass
+class SearchPlan:
+    """Pre-allocated workspace + outputs for repeated searches of one shape (no allocation in the hot loop)."""
+
+    cfg: _abi.EazSearchConfig
+    env: EnvSpec
+    net: FcParams
+    want_tree: bool = False
+    device: str = "cuda"
+    workspace: object = None
+    out: dict = field(default_factory=dict)
+    num_launches: int = 0
+
+    def __post_init__(self):
+        torch = require_cuda()
+        e = self.env.struct()
+        nbytes = load().eaz_search_workspace_bytes(C.byref(self.cfg), C.byref(e))
+        if nbytes == 0:
+            raise EazError("eaz_search_workspace_bytes rejected the configuration")
+        self.workspace = torch.empty(nbytes + 256, dtype=torch.uint8, device=self.device)
+        off = (-self.workspace.data_ptr()) % 256
+        self._ws_ptr = C.c_void_p(self.workspace.data_ptr() + off)
+        self._ws_bytes = C.c_size_t(nbytes)
+        B, N, A = self.cfg.batch, self.cfg.num_simulations + 1, self.env.num_actions
+        self.out = alloc_search_outputs(B, N, A, self.env.compact_bytes, self.want_tree, self.device)
+        self.num_launches = load().eaz_search_num_launches(C.byref(self.cfg), C.byref(e))
+
+    def run(self, root: dict) -> dict:
+        """root: prior_logits [B,A], value [B], value_epistemic_variance [B], beta [B], embedding (state dict),
+        gumbel [B,A] pre-drawn standard Gumbel noise, optional invalid_actions [B,A] (bool/uint8)."""
+        import torch
+
+        f32, u8 = torch.float32, torch.uint8
+        inv = root.get("invalid_actions")
+        if inv is not None and inv.dtype != u8:
+            inv = inv.to(u8)
+        e, n, s = self.env.struct(), self.net.struct(), state_struct(self.env, root["embedding"])
+        inp = _abi.EazSearchInputs(_ptr(root["prior_logits"], f32), _ptr(root["value"], f32), _ptr(root["value_epistemic_variance"], f32),
+                                   _ptr(root["beta"], f32), C.pointer(s), _ptr(inv), _ptr(root["gumbel"], f32), C.pointer(e), C.pointer(n))
+        o = _abi.EazSearchOutputs()
+        for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
+            setattr(o, name, _ptr(self.out.get(name)))
+        check(load().eaz_search_gumbel(C.byref(self.cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream()), "eaz_search_gumbel")
+        return self.out
+
+
+def search(cfg: _abi.EazSearchConfig, env: EnvSpec, net: FcParams, root: dict, want_tree=False) -> dict:
+    cfg.batch = root["prior_logits"].shape[0]
+    plan = SearchPlan(cfg, env, net, want_tree, device=str(root["prior_logits"].device))
+    return plan.run(root)

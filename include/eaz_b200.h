@@ -147,6 +147,7 @@ typedef struct eaz_fc_params {
   const uint8_t* binary_set; /* hash state */
   int32_t hash_bits;         /* bits_per_hash (24) */
   int32_t hash_io;           /* fully_connected.py:85: hash rows word_size: only */
+  int32_t word_size;         /* fully_connected.py:26,86: first row of the hashed IO block (0 for DeepSea) */
   float max_u;               /* max_ube (1.0; context.py:68-75 never forwards config.max_ube) */
   float novelty_scale;       /* max_epistemic_variance_reward (1.0) */
 } eaz_fc_params;
@@ -163,7 +164,11 @@ int eaz_mlp_forward(const eaz_fc_params* net, const uint8_t* observation, int32_
  * observation): what the fused recurrent_fn uses. */
 int eaz_mlp_forward_states(const eaz_fc_params* net, const eaz_env* env, const eaz_state* state, int32_t B,
                            float* exploit_logits, float* explore_logits, float* value, float* ube,
-                           float* novelty, void* stream);
+                           float* novelty, void* workspace, size_t workspace_bytes, void* stream);
+/* workspace for the call above: B * eaz_env_compact_bytes(env), 16-byte aligned */
+
+/* Pack pgx.State leaves into the compact in-tree encoding, out: uint8 [B, eaz_env_compact_bytes]. */
+int eaz_env_compact(const eaz_env* env, const eaz_state* state, uint8_t* out, int32_t B, void* stream);
 
 /* ------------------------------------------------------------------------ */
 /* emctx.epistemic_gumbel_muzero_policy (selfplay.py:107-117,                  */

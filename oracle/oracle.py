@@ -240,12 +240,13 @@ class FcNet:
     binary_set: np.ndarray
     hash_bits: int = 24
     hash_io: int = 0
+    word_size: int = 0
     max_u: float = 1.0
     novelty_scale: float = 1.0
     _keep: list = field(default_factory=list)
 
     @staticmethod
-    def random(in_dim, num_actions, hidden=256, seed=0, hash_bits=24, hash_io=0, bias_scale=0.05):
+    def random(in_dim, num_actions, hidden=256, seed=0, hash_bits=24, hash_io=0, bias_scale=0.05, word_size=0):
         """haiku default init (trunc-normal, std 1/sqrt(fan_in)); biases get a small
         non-zero value so that the parity tests exercise them."""
         rng = np.random.default_rng(seed)
@@ -260,7 +261,7 @@ class FcNet:
                 bs.append(np.ascontiguousarray(rng.standard_normal(o) * bias_scale, np.float32))
             w.append(ws)
             b.append(bs)
-        return FcNet(in_dim, hidden, num_actions, w, b, np.zeros(1 << (hash_bits - 3), np.uint8), hash_bits, hash_io)
+        return FcNet(in_dim, hidden, num_actions, w, b, np.zeros(1 << (hash_bits - 3), np.uint8), hash_bits, hash_io, word_size)
 
     def struct(self) -> _abi.EazFcParams:
         s = _abi.EazFcParams()
@@ -270,7 +271,7 @@ class FcNet:
                 s.w[h][l] = _ptr(self.w[h][l])
                 s.b[h][l] = _ptr(self.b[h][l])
         s.binary_set = _ptr(self.binary_set)
-        s.hash_bits, s.hash_io = self.hash_bits, self.hash_io
+        s.hash_bits, s.hash_io, s.word_size = self.hash_bits, self.hash_io, self.word_size
         s.max_u, s.novelty_scale = self.max_u, self.novelty_scale
         return s
 

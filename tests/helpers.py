@@ -1,0 +1,108 @@
+"""Shared builders for the parity tests: seeded synthetic inputs on the host (numpy),
+mirrored to the device for the CUDA path."""
+import numpy as np
+
+from e_alphazero_b200 import _abi
+from oracle import oracle as O
+
+
+def make_env(kind, seed=0, **kw):
+    rng = np.random.default_rng(seed)
+    if kind == "deepsea":
+        N = kw.get("size", 10)
+        return O.Env.deepsea(N, (rng.random((N, N)) < 0.5).astype(np.uint8))
+    return O.Env.subleq(kw.get("word_size", 16), kw.get("binary", True), kw.get("reward_fn", 0))
+
+
+def make_net(env, seed=0, hash_io=None, fill=0.0):
+    if hash_io is None:
+        hash_io = int(env.kind == _abi.ENV_SUBLEQ)
+    net = O.FcNet.random(env.obs_dim, env.num_actions, seed=seed, hash_io=hash_io, word_size=env.word_size)
+    if fill > 0:
+        rng = np.random.default_rng(seed + 1)
+        net.binary_set[:] = (rng.random(net.binary_set.size) < fill) * rng.integers(1, 256, net.binary_set.size)
+    return net
+
+
+def random_states(env, B, seed=0, max_steps=None):
+    """States reached by random play from init (exercises every depth, terminal and solved states)."""
+    rng = np.random.default_rng(seed)
+    A = env.num_actions
+    if env.kind == _abi.ENV_DEEPSEA:
+        st = O.env_init(env, B)
+        T = max_steps if max_steps is not None else env.size
+    else:
+        st = O.env_init(env, B, rng.integers(1, 4, B))
+        T = max_steps if max_steps is not None else 10
+    stop = rng.integers(0, T + 1, B)
+    for t in range(T):
+        act = rng.integers(0, A, B)
+        if env.kind == _abi.ENV_SUBLEQ:  # bias towards IN/OUT addresses so programs do something
+            ws = env.word_size
+            act = np.where(rng.random(B) < 0.5, rng.integers(ws - 4, ws, B), act)
+            if t == 0:
+                act[: B // 8] = ws - 2
+            if t == 1:
+                act[: B // 8] = ws - 3
+        nxt = O.env_step(env, st, act)
+        adv = t < stop
+        for k in st:
+            st[k] = np.where(adv.reshape((-1,) + (1,) * (st[k].ndim - 1)), nxt[k], st[k])
+    return st
+
+
+def make_root(env, net, B, seed=0, beta_max=1.0, invalid_frac=0.0, states=None):
+    rng = np.random.default_rng(seed + 7)
+    A = env.num_actions
+    st = states if states is not None else random_states(env, B, seed)
+    ev = O.mlp_forward_states(net, env, st)
+    root = dict(prior_logits=ev["exploit_logits"], value=ev["value"], value_epistemic_variance=ev["ube"],
+                beta=(beta_max * np.linspace(0, 1, B)).astype(np.float32), embedding=st,
+                gumbel=rng.gumbel(size=(B, A)).astype(np.float32))
+    if invalid_frac > 0:
+        inv = rng.random((B, A)) < invalid_frac
+        inv[:, 0] &= rng.random(B) < 0.5
+        inv[0, :] = True  # one all-invalid row: masked_argmax must return 0
+        root["invalid_actions"] = inv.astype(np.uint8)
+    return root
+
+
+def to_device(x):
+    import torch
+
+    return torch.as_tensor(np.ascontiguousarray(x)).cuda()
+
+
+def device_env(env):
+    from e_alphazero_b200 import ops
+
+    if env.kind == _abi.ENV_DEEPSEA:
+        return ops.deepsea_spec(env.size, env.action_map)
+    return ops.subleq_spec(env.word_size, env.binary_encoding, env.reward_fn)
+
+
+def device_net(net):
+    from e_alphazero_b200 import ops
+
+    return ops.FcParams.from_numpy(net.w, net.b, net.binary_set, net.num_actions, net.hash_bits, net.hash_io, net.word_size,
+                                   net.max_u, net.novelty_scale)
+
+
+def device_root(env, denv, root):
+    from e_alphazero_b200 import ops
+
+    d = {k: to_device(v) for k, v in root.items() if k != "embedding"}
+    d["embedding"] = ops.state_to_device(denv, root["embedding"])
+    return d
+
+
+def assert_same_bits(a, b, name=""):
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    assert a.shape == b.shape, (name, a.shape, b.shape)
+    if a.dtype.kind == "f":
+        same = (a.view(np.uint32) == b.view(np.uint32)) | ((a == 0) & (b == 0))
+    else:
+        same = a == b
+    if not same.all():
+        bad = np.argwhere(~same)
+        raise AssertionError(f"{name}: {len(bad)} of {a.size} differ; first at {bad[0].tolist()}: {a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r}")

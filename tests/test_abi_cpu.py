@@ -1,0 +1,92 @@
+"""CPU-side checks of the boundary: the CUDA library builds for sm_100a, loads without a GPU and
+exports every symbol include/eaz_b200.h declares; ctypes mirrors match the header; product code never
+imports the oracle."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+from e_alphazero_b200 import _abi, _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    if not os.path.exists(_lib.SO_PATH):
+        _lib.build()
+    return _lib.load()
+
+
+def test_exports_every_declared_symbol(lib):
+    header = open(os.path.join(ROOT, "include", "eaz_b200.h")).read()
+    declared = set(re.findall(r"\b(eaz_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.eaz_abi_version() == _abi.ABI_VERSION
+
+
+def test_struct_sizes_match_header():
+    # pointer/int layouts: compile a tiny C program printing sizeof/offsetof and compare with ctypes
+    import subprocess, tempfile, textwrap
+
+    src = textwrap.dedent("""
+        #include <stdio.h>
+        #include <stddef.h>
+        #include "eaz_b200.h"
+        int main(void) {
+          printf("%zu %zu %zu %zu %zu %zu ", sizeof(eaz_env), sizeof(eaz_state), sizeof(eaz_fc_params), sizeof(eaz_search_config),
+                 sizeof(eaz_search_inputs), sizeof(eaz_search_outputs));
+          printf("%zu %zu %zu %zu\\n", offsetof(eaz_fc_params, binary_set), offsetof(eaz_fc_params, novelty_scale),
+                 offsetof(eaz_search_config, mlp_mode), offsetof(eaz_search_outputs, embeddings));
+          return 0;
+        }""")
+    with tempfile.TemporaryDirectory() as d:
+        open(os.path.join(d, "t.c"), "w").write(src)
+        subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
+        got = [int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
+    exp = [C.sizeof(_abi.EazEnv), C.sizeof(_abi.EazState), C.sizeof(_abi.EazFcParams), C.sizeof(_abi.EazSearchConfig),
+           C.sizeof(_abi.EazSearchInputs), C.sizeof(_abi.EazSearchOutputs), _abi.EazFcParams.binary_set.offset,
+           _abi.EazFcParams.novelty_scale.offset, _abi.EazSearchConfig.mlp_mode.offset, _abi.EazSearchOutputs.embeddings.offset]
+    assert got == exp
+
+
+def test_argument_validation_without_gpu(lib):
+    # host-side checks mirror the reference asserts and never touch the device
+    env = _abi.EazEnv(_abi.ENV_SUBLEQ, 0, None, 8, 1, 0)  # word_size < 16 (subleq.py:606)
+    assert lib.eaz_env_num_actions(C.byref(env)) == -1
+    assert b"16 <= word_size <= 256" in lib.eaz_last_error()
+    env = _abi.EazEnv(_abi.ENV_SUBLEQ, 0, None, 16, 1, 0)
+    assert lib.eaz_env_num_actions(C.byref(env)) == 16
+    assert lib.eaz_env_obs_dim(C.byref(env)) == 48 * 5 and lib.eaz_env_hash_dim(C.byref(env), 1) == 160
+    assert lib.eaz_env_compact_bytes(C.byref(env)) == 56
+    env = _abi.EazEnv(_abi.ENV_DEEPSEA, 30, None, 0, 0, 0)
+    assert lib.eaz_env_obs_dim(C.byref(env)) == 900 and lib.eaz_env_compact_bytes(C.byref(env)) == 4
+    assert lib.eaz_xxhash_indices(None, 1, 25, 24, None, None) == _abi.EAZ_ERR_INVALID_ARG  # hashes.py:210
+    cfg = _abi.default_search_config(batch=4096, num_simulations=64)
+    assert lib.eaz_search_workspace_bytes(C.byref(cfg), C.byref(env)) > 4096 * 65 * (7 * 2 * 4 + 7 * 4)
+    assert lib.eaz_search_num_launches(C.byref(cfg), C.byref(env)) == 2 + 4 + 3 * 64 + 1
+
+
+def test_ops_fail_loudly_without_cuda():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from e_alphazero_b200 import ops
+
+    with pytest.raises(_lib.EazError):
+        ops.env_init(ops.subleq_spec(16), 4)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "e_alphazero_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
+                assert not re.search(r"#\s*include[^\n]*oracle", text), f
+                assert "libeaz_oracle" not in text, f

@@ -1,0 +1,236 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+seeded inputs.  Integer / byte / index work and -- in EXACT network mode -- every float are bit-exact."""
+import numpy as np
+import pytest
+
+from e_alphazero_b200 import _abi
+from oracle import oracle as O
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import torch
+
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from e_alphazero_b200 import ops as _ops
+
+    return _ops
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def assert_state_equal(env, dst, st, ctx=""):
+    for k in O.state_fields(env):
+        H.assert_same_bits(host(dst[k]), st[k], f"{ctx}{k}")
+
+
+# ----------------------------------------------------------------------------- envs
+@pytest.mark.parametrize("N,B", [(4, 33), (10, 257), (30, 1000)])
+def test_deepsea_env(ops, N, B):
+    rng = np.random.default_rng(N)
+    env = H.make_env("deepsea", seed=N, size=N)
+    denv = H.device_env(env)
+    st, dst = O.env_init(env, B), ops.env_init(denv, B)
+    assert_state_equal(env, dst, st, "init ")
+    for t in range(2 * N + 3):
+        act = rng.integers(0, 2, B).astype(np.int32)
+        auto = t % 3 == 2
+        st = O.env_step(env, st, act, auto_reset=auto)
+        dst = ops.env_step(denv, dst, H.to_device(act), auto_reset=auto)
+        assert_state_equal(env, dst, st, f"t={t} ")
+        H.assert_same_bits(host(ops.env_observe(denv, dst)), O.env_observe(env, st), f"obs t={t}")
+        H.assert_same_bits(host(ops.env_compact(denv, dst)), O.env_compact(env, st), f"compact t={t}")
+
+
+def test_deepsea_golden(ops, golden_dir):
+    import os
+
+    g = np.load(os.path.join(golden_dir, "deepsea.npz"))
+    for N in (4, 10, 30):
+        denv = ops.deepsea_spec(N, g[f"N{N}_action_map"])
+        actions = g[f"N{N}_actions"]
+        E, T = actions.shape
+        dst = ops.env_init(denv, E)
+        for t in range(T + 1):
+            assert (host(dst["step_count"]) == g[f"N{N}_step_count"][:, t]).all()
+            assert (host(dst["col"]) == g[f"N{N}_col"][:, t]).all()
+            assert (host(dst["terminated"]) == g[f"N{N}_terminated"][:, t]).all()
+            assert (host(dst["rewards"])[:, 0] == g[f"N{N}_rewards"][:, t]).all()
+            assert (host(ops.env_observe(denv, dst)).argmax(1) == g[f"N{N}_obs_index"][:, t]).all()
+            if t < T:
+                dst = ops.env_step(denv, dst, H.to_device(actions[:, t]))
+
+
+@pytest.mark.parametrize("ws,binary,reward_fn,B", [(16, True, 0, 515), (16, False, 1, 100), (23, True, 0, 64), (256, True, 0, 40)])
+def test_subleq_env(ops, ws, binary, reward_fn, B):
+    rng = np.random.default_rng(ws + reward_fn)
+    env = H.make_env("subleq", word_size=ws, binary=binary, reward_fn=reward_fn)
+    denv = H.device_env(env)
+    tasks = rng.integers(0, 9, B).astype(np.int32)  # includes out-of-range ids (lax.switch clamps)
+    st, dst = O.env_init(env, B, tasks), ops.env_init(denv, B, tasks)
+    assert_state_equal(env, dst, st, "init ")
+    steps = 16 if ws <= 32 else 8
+    for t in range(steps):
+        act = np.where(rng.random(B) < 0.5, rng.integers(ws - 4, ws, B), rng.integers(0, ws, B)).astype(np.int32)
+        if t == 0:
+            act[: B // 4] = ws - 2
+        if t == 1:
+            act[: B // 4] = ws - 3
+        auto = t % 5 == 4
+        newt = rng.integers(1, 7, B).astype(np.int32)
+        st = O.env_step(env, st, act, auto_reset=auto, task_ids=newt)
+        dst = ops.env_step(denv, dst, H.to_device(act), auto_reset=auto, task_ids=newt)
+        assert_state_equal(env, dst, st, f"t={t} ")
+        H.assert_same_bits(host(ops.env_observe(denv, dst)), O.env_observe(env, st), f"obs t={t}")
+        H.assert_same_bits(host(ops.env_compact(denv, dst)), O.env_compact(env, st), f"compact t={t}")
+    assert st["solved"].any() and st["terminated"].any()
+
+
+def test_subleq_golden(ops, golden_dir):
+    import os
+
+    g = np.load(os.path.join(golden_dir, "subleq_env.npz"))
+    for i in range(int(g["num_cases"])):
+        ws, binary, rf, task = (int(g[f"c{i}_{k}"]) for k in ("ws", "binary", "reward_fn", "task"))
+        denv = ops.subleq_spec(ws, bool(binary), rf)
+        dst = ops.env_init(denv, 1, [task])
+        acts = g[f"c{i}_actions"]
+        for t in range(len(acts) + 1):
+            ctx = f"case {i} t={t}"
+            assert host(dst["step_count"])[0] == g[f"c{i}__step_count"][t], ctx
+            assert host(dst["solved"])[0] == g[f"c{i}__solved"][t], ctx
+            assert host(dst["terminated"])[0] == g[f"c{i}_terminated"][t], ctx
+            assert (host(dst["memory"])[0] == g[f"c{i}__memory_state"][t]).all(), ctx
+            assert (host(dst["input_after"])[0] == g[f"c{i}__example_input_after"][t]).all(), ctx
+            assert (host(dst["output_after"])[0] == g[f"c{i}__example_output_after"][t]).all(), ctx
+            assert host(dst["rewards"])[0, 0] == g[f"c{i}_rewards"][t, 0], ctx
+            assert (host(ops.env_observe(denv, dst))[0] == g[f"c{i}_observation"][t]).all(), ctx
+            if t < len(acts):
+                dst = ops.env_step(denv, dst, [int(acts[t])])
+    tin, tout = ops.subleq_test_cases(4, 100)
+    oin, oout = O.subleq_test_cases(4, 100)
+    assert (tin == oin).all() and (tout == oout).all()
+
+
+# ----------------------------------------------------------------------------- hash
+@pytest.mark.parametrize("B,D,bits", [(1, 4, 24), (77, 100, 24), (9, 10000, 24), (33, 160, 16), (5, 2592, 32)])
+def test_xxhash(ops, B, D, bits):
+    rng = np.random.default_rng(D)
+    x = np.where(rng.random((B, D)) < 0.5, rng.standard_normal((B, D)), (rng.random((B, D)) < 0.5)).astype(np.float32)
+    idx = host(ops.xxhash_indices(H.to_device(x), bits)).view(np.uint32)
+    assert (idx == O.xxhash_indices(x, bits)).all()
+    if bits >= 8:
+        bset = np.zeros(1 << (bits - 3) if bits <= 24 else 1 << 21, np.uint8)
+        b24 = min(bits, 24)
+        dset = H.to_device(bset)
+        ops.hash_update_(H.to_device(x[: B // 2 + 1]), dset, b24)
+        O.hash_update(x[: B // 2 + 1], bset, b24)
+        assert (host(dset) == bset).all()
+        assert (host(ops.hash_lookup(H.to_device(x), dset, b24)) == O.hash_lookup(x, bset, b24)).all()
+
+
+def test_xxhash_golden(ops, golden_dir):
+    import os
+
+    g = np.load(os.path.join(golden_dir, "xxhash.npz"))
+    for i in range(int(g["num"])):
+        idx = host(ops.xxhash_indices(H.to_device(g[f"h{i}_x"]), int(g[f"h{i}_bits"]))).view(np.uint32)
+        assert (idx == g[f"h{i}_idx"]).all(), i
+
+
+# ----------------------------------------------------------------------------- network
+@pytest.mark.parametrize("kind,kw,B", [("deepsea", dict(size=10), 70), ("deepsea", dict(size=30), 33),
+                                       ("subleq", dict(word_size=16), 100), ("subleq", dict(word_size=16, binary=False), 40),
+                                       ("subleq", dict(word_size=40), 37), ("subleq", dict(word_size=256), 33)])
+def test_network_exact(ops, kind, kw, B):
+    env = H.make_env(kind, seed=1, **kw)
+    net = H.make_net(env, seed=2, fill=0.5)
+    st = H.random_states(env, B, seed=3)
+    exp = O.mlp_forward_states(net, env, st)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    dst = ops.state_to_device(denv, st)
+    got = ops.mlp_forward_states(dnet, denv, dst)
+    for k in exp:
+        H.assert_same_bits(host(got[k]), exp[k], f"states {k}")
+    got = ops.mlp_forward(dnet, ops.env_observe(denv, dst))
+    for k in exp:
+        H.assert_same_bits(host(got[k]), exp[k], f"dense {k}")
+    assert 0 < exp["novelty"].sum() < B
+
+
+def test_network_golden(ops, golden_dir):
+    import os
+
+    g = np.load(os.path.join(golden_dir, "fcnet.npz"))
+    for tag, A, hash_io, ws in (("ds10", 2, 0, 0), ("sub16", 16, 1, 16)):
+        w = [[g[f"{tag}_w{h * 3 + l}"] for l in range(3)] for h in range(4)]
+        b = [[g[f"{tag}_b{h * 3 + l}"] for l in range(3)] for h in range(4)]
+        bset = np.zeros(1 << 21, np.uint8)
+        bset[g[f"{tag}_set_idx"]] = g[f"{tag}_set_val"]
+        dnet = ops.FcParams.from_numpy(w, b, bset, A, 24, hash_io, ws)
+        got = ops.mlp_forward(dnet, H.to_device(g[f"{tag}_obs"]))
+        assert (host(got["novelty"]) == g[f"{tag}_novelty"]).all()
+        for k, gk in (("exploit_logits", "exploit"), ("explore_logits", "explore"), ("value", "value"), ("ube", "ube")):
+            np.testing.assert_allclose(host(got[k]), g[f"{tag}_{gk}"], rtol=1e-5, atol=2e-6, err_msg=f"{tag} {k}")
+
+
+# ----------------------------------------------------------------------------- search
+def run_both(ops, env, net, root, cfg_kw):
+    cfg = _abi.default_search_config(**cfg_kw)
+    exp = O.search(cfg, env, net, root, want_tree=True)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg2 = _abi.default_search_config(**cfg_kw)
+    got = ops.search(cfg2, denv, dnet, H.device_root(env, denv, root), want_tree=True)
+    return exp, {k: host(v) for k, v in got.items()}
+
+
+def assert_tree_equal(exp, got):
+    for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
+        H.assert_same_bits(got[name], exp[name], name)
+
+
+SEARCH_CASES = [
+    # BASELINE config C1: DeepSea size=10, 64 envs, 32 simulations
+    ("deepsea", dict(size=10), 64, dict(num_simulations=32, discount=0.997), dict(beta_max=1.0)),
+    ("deepsea", dict(size=10), 64, dict(num_simulations=32, discount=0.997, rescale_values=0, exploration=1), dict(beta_max=0.0)),
+    ("deepsea", dict(size=30), 130, dict(num_simulations=64, discount=0.997), dict(beta_max=1.0)),
+    ("deepsea", dict(size=6), 50, dict(num_simulations=40, discount=0.997, max_depth=3, gumbel_scale=0.0), dict(beta_max=0.5)),
+    ("deepsea", dict(size=10), 40, dict(num_simulations=16, discount=0.9, flags=_abi.FLAG_BACKUP_STD | _abi.FLAG_BETA_FINAL, two_players_game=1),
+     dict(beta_max=2.0, invalid_frac=0.3)),
+    ("subleq", dict(word_size=16), 96, dict(num_simulations=32, discount=0.97), dict(beta_max=1.0)),
+    ("subleq", dict(word_size=16), 48, dict(num_simulations=64, discount=0.97, max_num_considered_actions=4), dict(beta_max=0.0, invalid_frac=0.4)),
+    ("subleq", dict(word_size=20, binary=False, reward_fn=1), 20, dict(num_simulations=24, discount=0.97), dict(beta_max=1.0)),
+    ("subleq", dict(word_size=40), 24, dict(num_simulations=20, discount=0.97), dict(beta_max=1.0)),
+    ("subleq", dict(word_size=256), 10, dict(num_simulations=40, discount=0.97), dict(beta_max=1.0)),
+]
+
+
+@pytest.mark.parametrize("kind,kw,B,cfg_kw,root_kw", SEARCH_CASES)
+def test_search_bit_exact(ops, kind, kw, B, cfg_kw, root_kw):
+    env = H.make_env(kind, seed=5, **kw)
+    net = H.make_net(env, seed=6, fill=0.5)
+    root = H.make_root(env, net, B, seed=8, **root_kw)
+    exp, got = run_both(ops, env, net, root, cfg_kw)
+    assert_tree_equal(exp, got)
+    n = cfg_kw["num_simulations"]
+    assert (got["visit_counts"].sum(1) == n).all()
+    assert (got["node_visits"][:, 0] == n + 1).all()
+
+
+def test_search_summary_only_and_plan_reuse(ops):
+    env = H.make_env("deepsea", seed=5, size=10)
+    net = H.make_net(env, seed=6, fill=0.5)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(batch=64, num_simulations=32)
+    plan = ops.SearchPlan(cfg, denv, dnet, want_tree=False)
+    for seed in (1, 2):
+        root = H.make_root(env, net, 64, seed=seed)
+        exp = O.search(_abi.default_search_config(num_simulations=32), env, net, root, want_tree=False)
+        got = plan.run(H.device_root(env, denv, root))
+        for name, _, _ in _abi.SUMMARY_FIELDS:
+            H.assert_same_bits(host(got[name]), exp[name], name)
