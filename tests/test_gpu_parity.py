@@ -75,6 +75,7 @@ def test_subleq_env(ops, ws, binary, reward_fn, B):
     st, dst = O.env_init(env, B, tasks), ops.env_init(denv, B, tasks)
     assert_state_equal(env, dst, st, "init ")
     steps = 16 if ws <= 32 else 8
+    saw_solved = saw_term = False
     for t in range(steps):
         act = np.where(rng.random(B) < 0.5, rng.integers(ws - 4, ws, B), rng.integers(0, ws, B)).astype(np.int32)
         if t == 0:
@@ -88,7 +89,9 @@ def test_subleq_env(ops, ws, binary, reward_fn, B):
         assert_state_equal(env, dst, st, f"t={t} ")
         H.assert_same_bits(host(ops.env_observe(denv, dst)), O.env_observe(env, st), f"obs t={t}")
         H.assert_same_bits(host(ops.env_compact(denv, dst)), O.env_compact(env, st), f"compact t={t}")
-    assert st["solved"].any() and st["terminated"].any()
+        saw_solved |= bool(st["solved"].any())
+        saw_term |= bool(st["terminated"].any())
+    assert saw_solved and saw_term
 
 
 def test_subleq_golden(ops, golden_dir):
