@@ -1,0 +1,384 @@
+#!/usr/bin/env python
+"""bench.py -- self-play env-steps/s including the E-MCTS search (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c1|c3]
+
+One "step" = one self-play move for a whole batch of envs: root network forward -> E-MCTS search
+(num_simulations x select/expand/backward with env step, hash probe and network per simulation) ->
+auto-reset env step (reference: selfplay.py:86-143).  Default workload = BASELINE config C2
+(DeepSea size=30, 4096 envs per GPU, 64 simulations, UBE variance propagation on).
+
+Prints ONE JSON line.  `value` is measured with inputs resident in HBM; `e2e` goes through host
+buffers (pinned H2D of the states, D2H of the step's results inside the timed region).
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads) on a
+bounded sample of the same workload: JAX/emctx/pgx are not installable in this image, so the
+reference's own JAX-CPU path cannot be run (DESIGN.md "CPU baseline").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (env kind, env kwargs, envs per GPU, simulations, discount, description)
+    "c1": ("deepsea", dict(size=10), 64, 32, 0.997, "C1: DeepSea size=10, 64 envs, 32 simulations"),
+    "c2": ("deepsea", dict(size=30), 4096, 64, 0.997, "C2: DeepSea size=30, 4096 envs/GPU, 64 simulations, UBE variance propagation on"),
+    "c3": ("subleq", dict(word_size=16), 8192, 64, 0.97, "C3: Subleq ws=16 binary, 8192 envs/GPU, 64 simulations, hash-count novelty on (IO hash)"),
+    "c4": ("deepsea", dict(size=100), 8192, 128, 0.997, "C4: DeepSea size=100, 8192 envs/GPU, 128 simulations"),
+}
+METRIC = "selfplay_env_steps_per_s_incl_emcts_search"
+UNIT = "env-steps/s"
+
+
+def synth_params(kind, kw, seed=0):
+    """Synthetic env + random-init network as host arrays (same generator for both arms)."""
+    rng = np.random.default_rng(seed)
+    if kind == "deepsea":
+        N = kw["size"]
+        env = dict(kind="deepsea", size=N, action_map=(rng.random((N, N)) < 0.5).astype(np.uint8))
+        D, A, hash_io, ws = N * N, 2, 0, 0
+    else:
+        ws = kw["word_size"]
+        w = (ws - 1).bit_length() + 1
+        env = dict(kind="subleq", word_size=ws)
+        D, A, hash_io = (ws + 32) * w, ws, 1
+    H = 256
+    W, Bv = [], []
+    for h in range(4):
+        outs, ins = [H, H, 1 if h < 2 else A], [D, H, H]
+        W.append([np.ascontiguousarray(rng.standard_normal((i, o)).clip(-2, 2) / np.sqrt(i), np.float32) for i, o in zip(ins, outs)])
+        Bv.append([np.ascontiguousarray(rng.standard_normal(o) * 0.05, np.float32) for o in outs])
+    bset = ((rng.random(1 << 21) < 0.5) * rng.integers(1, 256, 1 << 21)).astype(np.uint8)  # ~half of the states "seen"
+    return env, dict(w=W, b=Bv, binary_set=bset, num_actions=A, hash_io=hash_io, word_size=ws, in_dim=D)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[1]) for r in rows)
+        reasons = [n for i, n in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap"))
+                   if any(r[i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
+                "samples": len(rows), "reasons": reasons}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), d.get("bf16_tflops_sustained", 1400.0), "measured"
+    return 6650.0, 1590.0, "fallback"  # B200_PROFILING.md fallback
+
+
+# ============================================================================== reference arm / cpu baseline (oracle)
+def oracle_step_time(kind, kw, n, gamma, B_sample, seed, repeats=1):
+    """Time `repeats` self-play steps of the CPU restatement on B_sample envs; returns seconds per step."""
+    from e_alphazero_b200 import _abi
+    from oracle import oracle as O
+
+    envp, netp = synth_params(kind, kw, 0)
+    env = O.Env.deepsea(envp["size"], envp["action_map"]) if kind == "deepsea" else O.Env.subleq(envp["word_size"], True)
+    net = O.FcNet(netp["in_dim"], 256, netp["num_actions"], netp["w"], netp["b"], netp["binary_set"], 24, netp["hash_io"], netp["word_size"])
+    rng = np.random.default_rng(seed)
+    A = env.num_actions
+    st = O.env_init(env, B_sample, rng.integers(1, 2, B_sample))
+    for _ in range(3):  # decorrelate depths
+        st = O.env_step(env, st, rng.integers(0, A, B_sample), auto_reset=True, task_ids=np.ones(B_sample, np.int32))
+    beta = np.linspace(0, 1, B_sample).astype(np.float32)
+    cfg = _abi.default_search_config(num_simulations=n, discount=gamma, exploration=1)
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        ev = O.mlp_forward_states(net, env, st)
+        root = dict(prior_logits=ev["explore_logits"], value=ev["value"], value_epistemic_variance=ev["ube"], beta=beta, embedding=st,
+                    gumbel=rng.gumbel(size=(B_sample, A)).astype(np.float32))
+        out = O.search(cfg, env, net, root, want_tree=False)
+        st = O.env_step(env, st, out["action"], auto_reset=True, task_ids=np.ones(B_sample, np.int32))
+    return (time.perf_counter() - t0) / repeats
+
+
+def cpu_baseline(kind, kw, n, gamma, budget_s=12.0):
+    from oracle import oracle as O
+
+    O.build()
+    cores = O.set_threads(os.cpu_count() or 1)
+    probe_B = max(cores * 4, 32)
+    t = oracle_step_time(kind, kw, n, gamma, probe_B, seed=1)
+    B_sample = int(min(4096, max(probe_B, probe_B * budget_s / max(t, 1e-3))))
+    B_sample -= B_sample % max(cores, 1) or 0
+    t = oracle_step_time(kind, kw, n, gamma, B_sample, seed=2)
+    return {"value": B_sample / t, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{B_sample} envs x 1 self-play step ({n} simulations) of the same workload, {t:.2f} s, OpenMP over envs",
+            "simulations_per_s": B_sample * n / t}
+
+
+def run_reference(args, kind, kw, B, n, gamma, desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+
+    O.build()
+    cores = O.set_threads(os.cpu_count() or 1)
+    probe_B = max(cores * 4, 32)
+    t = oracle_step_time(kind, kw, n, gamma, probe_B, seed=1)
+    per_step_budget = min(6.0, 150.0 / max(args.steps + args.warmup, 1))
+    B_sample = int(min(B, max(cores, probe_B * per_step_budget / max(t, 1e-3))))
+    for _ in range(args.warmup):
+        oracle_step_time(kind, kw, n, gamma, B_sample, seed=3)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        oracle_step_time(kind, kw, n, gamma, B_sample, seed=10 + i)
+    dt = time.perf_counter() - t0
+    value = B_sample * args.steps / dt
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": desc, "envs_per_step_sample": B_sample, "num_simulations": n,
+                                            "note": "CPU restatement of the reference (oracle/eaz_oracle.c), not JAX: jax/emctx/pgx are not installable here"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{B_sample} envs per step x {args.steps} steps ({n} simulations each)"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "simulations_per_s": value * n, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ============================================================================== B200 arm
+def run_b200(args, kind, kw, B, n, gamma, desc):
+    import torch
+    import torch.distributed as dist
+
+    from e_alphazero_b200 import _abi, ops
+    from e_alphazero_b200.selfplay import SelfplayRunner
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device: the CUDA library is the only implementation")
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+
+    envp, netp = synth_params(kind, kw, 0)
+    env = ops.deepsea_spec(envp["size"], envp["action_map"], dev) if kind == "deepsea" else ops.subleq_spec(envp["word_size"], True)
+    net = ops.FcParams.from_numpy(netp["w"], netp["b"], netp["binary_set"], netp["num_actions"], 24, netp["hash_io"], netp["word_size"], device=dev)
+    if world > 1:  # parameter broadcast (learner -> actors), once per learner update: outside the timed region
+        for h in range(4):
+            for l in range(3):
+                dist.broadcast(net.w[h][l], 0)
+                dist.broadcast(net.b[h][l], 0)
+        dist.broadcast(net.binary_set, 0)
+
+    # shard = this rank's envs (weak scaling: B per GPU fixed); directed exploration with beta = linspace(0,1,B) (UBE on)
+    runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=100 + rank)
+    gen = torch.Generator(device=dev).manual_seed(7 + rank)
+    states = ops.env_init(env, B, task_ids=torch.ones(B, dtype=torch.int32, device=dev) if kind == "subleq" else None, device=dev)
+    A = env.num_actions
+    for _ in range(5 if kind == "deepsea" else 3):  # spread the envs over depths with random play (product env kernels)
+        act = torch.randint(0, A, (B,), device=dev, generator=gen, dtype=torch.int32)
+        keep = torch.rand(B, device=dev, generator=gen) < 0.5
+        nxt = ops.env_step(env, states, act)
+        for k in states:
+            m = keep.reshape((-1,) + (1,) * (states[k].dim() - 1))
+            states[k] = torch.where(m, nxt[k], states[k]).contiguous()
+
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    gather_buf = torch.empty((world, B, 4), dtype=torch.int32, device=dev) if world > 1 else None
+
+    def one_step(st):
+        st, out = runner.step(st)
+        if world > 1:  # trajectory all-gather into the replay buffer (compact: action, reward bits, flags, state)
+            traj = torch.stack([out.action, st["rewards"][:, 0].view(torch.int32), st["terminated"].to(torch.int32), st["step_count"]], 1).contiguous()
+            dist.all_gather_into_tensor(gather_buf.view(-1), traj.view(-1))
+        return st, out
+
+    for _ in range(max(args.warmup, 3)):
+        states, _ = one_step(states)
+    torch.cuda.synchronize()
+
+    # ---- timed region: exactly K steps, CUDA events per step, L2 flushed between steps (outside the events)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    for i in range(args.steps):
+        flush.zero_()
+        ev[i][0].record()
+        states, out = one_step(states)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_wall1 = time.time()
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms_total], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+    value = world * B * args.steps / (ms_total * 1e-3)
+
+    # ---- e2e: host buffers in, host results out, copies inside the timed region (rank-local, max over ranks)
+    fields = ops.state_fields(env)
+    host_in = {k: states[k].detach().cpu().pin_memory() for k in fields}
+    host_out = {k: torch.empty_like(host_in[k]).pin_memory() for k in fields}
+    res_names = ("action", "root_value", "root_epistemic_std", "value_prediction", "ube_prediction", "q_values_epistemic_variance")
+    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+    e2e_ms, d2h = 0.0, 0
+    dstates = {k: torch.empty_like(states[k]) for k in fields}
+    host_res = None
+    for i in range(args.steps + 2):
+        flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for k in fields:
+            dstates[k].copy_(host_in[k], non_blocking=True)
+        dstates, out = one_step(dstates)
+        for k in fields:
+            host_out[k].copy_(dstates[k], non_blocking=True)
+        res = [getattr(out, nme) for nme in res_names]
+        if host_res is None:
+            host_res = [torch.empty_like(r, device="cpu").pin_memory() for r in res]
+            d2h = sum(v.numel() * v.element_size() for v in host_out.values()) + sum(r.numel() * r.element_size() for r in res)
+        for hr, r in zip(host_res, res):
+            hr.copy_(r, non_blocking=True)
+        b.record()
+        torch.cuda.synchronize()
+        if i >= 2:
+            e2e_ms += a.elapsed_time(b)
+        host_in, host_out = host_out, host_in
+    if world > 1:
+        t = torch.tensor([e2e_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+
+    # ---- roofline: per-kernel-class CUDA-event times of the search (measured live, rank 0), algorithmic bytes per SURVEY 8(d)
+    roofline = None
+    if rank == 0:
+        ev0 = ops.mlp_forward_states(net, env, states)
+        root = dict(prior_logits=ev0["explore_logits"], value=ev0["value"], value_epistemic_variance=ev0["ube"], beta=runner.beta,
+                    embedding=states, gumbel=runner.draw_gumbel())
+        tplan = ops.SearchPlan(_abi.default_search_config(batch=B, num_simulations=n, discount=gamma, exploration=1, mlp_mode=args.mlp_mode), env, net,
+                               want_tree=True, device=dev)
+        tout = tplan.run(root)
+        V = int(tout["node_visits"][:, 1:].sum().item())  # edge traversals = sum over simulations of path depth
+        del tplan
+        prof = {}
+        reps = 3
+        for _ in range(reps):
+            _, p = runner.plan.run(root, profile=True)
+            for k, (ms, cnt) in p.items():
+                prof[k] = (prof.get(k, (0.0, 0))[0] + ms / reps, cnt)
+        S = env.compact_bytes
+        tree_bytes = V * (32 * A + 68) + B * n * (2 * S + 4 * A + 44)
+        io_bytes = B * (8 * A + A + 16 + S) + B * (4 + 20 * A + 8)
+        tree_ms = prof["select"][0] + prof["expand_backward"][0] + prof["env_step"][0]
+        hbm_peak, tf_peak, which = measured_peaks()
+        D, H = netp["in_dim"], 256
+        l1 = 0 if kind == "deepsea" else 2 * D * H  # one-hot DeepSea layer 1 is a row gather
+        flops_fwd = 3 * (l1 + 2 * H * H) + 2 * (2 * H) + 2 * H * A  # 3 heads evaluated per node (value, UBE, one policy head)
+        mlp_ms = prof["network"][0]
+        total_ms = sum(v[0] for v in prof.values())
+        dominant = "network" if mlp_ms >= tree_ms else "tree"
+        tree_gbs = (tree_bytes + io_bytes) / (tree_ms * 1e-3) / 1e9
+        mlp_tfs = flops_fwd * B * n / (mlp_ms * 1e-3) / 1e12
+        tree_obj = {"bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tree_gbs / hbm_peak, "traffic": None,
+                    "kernels": "select + expand_backward" + (" + subleq_tree_step" if kind == "subleq" else ""),
+                    "algorithmic_bytes_per_search": tree_bytes + io_bytes, "ms_per_search": tree_ms,
+                    "avg_launch_us": 1e3 * tree_ms / max(prof["select"][1] + prof["expand_backward"][1] + prof["env_step"][1], 1),
+                    "edge_traversals": V, "peak_source": which}
+        mlp_obj = {"bound": "tensor", "achieved": mlp_tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": mlp_tfs / tf_peak, "traffic": None,
+                   "kernels": "mlp_exact_kernel (fp32 FMA chains, bit-exact mode)" if args.mlp_mode == 0 else "mlp_tensor_kernel (tcgen05)",
+                   "flops_per_search": flops_fwd * B * n, "ms_per_search": mlp_ms, "avg_launch_us": 1e3 * mlp_ms / max(prof["network"][1], 1),
+                   "peak_source": which}
+        roofline = dict(mlp_obj if dominant == "network" else tree_obj)
+        roofline["dominant"] = dominant
+        roofline["share_of_search_time"] = (mlp_ms if dominant == "network" else tree_ms) / total_ms
+        roofline["other"] = tree_obj if dominant == "network" else mlp_obj
+        roofline["per_class_ms"] = {k: round(v[0], 4) for k, v in prof.items()}
+        roofline["per_class_launches"] = {k: v[1] for k, v in prof.items()}
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = cpu_baseline(kind, kw, n, gamma) if world == 1 and not args.no_cpu_baseline else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": desc, "envs_per_gpu": B, "num_simulations": n, "mlp_mode": "exact_fp32" if args.mlp_mode == 0 else "tensor",
+                       "l2": "flushed between timed steps (256 MiB write)", "directed_exploration": True, "beta": "linspace(0,1,B)",
+                       "multi_gpu": "envs sharded per rank, params broadcast once, compact trajectory all-gather per step" if world > 1 else "single GPU"},
+            "simulations_per_s": value * n, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "gpu_launches": runner.launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--mlp-mode", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    kind, kw, B, n, gamma, desc = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, kind, kw, B, n, gamma, desc)
+    else:
+        run_b200(args, kind, kw, B, n, gamma, desc)
+
+
+if __name__ == "__main__":
+    main()

@@ -24,7 +24,7 @@ EXPORTS = [
     "eaz_subleq_test_cases",
     "eaz_xxhash_indices", "eaz_hash_lookup", "eaz_hash_update",
     "eaz_mlp_forward", "eaz_mlp_forward_states",
-    "eaz_search_workspace_bytes", "eaz_search_gumbel", "eaz_search_num_launches",
+    "eaz_search_workspace_bytes", "eaz_search_gumbel", "eaz_search_gumbel_profiled", "eaz_search_num_launches",
 ]
 
 

@@ -19,7 +19,34 @@
 // host synchronisation, so a whole search is CUDA-graph capturable.
 #include "mlp.cuh"
 
+#include <vector>
+
 namespace eaz {
+
+// ---- optional per-kernel-class timing (eaz_search_gumbel_profiled): CUDA events around every launch
+enum { CLS_INIT = 0, CLS_SELECT, CLS_ENV, CLS_MLP, CLS_EXPAND, CLS_FINAL, CLS_EXPORT, CLS_COUNT };
+struct Prof {
+  std::vector<cudaEvent_t> ev;  // begin/end pairs
+  std::vector<int> cls;
+};
+static thread_local Prof* tl_prof = nullptr;
+struct ProfScope {
+  cudaStream_t st;
+  bool on;
+  ProfScope(int c, cudaStream_t s) : st(s), on(tl_prof != nullptr) {
+    if (!on) return;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    tl_prof->ev.push_back(a);
+    tl_prof->ev.push_back(b);
+    tl_prof->cls.push_back(c);
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (on) cudaEventRecord(tl_prof->ev.back(), st);
+  }
+};
 
 struct Tree {
   int B, N, A, S;
@@ -644,7 +671,10 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
                       const SummaryOut& so, int mlp_mode, int exploration, cudaStream_t st) {
   const int envs_per_block = 4 * (32 / G);
   const int grid = ceil_div(t.B, envs_per_block);
-  root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->prior_logits, in->value, in->value_epistemic_variance, in->gumbel, in->invalid_actions);
+  {
+    ProfScope ps(CLS_INIT, st);
+    root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->prior_logits, in->value, in->value_epistemic_variance, in->gumbel, in->invalid_actions);
+  }
   EAZ_CHECK_LAUNCH("root_init_kernel");
   const int lhead = exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;  // context.py:132
   const int mask = (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead);
@@ -652,17 +682,30 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   MlpOutputs mo{{nullptr, nullptr}, t.net_value, t.net_ube, nullptr};
   mo.logits[lhead - EAZ_HEAD_EXPLOIT] = t.net_logits;
   for (int sim = 0; sim < sp.n; ++sim) {
-    select_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env, sim, in->beta, in->invalid_actions);
+    {
+      ProfScope ps(CLS_SELECT, st);
+      select_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env, sim, in->beta, in->invalid_actions);
+    }
     EAZ_CHECK_LAUNCH("select_kernel");
     if (env.kind == EAZ_ENV_SUBLEQ) {
+      ProfScope ps(CLS_ENV, st);
       subleq_tree_step_kernel<<<ceil_div(t.B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, 0, st>>>(t, env);
       EAZ_CHECK_LAUNCH("subleq_tree_step_kernel");
     }
-    if (int rc = launch_mlp(net, env, src, t.B, mask, mo, mlp_mode, st)) return rc;
-    expand_backward_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env);
+    {
+      ProfScope ps(CLS_MLP, st);
+      if (int rc = launch_mlp(net, env, src, t.B, mask, mo, mlp_mode, st)) return rc;
+    }
+    {
+      ProfScope ps(CLS_EXPAND, st);
+      expand_backward_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env);
+    }
     EAZ_CHECK_LAUNCH("expand_backward_kernel");
   }
-  finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so);
+  {
+    ProfScope ps(CLS_FINAL, st);
+    finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so);
+  }
   EAZ_CHECK_LAUNCH("finalize_kernel");
   return 0;
 }
@@ -755,6 +798,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   SearchParams sp{n, cfg->max_depth > 0 ? cfg->max_depth : n, cfg->max_num_considered_actions, cfg->gumbel_scale, cfg->discount,
                   cfg->value_scale, cfg->maxvisit_init, cfg->epsilon, cfg->two_players_game, cfg->rescale_values, cfg->use_mixed_value,
                   cfg->flags};
+  ProfScope* init_scope = new ProfScope(CLS_INIT, st);
   cudaError_t e = cudaMemsetAsync((uint8_t*)workspace + L.zero_begin, 0, L.zero_end - L.zero_begin, st);
   if (e == cudaSuccess) e = cudaMemsetAsync((uint8_t*)workspace + L.ones_begin, 0xFF, L.ones_end - L.ones_begin, st);
   if (e != cudaSuccess) return cuda_fail(e, "search memset");
@@ -763,6 +807,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   if (int rc = eaz_env_compact(in->env, in->embedding, t.states, B, stream)) return rc;  // node 0 = roots
   if (env.kind == EAZ_ENV_DEEPSEA)
     if (int rc = launch_deepsea_seen_table(net, env, t.ds_seen, st)) return rc;
+  delete init_scope;
 
   SummaryOut so{out->action, out->action_weights, out->value, out->value_epistemic_std, out->visit_counts, out->visit_probs,
                 out->qvalues, out->qvalues_epistemic_variance};
@@ -789,10 +834,32 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
                out->raw_values, out->node_values, out->raw_values_epistemic_variance, out->node_values_epistemic_variance,
                out->children_prior_logits, out->children_rewards, out->children_discounts, out->children_values,
                out->children_rewards_epistemic_variance, out->children_values_epistemic_variance, out->embeddings};
+    ProfScope ps(CLS_EXPORT, st);
     export_tree_kernel<<<148 * 8, 256, 0, st>>>(t, to);
     EAZ_CHECK_LAUNCH("export_tree_kernel");
   }
   return 0;
+}
+
+int eaz_search_gumbel_profiled(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
+                               size_t workspace_bytes, void* stream, float* ms_by_class, int32_t* launches_by_class) {
+  EAZ_CHECK_ARG(ms_by_class && launches_by_class, "profiled search: NULL result arrays");
+  Prof prof;
+  tl_prof = &prof;
+  const int rc = eaz_search_gumbel(cfg, in, out, workspace, workspace_bytes, stream);
+  tl_prof = nullptr;
+  cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+  for (int c = 0; c < EAZ_PROFILE_CLASSES; ++c) { ms_by_class[c] = 0.0f; launches_by_class[c] = 0; }
+  for (size_t i = 0; i < prof.cls.size(); ++i) {
+    float ms = 0.0f;
+    if (e == cudaSuccess && rc == 0) cudaEventElapsedTime(&ms, prof.ev[2 * i], prof.ev[2 * i + 1]);
+    ms_by_class[prof.cls[i]] += ms;
+    launches_by_class[prof.cls[i]] += 1;
+    cudaEventDestroy(prof.ev[2 * i]);
+    cudaEventDestroy(prof.ev[2 * i + 1]);
+  }
+  if (e != cudaSuccess) return cuda_fail(e, "profiled search sync");
+  return rc;
 }
 
 }  // extern "C"

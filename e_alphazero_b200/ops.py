@@ -368,7 +368,9 @@ class SearchPlan:
         self.out = alloc_search_outputs(B, N, A, self.env.compact_bytes, self.want_tree, self.device)
         self.num_launches = load().eaz_search_num_launches(C.byref(self.cfg), C.byref(e))
 
-    def run(self, root: dict) -> dict:
+    PROFILE_CLASSES = ("init", "select", "env_step", "network", "expand_backward", "finalize", "export")
+
+    def run(self, root: dict, profile: bool = False):
         """root: prior_logits [B,A], value [B], value_epistemic_variance [B], beta [B], embedding (state dict),
         gumbel [B,A] pre-drawn standard Gumbel noise, optional invalid_actions [B,A] (bool/uint8)."""
         import torch
@@ -383,6 +385,12 @@ class SearchPlan:
         o = _abi.EazSearchOutputs()
         for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
             setattr(o, name, _ptr(self.out.get(name)))
+        if profile:  # measurement aid: synchronises; returns (outputs, {class: (ms, launches)})
+            ms = (C.c_float * len(self.PROFILE_CLASSES))()
+            cnt = (C.c_int32 * len(self.PROFILE_CLASSES))()
+            check(load().eaz_search_gumbel_profiled(C.byref(self.cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream(), ms, cnt),
+                  "eaz_search_gumbel_profiled")
+            return self.out, {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
         check(load().eaz_search_gumbel(C.byref(self.cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream()), "eaz_search_gumbel")
         return self.out
 

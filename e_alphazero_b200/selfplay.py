@@ -1,0 +1,63 @@
+"""Host-side mirror of the reference's selfplay step (selfplay.py:86-143) and reanalyze search
+(reanalyze.py:52-131) on top of the fused CUDA path.  One `SelfplayRunner.step()` is the unit the
+benchmark times: root forward -> E-MCTS search -> auto-reset env step."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Any
+
+from . import _abi, ops
+from ._lib import require_cuda
+
+
+@dataclass
+class SelfplayOutput:  # selfplay.py:17-23
+    state: Any
+    root_value: Any
+    root_epistemic_std: Any
+    value_prediction: Any
+    ube_prediction: Any
+    q_values_epistemic_variance: Any
+    action: Any = None
+
+
+class SelfplayRunner:
+    """Pre-allocates the search plan; `step(states, gumbel=None)` advances a batch of envs by one move."""
+
+    def __init__(self, env_spec: ops.EnvSpec, net: ops.FcParams, batch: int, num_simulations: int, discount: float,
+                 exploration_beta: float = 0.0, directed_exploration: bool = False, rescale_values: bool = True,
+                 mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0):
+        torch = require_cuda()
+        self.env, self.net, self.B, self.device = env_spec, net, batch, device
+        self.directed = directed_exploration
+        self.cfg = _abi.default_search_config(batch=batch, num_simulations=num_simulations, discount=discount,
+                                              exploration=int(directed_exploration), rescale_values=int(rescale_values), mlp_mode=mlp_mode)
+        self.plan = ops.SearchPlan(self.cfg, env_spec, net, want_tree=False, device=device)
+        beta = exploration_beta if directed_exploration else 0.0  # selfplay.py:92, config.py:172
+        self.beta = (beta * torch.linspace(0, 1, batch, device=device)).contiguous()  # selfplay.py:105
+        self.gen = torch.Generator(device=device).manual_seed(seed)
+        self.tasks = torch.tensor(list(tasks), dtype=torch.int32, device=device)
+        self.A = env_spec.num_actions
+        # launches per step: compact+mlp (root forward), search, env step
+        self.launches_per_step = 2 + self.plan.num_launches + 1
+
+    def draw_gumbel(self):
+        torch = require_cuda()
+        u = torch.rand((self.B, self.A), device=self.device, generator=self.gen).clamp_(1e-20, 1.0 - 1e-7)
+        return (-(-u.log()).log()).contiguous()
+
+    def step(self, states: dict, gumbel=None, task_ids=None):
+        """states: device state dict (updated in place).  Returns (states, SelfplayOutput)."""
+        torch = require_cuda()
+        ev = ops.mlp_forward_states(self.net, self.env, states)  # selfplay.py:89
+        logits = ev["explore_logits"] if self.directed else ev["exploit_logits"]  # :93-95
+        root = dict(prior_logits=logits, value=ev["value"], value_epistemic_variance=ev["ube"], beta=self.beta, embedding=states,
+                    gumbel=self.draw_gumbel() if gumbel is None else gumbel)
+        out = self.plan.run(root)  # :107-117 (invalid_actions = ~legal_action_mask = none)
+        if task_ids is None and self.env.kind == _abi.ENV_SUBLEQ:
+            idx = torch.randint(0, self.tasks.numel(), (self.B,), device=self.device, generator=self.gen)
+            task_ids = self.tasks[idx].contiguous()
+        ops.env_step_(self.env, states, out["action"], auto_reset=True, task_ids=task_ids)  # :135
+        return states, SelfplayOutput(state=states, root_value=out["value"], root_epistemic_std=out["value_epistemic_std"],
+                                      value_prediction=ev["value"], ube_prediction=ev["ube"],
+                                      q_values_epistemic_variance=out["qvalues_epistemic_variance"], action=out["action"])

@@ -265,6 +265,15 @@ size_t eaz_search_workspace_bytes(const eaz_search_config* cfg, const eaz_env* e
 int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out,
                       void* workspace, size_t workspace_bytes, void* stream);
 
+/* Measurement aid (bench.py's roofline breakdown): the same search with CUDA events recorded around every
+ * launch on `stream`; SYNCHRONISES the stream and returns summed milliseconds and launch counts per kernel
+ * class (host arrays of EAZ_PROFILE_CLASSES entries: init, select, env step, network, expand+backward,
+ * finalize, export). */
+#define EAZ_PROFILE_CLASSES 7
+int eaz_search_gumbel_profiled(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out,
+                               void* workspace, size_t workspace_bytes, void* stream, float* ms_by_class,
+                               int32_t* launches_by_class);
+
 /* Number of kernel launches one eaz_search_gumbel call enqueues (for bench.py's
  * gpu_launches accounting). */
 int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env);
