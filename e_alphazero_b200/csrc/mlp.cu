@@ -321,10 +321,17 @@ int launch_deepsea_seen_table(const NetDesc& net, const EnvDesc& env, uint8_t* s
 int mlp_num_launches(int mode) { return 1; }
 
 int launch_mlp(const NetDesc& net, const EnvDesc& env, const MlpSource& src, int B, int heads_mask, const MlpOutputs& out, int mode,
-               cudaStream_t stream) {
+               cudaStream_t stream, const TensorWeights* tw) {
+  if (mode == EAZ_MLP_TENSOR) {
+    if (!tw) {
+      set_error("mlp_mode TENSOR needs prepared weight images");
+      return EAZ_ERR_INVALID_ARG;
+    }
+    return launch_mlp_tensor(net, env, src, *tw, B, heads_mask, out, stream);
+  }
   if (mode != EAZ_MLP_EXACT) {
-    set_error("mlp_mode %d is not built into this library", mode);
-    return EAZ_ERR_UNSUPPORTED;
+    set_error("unknown mlp_mode %d", mode);
+    return EAZ_ERR_INVALID_ARG;
   }
   HeadList hl{0, {0, 0, 0, 0}};
   for (int h = 0; h < 4; ++h)

@@ -29,9 +29,20 @@ struct MlpOutputs {
   float* novelty;    // [B]
 };
 
-// heads_mask: bit h set = evaluate head h.  mode: EAZ_MLP_EXACT | EAZ_MLP_TENSOR.
+// Pre-split (3xTF32 hi/lo), pre-tiled weight images for the tensor-core path (mlp_tensor.cu):
+// img[head][layer] = K-chunk images in the canonical UMMA layout of umma.cuh.
+struct TensorWeights {
+  const uint32_t* img[4][3];
+  int k1pad;
+};
+size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env);
+int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mask, void* buf, TensorWeights* tw, cudaStream_t st);
+int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,
+                      const MlpOutputs& out, cudaStream_t stream);
+
+// heads_mask: bit h set = evaluate head h.  mode: EAZ_MLP_EXACT | EAZ_MLP_TENSOR (needs `tw`).
 int launch_mlp(const NetDesc& net, const EnvDesc& env, const MlpSource& src, int B, int heads_mask, const MlpOutputs& out, int mode,
-               cudaStream_t stream);
+               cudaStream_t stream, const TensorWeights* tw = nullptr);
 int mlp_num_launches(int mode);
 
 // DeepSea: seen[cell] for every one-hot observation (one hash per grid cell).

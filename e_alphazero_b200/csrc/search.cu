@@ -61,6 +61,7 @@ struct Tree {
   int32_t *parent, *action, *leaf;
   int32_t* table;
   uint8_t* ds_seen;
+  uint8_t* wimg;  // tensor-path weight images (mlp_mode TENSOR)
 };
 
 struct Layout {
@@ -71,7 +72,7 @@ struct Layout {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, Layout* L) {
+static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, size_t wimg_bytes, Layout* L) {
   const size_t nb = (size_t)N * B, nba = nb * A;
   size_t o = 0;
   int i = 0;
@@ -104,6 +105,7 @@ static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, 
   put((size_t)B * 4);      // 21 leaf
   put((size_t)table_len * 4);  // 22 table
   put((size_t)obs_dim);        // 23 ds_seen
+  put(wimg_bytes);             // 24 tensor weight images
   L->total = o;
 }
 
@@ -135,6 +137,7 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
   t.leaf = (int32_t*)(p + L.off[21]);
   t.table = (int32_t*)(p + L.off[22]);
   t.ds_seen = p + L.off[23];
+  t.wimg = p + L.off[24];
   return t;
 }
 
@@ -668,7 +671,7 @@ __global__ void export_tree_kernel(Tree t, TreeOut o) {
 // ------------------------------------------------------------------ host side
 template <int G, int J>
 static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env, const NetDesc& net, const eaz_search_inputs* in,
-                      const SummaryOut& so, int mlp_mode, int exploration, cudaStream_t st) {
+                      const SummaryOut& so, int mlp_mode, int exploration, const TensorWeights* tw, cudaStream_t st) {
   const int envs_per_block = 4 * (32 / G);
   const int grid = ceil_div(t.B, envs_per_block);
   {
@@ -694,7 +697,7 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     }
     {
       ProfScope ps(CLS_MLP, st);
-      if (int rc = launch_mlp(net, env, src, t.B, mask, mo, mlp_mode, st)) return rc;
+      if (int rc = launch_mlp(net, env, src, t.B, mask, mo, mlp_mode, st, tw)) return rc;
     }
     {
       ProfScope ps(CLS_EXPAND, st);
@@ -708,6 +711,15 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   }
   EAZ_CHECK_LAUNCH("finalize_kernel");
   return 0;
+}
+
+static size_t wimg_bytes_for(int mlp_mode, const EnvDesc& env) {
+  if (mlp_mode != EAZ_MLP_TENSOR) return 0;
+  NetDesc nd{};
+  nd.D = env.obs_dim;
+  nd.H = EAZ_FC_HIDDEN_MAX;
+  nd.A = env.num_actions;
+  return tensor_weights_bytes(nd, env);
 }
 
 static int check_search(const eaz_search_config* cfg, const eaz_search_inputs* in, const eaz_search_outputs* out, EnvDesc* env, NetDesc* net) {
@@ -769,7 +781,7 @@ size_t eaz_search_workspace_bytes(const eaz_search_config* cfg, const eaz_env* e
   if (!cfg || make_env_desc(env, &d) || cfg->batch < 1 || cfg->num_simulations < 1) return 0;
   Layout L;
   make_layout(cfg->batch, cfg->num_simulations + 1, d.num_actions, d.compact_bytes,
-              (cfg->max_num_considered_actions + 1) * cfg->num_simulations, d.obs_dim, &L);
+              (cfg->max_num_considered_actions + 1) * cfg->num_simulations, d.obs_dim, wimg_bytes_for(cfg->mlp_mode, d), &L);
   return L.total;
 }
 
@@ -777,8 +789,9 @@ int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env
   EnvDesc d;
   if (!cfg || make_env_desc(env, &d)) return -1;
   const int per_sim = 2 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
+  const int prep = cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * (d.kind == EAZ_ENV_DEEPSEA ? 2 : 3) : 0;  // weight tiling, 3 heads
   // 2 memsets + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
-  return 2 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + per_sim * cfg->num_simulations + 1;
+  return 2 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1;
 }
 
 int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
@@ -788,7 +801,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   if (int rc = check_search(cfg, in, out, &env, &net)) return rc;
   const int B = cfg->batch, n = cfg->num_simulations, N = n + 1, A = env.num_actions, S = env.compact_bytes;
   Layout L;
-  make_layout(B, N, A, S, (cfg->max_num_considered_actions + 1) * n, env.obs_dim, &L);
+  make_layout(B, N, A, S, (cfg->max_num_considered_actions + 1) * n, env.obs_dim, wimg_bytes_for(cfg->mlp_mode, env), &L);
   if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
     set_error("search workspace must be >= %zu bytes and 256-byte aligned (got %zu)", L.total, workspace_bytes);
     return EAZ_ERR_WORKSPACE;
@@ -807,12 +820,17 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   if (int rc = eaz_env_compact(in->env, in->embedding, t.states, B, stream)) return rc;  // node 0 = roots
   if (env.kind == EAZ_ENV_DEEPSEA)
     if (int rc = launch_deepsea_seen_table(net, env, t.ds_seen, st)) return rc;
+  TensorWeights tw{};
+  if (cfg->mlp_mode == EAZ_MLP_TENSOR) {
+    const int lhead = cfg->exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;
+    if (int rc = prepare_tensor_weights(net, env, (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead), t.wimg, &tw, st)) return rc;
+  }
   delete init_scope;
 
   SummaryOut so{out->action, out->action_weights, out->value, out->value_epistemic_std, out->visit_counts, out->visit_probs,
                 out->qvalues, out->qvalues_epistemic_variance};
   int rc;
-#define EAZ_RUN(G, J) rc = run_search<G, J>(t, sp, env, net, in, so, cfg->mlp_mode, cfg->exploration, st)
+#define EAZ_RUN(G, J) rc = run_search<G, J>(t, sp, env, net, in, so, cfg->mlp_mode, cfg->exploration, cfg->mlp_mode == EAZ_MLP_TENSOR ? &tw : nullptr, st)
   if (A <= 2) EAZ_RUN(2, 1);
   else if (A <= 4) EAZ_RUN(4, 1);
   else if (A <= 8) EAZ_RUN(8, 1);

@@ -106,3 +106,27 @@ def assert_same_bits(a, b, name=""):
     if not same.all():
         bad = np.argwhere(~same)
         raise AssertionError(f"{name}: {len(bad)} of {a.size} differ; first at {bad[0].tolist()}: {a[tuple(bad[0])]!r} vs {b[tuple(bad[0])]!r}")
+
+
+def uncompact(env, emb):
+    """Compact in-tree states [M,S] (uint8) -> oracle state dict (numpy); inverse of the packing in DESIGN.md."""
+    emb = np.ascontiguousarray(emb)
+    M = emb.shape[0]
+    st = O.alloc_state(env, M)
+    if env.kind == _abi.ENV_DEEPSEA:
+        v = emb.view(np.uint32).reshape(M)
+        st["step_count"][:] = v & 0xFFF
+        st["col"][:] = (v >> 12) & 0xFFF
+        st["terminated"][:] = (v >> 24) & 1
+        st["truncated"][:] = (v >> 25) & 1
+        return st
+    h = emb[:, :40].copy().view(np.uint16).reshape(M, 20)
+    st["input_after"][:] = h[:, 0:8]
+    st["output_after"][:] = h[:, 8:16]
+    st["step_count"][:] = h[:, 16]
+    st["task"][:] = emb[:, 34]
+    st["terminated"][:] = emb[:, 35] & 1
+    st["truncated"][:] = (emb[:, 35] >> 1) & 1
+    st["solved"][:] = (emb[:, 35] >> 2) & 1
+    st["memory"][:] = emb[:, 40:40 + env.word_size]
+    return st

@@ -237,3 +237,41 @@ def test_search_summary_only_and_plan_reuse(ops):
         got = plan.run(H.device_root(env, denv, root))
         for name, _, _ in _abi.SUMMARY_FIELDS:
             H.assert_same_bits(host(got[name]), exp[name], name)
+
+
+# ----------------------------------------------------------------------------- tensor-core network mode
+TENSOR_CASES = [
+    ("deepsea", dict(size=10), 64, dict(num_simulations=32, discount=0.997), dict(beta_max=1.0)),
+    ("deepsea", dict(size=30), 300, dict(num_simulations=64, discount=0.997, exploration=1), dict(beta_max=1.0)),
+    ("subleq", dict(word_size=16), 200, dict(num_simulations=32, discount=0.97), dict(beta_max=1.0)),
+    ("subleq", dict(word_size=20, binary=False), 40, dict(num_simulations=16, discount=0.97), dict(beta_max=0.0)),
+    ("subleq", dict(word_size=256), 20, dict(num_simulations=24, discount=0.97, exploration=1), dict(beta_max=1.0)),
+]
+
+
+@pytest.mark.parametrize("kind,kw,B,cfg_kw,root_kw", TENSOR_CASES)
+def test_search_tensor_mode(ops, kind, kw, B, cfg_kw, root_kw):
+    """mlp_mode=TENSOR (tcgen05 3xTF32): (a) every node's network outputs agree with the fp32 oracle network to 1e-5;
+    (b) the tree is bit-identical to the oracle search replayed with the GPU's own per-node network outputs."""
+    env = H.make_env(kind, seed=11, **kw)
+    net = H.make_net(env, seed=12, fill=0.5)
+    root = H.make_root(env, net, B, seed=13, **root_kw)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(mlp_mode=_abi.MLP_TENSOR, **cfg_kw)
+    got = {k: host(v) for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
+    n, N, A = cfg_kw["num_simulations"], cfg_kw["num_simulations"] + 1, env.num_actions
+    # (a) network accuracy on the expanded nodes
+    emb = got["embeddings"][:, 1:].reshape(B * n, -1)
+    st = H.uncompact(env, emb)
+    ev = O.mlp_forward_states(net, env, st)
+    lg = ev["explore_logits"] if cfg_kw.get("exploration") else ev["exploit_logits"]
+    lg = lg - lg.max(1, keepdims=True)
+    term = st["terminated"].astype(bool)
+    np.testing.assert_allclose(got["children_prior_logits"][:, 1:].reshape(B * n, A), lg, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got["raw_values"][:, 1:].reshape(-1), np.where(term, 0, ev["value"]), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got["raw_values_epistemic_variance"][:, 1:].reshape(-1), np.where(term, 0, ev["ube"]), rtol=1e-5, atol=2e-6)
+    # (b) search logic bit-exact under the GPU's own network outputs
+    replay = dict(states=got["embeddings"], logits=got["children_prior_logits"], value=got["raw_values"], var=got["raw_values_epistemic_variance"])
+    exp = O.search(_abi.default_search_config(**cfg_kw), env, None, root, want_tree=True, replay=replay)
+    assert exp["replay_misses"] == 0
+    assert_tree_equal(exp, got)
