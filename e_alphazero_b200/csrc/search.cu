@@ -62,6 +62,8 @@ struct Tree {
   int32_t* table;
   uint8_t* ds_seen;
   uint8_t* wimg;  // tensor-path weight images (mlp_mode TENSOR)
+  int2* path;     // [max_depth][B] (node, action) per level of the current descent
+  int32_t* path_len;
 };
 
 struct Layout {
@@ -72,7 +74,7 @@ struct Layout {
 
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
-static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, size_t wimg_bytes, Layout* L) {
+static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, size_t wimg_bytes, int max_depth, Layout* L) {
   const size_t nb = (size_t)N * B, nba = nb * A;
   size_t o = 0;
   int i = 0;
@@ -106,6 +108,8 @@ static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, 
   put((size_t)table_len * 4);  // 22 table
   put((size_t)obs_dim);        // 23 ds_seen
   put(wimg_bytes);             // 24 tensor weight images
+  put((size_t)max_depth * B * 8);  // 25 path
+  put((size_t)B * 4);              // 26 path_len
   L->total = o;
 }
 
@@ -138,6 +142,8 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
   t.table = (int32_t*)(p + L.off[22]);
   t.ds_seen = p + L.off[23];
   t.wimg = p + L.off[24];
+  t.path = (int2*)(p + L.off[25]);
+  t.path_len = (int32_t*)(p + L.off[26]);
   return t;
 }
 
@@ -359,82 +365,9 @@ __global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp,
   }
 }
 
-// ------------------------------------------------------------------ simulate (A.3) [+ DeepSea transition]
-template <int G, int J>
-__global__ void __launch_bounds__(128) select_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, const float* __restrict__ beta_in,
-                                                      const uint8_t* __restrict__ invalid) {
-  EAZ_GROUP_PROLOGUE();
-  const float beta = (in_range && beta_in) ? beta_in[b] : 0.0f;
-  float gum[J];
-  bool inval[J];
-  int num_valid = 0;
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    const int a = gl + G * j;
-    gum[j] = (in_range && valid[j]) ? t.gumbel[(size_t)b * t.A + a] : 0.0f;
-    inval[j] = (in_range && valid[j] && invalid) ? (invalid[(size_t)b * t.A + a] != 0) : false;
-    num_valid += (valid[j] && !inval[j]) ? 1 : 0;
-  }
-  num_valid = group_sum_i<G>(num_valid);
-  const int num_considered = min(sp.max_considered, num_valid);
-
-  int node = 0, parent = 0, action = 0, next = 0, depth = 0;
-  bool cont = in_range;
-  while (__any_sync(0xffffffffu, cont)) {
-    Edge<G, J> e;
-    const size_t slot = (size_t)node * t.B + b;
-    load_edges<G, J>(t, slot, gl, cont, e);
-    const float raw = cont ? t.raw_values[slot] : 0.0f;
-    const float raw_var = cont ? t.raw_var[slot] : 0.0f;
-    float cq[J];
-    int sumN, maxN, act;
-    if (depth == 0) {  // gumbel_muzero_root_action_selection (uniform: all trees start at the root together)
-      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, true, cq, sumN, maxN);
-      const int considered_visit = cont ? t.table[(size_t)num_considered * sp.n + min(sumN, sp.n - 1)] : 0;
-      act = root_argmax<G, J>(e, valid, gum, inval, cq, considered_visit, gl);
-    } else {  // gumbel_muzero_interior_action_selection
-      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0, cq, sumN, maxN);
-      float x[J], p[J];
-#pragma unroll
-      for (int j = 0; j < J; ++j) x[j] = __fadd_rn(e.pl[j], cq[j]);
-      group_softmax<G, J>(x, valid, p);
-      const float den = (float)(1 + sumN);
-      float best = -INFINITY;
-      int besti = 1 << 30;
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const float s = valid[j] ? __fsub_rn(p[j], __fdiv_rn((float)e.vis[j], den)) : -INFINITY;
-        const int ia = valid[j] ? gl + G * j : (1 << 30);
-        if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
-      }
-      act = group_argmax<G>(best, besti);
-    }
-    // children_index[node, act]: owned by lane act % G, slot act / G
-    int ci_sel = -1;
-#pragma unroll
-    for (int j = 0; j < J; ++j) if (j == act / G) ci_sel = e.ci[j];
-    const int nxt = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
-    depth += 1;
-    if (cont) {
-      parent = node;
-      action = act;
-      next = nxt;
-      cont = (nxt != -1) && (depth < sp.max_depth);
-      if (cont) node = nxt;
-    }
-  }
-  if (!in_range || gl != 0) return;
-  const int leaf = next == -1 ? sim + 1 : next;  // search.py: node first expanded on simulation i gets index i+1
-  t.parent[b] = parent;
-  t.action[b] = action;
-  t.leaf[b] = leaf;
-  if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
-    uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
-    float reward;
-    st[(size_t)leaf * t.B + b] = deepsea_step(st[(size_t)parent * t.B + b], action, env.size, env.action_map, &reward);
-    t.reward[b] = reward;
-  }
-}
+}  // namespace eaz
+#include "tree_step.cuh"
+namespace eaz {
 
 // ------------------------------------------------------------------ Subleq transition on tree states (context.py:127)
 __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_tree_step_kernel(Tree t, EnvDesc env) {
@@ -490,86 +423,6 @@ __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_tree_step_kernel(Tree t
   for (int i = 0; i < EAZ_SQ_HDR / 8; ++i) reinterpret_cast<uint2*>(cs)[i] = reinterpret_cast<const uint2*>(hdr[e])[i];
   for (int i = 0; i < S - EAZ_SQ_HDR; i += 8) *reinterpret_cast<uint2*>(cs + EAZ_SQ_HDR + i) = *reinterpret_cast<const uint2*>(&sh.base[e][i]);
   t.reward[b] = reward;
-}
-
-// ------------------------------------------------------------------ expand (A.4, context.py:132-154) + backward (A.5)
-template <int G, int J>
-__global__ void __launch_bounds__(128) expand_backward_kernel(Tree t, SearchParams sp, EnvDesc env) {
-  EAZ_GROUP_PROLOGUE();
-  float lg[J];
-  float m = -INFINITY;
-#pragma unroll
-  for (int j = 0; j < J; ++j) {
-    lg[j] = (in_range && valid[j]) ? t.net_logits[(size_t)b * t.A + gl + G * j] : 0.0f;
-    if (valid[j]) m = fmaxf(m, lg[j]);
-  }
-  m = group_max<G>(m);  // context.py:135
-  if (!in_range) return;
-  const int parent = t.parent[b], action = t.action[b], leaf = t.leaf[b];
-  const size_t lslot = (size_t)leaf * t.B + b;
-#pragma unroll
-  for (int j = 0; j < J; ++j)
-    if (valid[j]) t.prior[lslot * t.A + gl + G * j] = __fsub_rn(lg[j], m);  // legal_action_mask is all True (:137)
-  if (gl != 0) return;
-
-  int term;
-  if (env.kind == EAZ_ENV_DEEPSEA) term = EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot]);
-  else term = t.states[lslot * t.S + 35] & EAZ_SQ_FLAG_TERM;
-  const float value = term ? 0.0f : t.net_value[b];  // :140
-  const float var = term ? 0.0f : t.net_ube[b];      // :141
-  float disc = sp.discount;
-  if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
-  if (term) disc = 0.0f;                              // :144
-  const float reward = t.reward[b];                   // :139
-  // update_tree_node
-  t.raw_values[lslot] = value;
-  t.node_values[lslot] = value;
-  t.raw_var[lslot] = var;
-  t.node_var[lslot] = var;
-  t.node_visits[lslot] = t.node_visits[lslot] + 1;
-  t.link[lslot] = make_int2(parent, action);
-  const size_t pe0 = ((size_t)parent * t.B + b) * t.A + action;
-  t.children_index[pe0] = leaf;
-  t.rewards[pe0] = reward;
-  t.discounts[pe0] = disc;
-
-  // backward
-  const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
-  float leaf_value = value, leaf_var = std_backup ? __fsqrt_rn(var) : var;
-  float cur_val = value, cur_var = var;
-  int par = parent, act = action;
-  float r = reward, d = disc;
-  while (true) {
-    const size_t pslot = (size_t)par * t.B + b;
-    const size_t pe = pslot * t.A + act;
-    const int2 up = t.link[pslot];  // prefetch the next hop
-    const float count = (float)t.node_visits[pslot];
-    leaf_value = __fadd_rn(r, __fmul_rn(d, leaf_value));
-    const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(t.node_values[pslot], count), leaf_value), __fadd_rn(count, 1.0f));
-    float pvar;
-    if (std_backup) {
-      leaf_var = __fadd_rn(0.0f, __fmul_rn(fabsf(d), leaf_var));
-      const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(t.node_var[pslot]), count), leaf_var), __fadd_rn(count, 1.0f));
-      pvar = __fmul_rn(ps, ps);
-    } else {
-      leaf_var = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(d, d), leaf_var));
-      pvar = __fdiv_rn(__fadd_rn(__fmul_rn(t.node_var[pslot], count), leaf_var), __fadd_rn(count, 1.0f));
-    }
-    t.node_values[pslot] = pv;
-    t.node_var[pslot] = pvar;
-    t.node_visits[pslot] = (int)count + 1;
-    t.values[pe] = cur_val;
-    t.values_var[pe] = cur_var;
-    t.children_visits[pe] = t.children_visits[pe] + 1;
-    cur_val = pv;
-    cur_var = pvar;
-    if (par == 0) break;
-    act = up.y;
-    par = up.x;
-    const size_t ne = ((size_t)par * t.B + b) * t.A + act;
-    r = t.rewards[ne];
-    d = t.discounts[ne];
-  }
 }
 
 // ------------------------------------------------------------------ policy output (A.1 step 4) + epistemic_summary (A.7)
@@ -684,12 +537,13 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   MlpSource src{nullptr, t.states, t.leaf, env.kind == EAZ_ENV_DEEPSEA ? t.ds_seen : nullptr};
   MlpOutputs mo{{nullptr, nullptr}, t.net_value, t.net_ube, nullptr};
   mo.logits[lhead - EAZ_HEAD_EXPLOIT] = t.net_logits;
-  for (int sim = 0; sim < sp.n; ++sim) {
-    {
-      ProfScope ps(CLS_SELECT, st);
-      select_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env, sim, in->beta, in->invalid_actions);
+  for (int sim = 0; sim <= sp.n; ++sim) {
+    {  // backward of simulation sim-1 fused with the descent of simulation sim
+      ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
+      tree_step_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env, sim, sim > 0, sim < sp.n, in->beta, in->invalid_actions);
     }
-    EAZ_CHECK_LAUNCH("select_kernel");
+    EAZ_CHECK_LAUNCH("tree_step_kernel");
+    if (sim == sp.n) break;
     if (env.kind == EAZ_ENV_SUBLEQ) {
       ProfScope ps(CLS_ENV, st);
       subleq_tree_step_kernel<<<ceil_div(t.B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, 0, st>>>(t, env);
@@ -699,11 +553,6 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
       ProfScope ps(CLS_MLP, st);
       if (int rc = launch_mlp(net, env, src, t.B, mask, mo, mlp_mode, st, tw)) return rc;
     }
-    {
-      ProfScope ps(CLS_EXPAND, st);
-      expand_backward_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env);
-    }
-    EAZ_CHECK_LAUNCH("expand_backward_kernel");
   }
   {
     ProfScope ps(CLS_FINAL, st);
@@ -781,17 +630,18 @@ size_t eaz_search_workspace_bytes(const eaz_search_config* cfg, const eaz_env* e
   if (!cfg || make_env_desc(env, &d) || cfg->batch < 1 || cfg->num_simulations < 1) return 0;
   Layout L;
   make_layout(cfg->batch, cfg->num_simulations + 1, d.num_actions, d.compact_bytes,
-              (cfg->max_num_considered_actions + 1) * cfg->num_simulations, d.obs_dim, wimg_bytes_for(cfg->mlp_mode, d), &L);
+              (cfg->max_num_considered_actions + 1) * cfg->num_simulations, d.obs_dim, wimg_bytes_for(cfg->mlp_mode, d),
+              cfg->max_depth > 0 ? cfg->max_depth : cfg->num_simulations, &L);
   return L.total;
 }
 
 int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env) {
   EnvDesc d;
   if (!cfg || make_env_desc(env, &d)) return -1;
-  const int per_sim = 2 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
+  const int per_sim = 1 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
   const int prep = cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * (d.kind == EAZ_ENV_DEEPSEA ? 2 : 3) : 0;  // weight tiling, 3 heads
   // 2 memsets + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
-  return 2 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1;
+  return 2 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1 + 1;
 }
 
 int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
@@ -801,7 +651,8 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   if (int rc = check_search(cfg, in, out, &env, &net)) return rc;
   const int B = cfg->batch, n = cfg->num_simulations, N = n + 1, A = env.num_actions, S = env.compact_bytes;
   Layout L;
-  make_layout(B, N, A, S, (cfg->max_num_considered_actions + 1) * n, env.obs_dim, wimg_bytes_for(cfg->mlp_mode, env), &L);
+  make_layout(B, N, A, S, (cfg->max_num_considered_actions + 1) * n, env.obs_dim, wimg_bytes_for(cfg->mlp_mode, env),
+              cfg->max_depth > 0 ? cfg->max_depth : n, &L);
   if (!workspace || workspace_bytes < L.total || ((uintptr_t)workspace & 255)) {
     set_error("search workspace must be >= %zu bytes and 256-byte aligned (got %zu)", L.total, workspace_bytes);
     return EAZ_ERR_WORKSPACE;
