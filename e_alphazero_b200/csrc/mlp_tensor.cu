@@ -10,8 +10,10 @@
 //   D3 (TMEM cols   0..Np-1) = h2 @ W3     (thread = row), split hi/lo and written to the A stage in shared memory
 // Weights are pre-split and pre-tiled once per search (tile_weights_kernel) so that a K-chunk of B is one
 // contiguous block fetched with a single 1-D bulk async copy (UBLKCP) that signals an mbarrier.
-// Warp roles: warps 0-3 produce A chunks / run the epilogue (TMEM lane == row), warp 4 issues copies and MMAs.
-// 2-stage pipeline: A(32 KB) + B(64 KB) per stage.
+// Warp roles: warps 0-7 = two producer groups (thread == row; group g produces chunks t % 2 == g, prefetching its
+// next chunk's operands before storing the current one) that also run the epilogue, warp 8 issues the MMAs,
+// warp 9 issues the weight copies.  4-stage mbarrier pipeline of K=16 chunks: A 16 KB + B 32 KB per stage, so
+// three weight copies and three A chunks are in flight behind the MMAs of the current chunk.
 //
 // Accuracy: <= ~1e-6 relative to the fp32 EXACT contract (tests: 1e-5); NOT bit-identical to it, so search
 // parity in this mode is proven by replaying the GPU's per-node network outputs through the oracle.
@@ -21,19 +23,28 @@
 namespace eaz {
 using namespace umma;
 
-int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st);
+int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st, int chunk_k);
 
-constexpr int kTM = 128;                          // rows per CTA
-constexpr int kAStage = 2 * kTM * kChunkK * 4;    // hi + lo
-constexpr int kBStageMax = 2 * 256 * kChunkK * 4; // hi + lo, N = 256
+constexpr int kTM = 128;                       // rows per CTA
+constexpr int kCK = 16;                        // K elements per pipeline stage
+constexpr int kStages = 4;
+constexpr int kSBO = (kCK / 4) * kCoreBytes;   // 8-row group stride inside a chunk tile
+constexpr int kAHalf = kTM * kCK * 4;          // one of hi / lo
+constexpr int kAStage = 2 * kAHalf;
+constexpr int kBStageMax = 2 * 256 * kCK * 4;  // hi + lo, N = 256
 constexpr int kH = 256;
+constexpr int kLayerChunks = kH / kCK;         // chunks of layers 2 and 3
+constexpr int kBitsWordsMax = 40;              // observation bit-strings cached in smem up to 40*32 bits per row
+constexpr int kSimtOutMax = 4;                 // heads with <= 4 outputs run layer 3 on the CUDA cores (see epilogue)
 
 struct TensorSmem {
-  uint64_t full_a[2], full_b[2], empty[2], acc_done[3];
+  uint64_t full_a[kStages], full_b[kStages], empty[kStages], acc_done[3];
   uint32_t tmem_base;
   float bias[3][kH];
+  alignas(16) float w3[kH][kSimtOutMax];    // layer-3 weights of narrow heads
+  alignas(16) float part[kTM][kSimtOutMax];  // partial dot products of producer group 1
 };
-constexpr size_t kTensorSmemBytes = 2 * kAStage + 2 * kBStageMax + sizeof(TensorSmem) + 128;
+constexpr size_t kTensorSmemFixed = (size_t)kStages * (kAStage + kBStageMax) + sizeof(TensorSmem) + 128;
 
 __device__ __forceinline__ int sq_word_g(const uint8_t* st, int row, int ws, int trow) {
   if (row < ws) return st[EAZ_SQ_HDR + row];
@@ -53,20 +64,18 @@ __device__ __forceinline__ int sq_bit_g(int v, int c, int w, int ws, int binary)
   return c == (v == ws ? ws : floormod(v, ws));
 }
 
-// write 32 fp32 values (one K-chunk of this thread's row) into the A stage as hi / lo tiles
-__device__ __forceinline__ void store_a_chunk(uint8_t* stage, int row, const float (&v)[32], bool with_lo) {
-  uint8_t* hi = stage;
-  uint8_t* lo = stage + kTM * kChunkK * 4;
+// write kCK fp32 values (one K-chunk of this thread's row) into the A stage as hi / lo tiles
+__device__ __forceinline__ void store_a_chunk(uint8_t* stage, int row, const float (&v)[kCK], bool with_lo) {
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
+  for (int q = 0; q < kCK / 4; ++q) {
     uint4 h, l;
     split_tf32(v[4 * q + 0], h.x, l.x);
     split_tf32(v[4 * q + 1], h.y, l.y);
     split_tf32(v[4 * q + 2], h.z, l.z);
     split_tf32(v[4 * q + 3], h.w, l.w);
-    const int off = tile_offset(row, q * 4);
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    if (with_lo) *reinterpret_cast<uint4*>(lo + off) = l;
+    const int off = tile_offset_ck<kCK>(row, q * 4);
+    *reinterpret_cast<uint4*>(stage + off) = h;
+    if (with_lo) *reinterpret_cast<uint4*>(stage + kAHalf + off) = l;
   }
 }
 
@@ -75,12 +84,18 @@ struct TensorHeads {
   int head[4];
 };
 
-__global__ void __launch_bounds__(160, 1) mlp_tensor_kernel(NetDesc net, EnvDesc env, MlpSource src, TensorWeights tw, int B, TensorHeads heads,
-                                                            MlpOutputs out) {
+// Optional timeline trace (eaz_debug_set_mlp_trace): CTA (0,0) records clock64() per chunk.
+// layout: [0]=start, [1]=end, [8+t]=MMA thread saw chunk t ready, [264+t]=producer lane 0 of the chunk's group arrived,
+// [520+t]=MMA thread issued+committed chunk t
+static unsigned long long* g_mlp_trace = nullptr;
+
+__global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc env, MlpSource src, TensorWeights tw, int B, TensorHeads heads,
+                                                            MlpOutputs out, int bits_words, unsigned long long* trace) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
-  uint8_t* sB = smem + 2 * kAStage;
-  TensorSmem* sh = reinterpret_cast<TensorSmem*>(sB + 2 * kBStageMax);
+  uint8_t* sB = smem + kStages * kAStage;
+  TensorSmem* sh = reinterpret_cast<TensorSmem*>(sB + kStages * kBStageMax);
+  uint32_t* sbits = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sh) + ((sizeof(TensorSmem) + 15) & ~15));  // [word][row]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int head = heads.head[blockIdx.y];
   const int r0 = blockIdx.x * kTM;
@@ -89,23 +104,52 @@ __global__ void __launch_bounds__(160, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   const bool policy = head >= EAZ_HEAD_EXPLOIT;
   const int nout = policy ? net.A : 1;
   const int np3 = (nout + 15) & ~15;
-  const int n1 = gather ? 0 : tw.k1pad / kChunkK;  // layer-1 chunks
-  const int total = n1 + 16;
+  const int n1 = gather ? 0 : tw.k1pad / kCK;  // layer-1 chunks
+  // Narrow heads (value, UBE, 2-action policy): layer 3 is 256 x nout -- as tcgen05.mma it would cost the same ~100
+  // issue slots as a 256-wide layer for no math, so it runs as fp32 FMAs straight out of the TMEM accumulator instead.
+  const bool simt3 = nout <= kSimtOutMax;
+  const int total = n1 + kLayerChunks + (simt3 ? 0 : kLayerChunks);
+  const bool cached_bits = bits_words > 0;
+  const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
+  if (tr && threadIdx.x == 0) trace[0] = clock64();
 
+  // per-row operands first: their dependent global loads (leaf index -> state -> W1 row) overlap the prologue below
+  const int row = threadIdx.x & (kTM - 1);
+  const bool live = row < nrows;
+  const int b = r0 + (live ? row : 0);
+  const uint8_t* st = nullptr;
+  int cell = 0, trow = 0;
+  if (src.compact) {
+    const size_t slot = src.node_index ? ((size_t)src.node_index[b] * B + b) : (size_t)b;
+    st = src.compact + slot * env.compact_bytes;
+    if (env.kind == EAZ_ENV_DEEPSEA) cell = deepsea_obs_index(*reinterpret_cast<const uint32_t*>(st), env.size);
+    else trow = sq_task_row(st[34]);
+  }
   if (threadIdx.x == 0) {
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&sh->full_a[s], kTM);
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sh->full_a[s], 4);  // one elected arrive per producer warp of the group
       mbar_init(&sh->full_b[s], 1);
       mbar_init(&sh->empty[s], 1);
     }
     for (int i = 0; i < 3; ++i) mbar_init(&sh->acc_done[i], 1);
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < 3 * kH; i += blockDim.x) {
-    const int l = i / kH, j = i % kH;
-    sh->bias[l][j] = (l < 2 || j < nout) ? __ldg(net.b[head][l] + j) : 0.0f;
+  if (threadIdx.x < kH) {  // biases and narrow-head W3 into shared memory: all loads issued before the first store
+    const int j = threadIdx.x;
+    const float b0 = __ldg(net.b[head][0] + j), b1 = __ldg(net.b[head][1] + j);
+    const float b2 = j < nout ? __ldg(net.b[head][2] + j) : 0.0f;
+    float w[kSimtOutMax] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (simt3) {
+#pragma unroll
+      for (int o = 0; o < kSimtOutMax; ++o)
+        if (o < nout) w[o] = __ldg(net.w[head][2] + (size_t)j * nout + o);
+    }
+    sh->bias[0][j] = b0;
+    sh->bias[1][j] = b1;
+    sh->bias[2][j] = b2;
+    if (simt3) *reinterpret_cast<float4*>(sh->w3[j]) = make_float4(w[0], w[1], w[2], w[3]);
   }
-  if (warp == 4) {
+  if (warp == 8) {
     tmem_alloc(&sh->tmem_base, 512);
     tmem_relinquish();
   }
@@ -114,67 +158,127 @@ __global__ void __launch_bounds__(160, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
 
-  if (warp == 4) {
-    // ================= control warp: B copies + MMA issue =================
+  if (warp == 9) {
+    // ================= weight-copy warp =================
     if (lane == 0) {
       for (int t = 0; t < total; ++t) {
-        const int s = t & 1, ph = (t >> 1) & 1;
-        const int layer = t < n1 ? 0 : (t < n1 + 8 ? 1 : 2);
-        const int c = layer == 0 ? t : (layer == 1 ? t - n1 : t - n1 - 8);
-        const int npad = layer == 2 ? np3 : kH;
-        const uint32_t bbytes = (uint32_t)(2 * npad * kChunkK * 4);
+        const int s = t % kStages, ph = (t / kStages) & 1;
+        const int layer = t < n1 ? 0 : (t < n1 + kLayerChunks ? 1 : 2);
+        const int c = layer == 0 ? t : (layer == 1 ? t - n1 : t - n1 - kLayerChunks);
+        const uint32_t bbytes = (uint32_t)(2 * (layer == 2 ? np3 : kH) * kCK * 4);
         mbar_wait(&sh->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&sh->full_b[s], bbytes);
         bulk_g2s(sB + s * kBStageMax, tw.img[head][layer] + (size_t)c * (bbytes / 4), bbytes, &sh->full_b[s]);
-        mbar_wait(&sh->full_b[s], ph);
-        mbar_wait(&sh->full_a[s], ph);
-        tc_fence_after();
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ================= MMA-issue warp =================
+    // Single issuing thread: everything that does not depend on the chunk is hoisted (descriptor high words,
+    // per-stage low words), so a chunk costs two mbarrier waits, 4-6 tcgen05.mma and one commit.
+    if (lane == 0) {
+      const uint32_t desc_hi = (uint32_t)(kSBO >> 4) | (1u << 14);              // SBO [32,46) + version=1 [46,48)
+      const uint32_t lbo_bits = (uint32_t)(kCoreBytes >> 4) << 16;              // LBO [16,30)
+      uint32_t a_lo32[kStages], b_lo32[kStages];
+#pragma unroll
+      for (int s = 0; s < kStages; ++s) {
+        a_lo32[s] = ((smem_u32(sA + s * kAStage) & 0x3FFFFu) >> 4) | lbo_bits;
+        b_lo32[s] = ((smem_u32(sB + s * kBStageMax) & 0x3FFFFu) >> 4) | lbo_bits;
+      }
+      auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+      int t = 0;
+#pragma unroll 1
+      for (int layer = 0; layer < 3; ++layer) {
+        const int nchunks = layer == 0 ? n1 : ((layer == 2 && simt3) ? 0 : kLayerChunks);
+        const int npad = layer == 2 ? np3 : kH;
         const uint32_t idesc = idesc_tf32(kTM, npad);
         const uint32_t d = tmem + (layer == 1 ? 256u : 0u);
-        const uint32_t a_hi = smem_u32(sA + s * kAStage), a_lo = a_hi + kTM * kChunkK * 4;
-        const uint32_t b_hi = smem_u32(sB + s * kBStageMax), b_lo = b_hi + npad * kChunkK * 4;
+        const uint32_t blo_off = (uint32_t)(npad * kCK * 4) >> 4, alo_off = (uint32_t)kAHalf >> 4;
+#pragma unroll 1
+        for (int c = 0; c < nchunks; ++c, ++t) {
+          const int s = t & (kStages - 1), ph = (t / kStages) & 1;
+          mbar_wait(&sh->full_b[s], ph);
+          mbar_wait(&sh->full_a[s], ph);
+          tc_fence_after();
+          if (tr) trace[8 + t] = clock64();
+          uint32_t al = 0, bl = 0;
 #pragma unroll
-        for (int j = 0; j < kKSteps; ++j) {
-          const uint32_t o = j * kKStepBytes;
-          mma_tf32(d, smem_desc(a_hi + o), smem_desc(b_hi + o), idesc, (c | j) != 0);
-          mma_tf32(d, smem_desc(a_hi + o), smem_desc(b_lo + o), idesc, 1);
-          if (layer != 0) mma_tf32(d, smem_desc(a_lo + o), smem_desc(b_hi + o), idesc, 1);  // x is exact in TF32: no lo part
+          for (int q = 0; q < kStages; ++q)
+            if (q == s) { al = a_lo32[q]; bl = b_lo32[q]; }
+#pragma unroll
+          for (int j = 0; j < kCK / 8; ++j) {
+            const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
+            mma_tf32(d, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
+            mma_tf32(d, mk(al + o), mk(bl + blo_off + o), idesc, 1);
+            if (layer != 0) mma_tf32(d, mk(al + alo_off + o), mk(bl + o), idesc, 1);  // x is exact in TF32: no lo part
+          }
+          mma_commit(&sh->empty[s]);
+          if (tr) trace[520 + t] = clock64();
         }
-        mma_commit(&sh->empty[s]);
-        if (t == n1 - 1) mma_commit(&sh->acc_done[0]);
-        if (t == n1 + 7) mma_commit(&sh->acc_done[1]);
-        if (t == total - 1) mma_commit(&sh->acc_done[2]);
+        if (nchunks > 0) mma_commit(&sh->acc_done[layer]);
       }
     }
     __syncwarp();
   } else {
     // ================= worker warps: A producer (thread == row) + epilogue =================
-    const int row = threadIdx.x;
-    const bool live = row < nrows;
-    const int b = r0 + (live ? row : 0);
-    const uint8_t* st = nullptr;
-    int cell = 0, trow = 0;
-    if (src.compact) {
-      const size_t slot = src.node_index ? ((size_t)src.node_index[b] * B + b) : (size_t)b;
-      st = src.compact + slot * env.compact_bytes;
-      if (env.kind == EAZ_ENV_DEEPSEA) cell = deepsea_obs_index(*reinterpret_cast<const uint32_t*>(st), env.size);
-      else trow = sq_task_row(st[34]);
+    if (cached_bits) {  // this row's whole observation as a bit-string in shared memory (Subleq._observe, subleq.py:679-707)
+      const int w = env.obs_cols, ws = env.ws;
+      if (st && env.binary) {  // words are in [0, ws] for any reachable state: v % ws == (v == ws ? 0 : v), no division
+        unsigned long long acc = 0ull;
+        int fill = 0, wd = 0;
+        for (int orow = 0; orow < ws + 32; ++orow) {
+          const int v = sq_word_g(st, orow, ws, trow);
+          const unsigned pat = (v == ws) ? (1u << (w - 1)) : ((unsigned)v & 0xffu);  // subleq.py:88-97
+          if (live) acc |= (unsigned long long)pat << fill;
+          fill += w;
+          if (fill >= 32) {
+            sbits[wd * kTM + row] = (uint32_t)acc;
+            acc >>= 32;
+            fill -= 32;
+            ++wd;
+          }
+        }
+        for (; wd < bits_words; ++wd) {
+          sbits[wd * kTM + row] = (uint32_t)acc;
+          acc >>= 32;
+        }
+      } else {
+        for (int wd = 0; wd < bits_words; ++wd) sbits[wd * kTM + row] = 0u;
+        if (live && st) {  // one-hot rows (subleq.py:51-55)
+          for (int orow = 0, pos = 0; orow < ws + 32; ++orow, pos += w) {
+            const int v = sq_word_g(st, orow, ws, trow);
+            const int k = pos + (v == ws ? ws : floormod(v, ws));
+            sbits[(k >> 5) * kTM + row] |= 1u << (k & 31);
+          }
+        } else if (live) {
+          const uint8_t* o = src.dense + (size_t)b * net.D;
+          for (int k = 0; k < net.D; ++k)
+            if (o[k]) sbits[(k >> 5) * kTM + row] |= 1u << (k & 31);
+        }
+      }
     }
-    const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-    for (int t = 0; t < total; ++t) {
-      const int s = t & 1, ph = (t >> 1) & 1;
-      const int layer = t < n1 ? 0 : (t < n1 + 8 ? 1 : 2);
-      const int c = layer == 0 ? t : (layer == 1 ? t - n1 : t - n1 - 8);
-      float v[32];
+    const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
+    const int grp = warp >> 2;  // two producer groups: group g produces chunks t with t % 2 == g
+    bool waited[2] = {false, false};
+    auto layer_of = [&](int t) { return t < n1 ? 0 : (t < n1 + kLayerChunks ? 1 : 2); };
+    auto chunk_of = [&](int t) { return t < n1 ? t : (t < n1 + kLayerChunks ? t - n1 : t - n1 - kLayerChunks); };
+    // stage 1 of producing chunk t: issue the loads (global gather / TMEM read / bit-string word); raw values in r[]
+    auto load_raw = [&](int t, uint32_t (&r)[kCK]) {
+      const int layer = layer_of(t), c = chunk_of(t);
       if (layer == 0) {  // observation bits of K-chunk c
-        const int k0 = c * kChunkK, w = env.obs_cols, ws = env.ws;
-        if (st) {
+        const int k0 = c * kCK;
+        if (cached_bits) {
+          const uint32_t wd = sbits[(k0 >> 5) * kTM + row] >> (k0 & 31);
+#pragma unroll
+          for (int i = 0; i < kCK; ++i) r[i] = ((wd >> i) & 1u) ? 0x3F800000u : 0u;
+        } else if (st) {
+          const int w = env.obs_cols, ws = env.ws;
           int orow = k0 / w, oc = k0 - orow * w;
           int word = (live && k0 < net.D) ? sq_word_g(st, orow, ws, trow) : 0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
+          for (int i = 0; i < kCK; ++i) {
             const bool in = live && (k0 + i) < net.D;
-            v[i] = (in && sq_bit_g(word, oc, w, ws, env.binary)) ? 1.0f : 0.0f;
+            r[i] = (in && sq_bit_g(word, oc, w, ws, env.binary)) ? 0x3F800000u : 0u;
             if (++oc == w) {
               oc = 0;
               ++orow;
@@ -184,37 +288,66 @@ __global__ void __launch_bounds__(160, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         } else {
           const uint8_t* o = src.dense + (size_t)b * net.D + k0;
 #pragma unroll
-          for (int i = 0; i < 32; ++i) v[i] = (live && k0 + i < net.D && o[i]) ? 1.0f : 0.0f;
+          for (int i = 0; i < kCK; ++i) r[i] = (live && k0 + i < net.D && o[i]) ? 0x3F800000u : 0u;
         }
-      } else if (layer == 1 && gather) {  // h1 = relu(W1[cell] + b1): one-hot observation
-        const float4* wrow = reinterpret_cast<const float4*>(net.w[head][0] + (size_t)cell * kH + c * kChunkK);
+      } else if (layer == 1 && gather) {  // W1[cell] row slice: one-hot observation
+        const uint4* wrow = reinterpret_cast<const uint4*>(net.w[head][0] + (size_t)cell * kH + c * kCK);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 x = live ? __ldg(wrow + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-          v[4 * q + 0] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+        for (int q = 0; q < kCK / 4; ++q) {
+          const uint4 x = live ? __ldg(wrow + q) : make_uint4(0u, 0u, 0u, 0u);
+          r[4 * q + 0] = x.x; r[4 * q + 1] = x.y; r[4 * q + 2] = x.z; r[4 * q + 3] = x.w;
         }
-#pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = live ? fmaxf(__fadd_rn(v[i], sh->bias[0][c * kChunkK + i]), 0.0f) : 0.0f;
-      } else {  // relu(previous accumulator + bias) read back from TMEM
-        if (c == 0) {
+      } else {  // previous layer's accumulator from TMEM
+        if (!waited[layer - 1]) {
           mbar_wait(&sh->acc_done[layer - 1], 0);
           tc_fence_after();
+          waited[layer - 1] = true;
         }
-        uint32_t r[32];
-        tmem_ld32(tmem + lane_base + (layer == 1 ? 0u : 256u) + c * kChunkK, r);
-        tmem_ld_wait();
+        tmem_ld16(tmem + lane_base + (layer == 1 ? 0u : 256u) + c * kCK, r);
+      }
+    };
+    // stage 2: bias + relu (layers 2, 3), split, store into the stage, signal the MMA warp
+    auto finish_store = [&](int t, uint32_t (&r)[kCK]) {
+      const int layer = layer_of(t), c = chunk_of(t), s = t % kStages, ph = (t / kStages) & 1;
+      float v[kCK];
+      if (layer == 0) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = live ? fmaxf(__fadd_rn(__uint_as_float(r[i]), sh->bias[layer - 1][c * kChunkK + i]), 0.0f) : 0.0f;
+        for (int i = 0; i < kCK; ++i) v[i] = __uint_as_float(r[i]);
+      } else {
+        if (!(layer == 1 && gather)) tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < kCK; ++i) v[i] = live ? fmaxf(__fadd_rn(__uint_as_float(r[i]), sh->bias[layer - 1][c * kCK + i]), 0.0f) : 0.0f;
       }
       mbar_wait(&sh->empty[s], ph ^ 1);
       store_a_chunk(sA + s * kAStage, row, v, layer != 0);
       fence_proxy_async();
-      mbar_arrive(&sh->full_a[s]);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->full_a[s]);
+      if (tr && (threadIdx.x & 127) == 0) trace[264 + t] = clock64();
+    };
+    // a chunk may be prefetched while the previous one is still being stored unless it needs an accumulator
+    // that the MMA warp can only finish after that store (first TMEM-sourced chunks of a layer)
+    auto can_prefetch = [&](int t) {
+      const int layer = layer_of(t);
+      if (layer == 0 || (layer == 1 && gather)) return true;
+      return waited[layer - 1];
+    };
+    uint32_t cur[kCK], nxt[kCK];
+    int t = grp;
+    if (t < total) load_raw(t, cur);
+    for (; t < total; t += 2) {
+      const int tn = t + 2;
+      const bool pre = tn < total && can_prefetch(tn);
+      if (pre) load_raw(tn, nxt);
+      finish_store(t, cur);
+      if (tn < total && !pre) load_raw(tn, nxt);
+#pragma unroll
+      for (int i = 0; i < kCK; ++i) cur[i] = nxt[i];
     }
 
     // ---- novelty probe (UBE head): fully_connected.py:83-90
     int seen = 0;
-    if (head == EAZ_HEAD_UBE && live) {
+    if (grp == 0 && head == EAZ_HEAD_UBE && live) {
       if (gather && src.ds_seen) {
         seen = src.ds_seen[cell];
       } else {
@@ -227,6 +360,13 @@ __global__ void __launch_bounds__(160, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
           for (int i = 0; i < L; ++i)
 #pragma unroll
             for (int l = 0; l < 4; ++l) a[l] = xx_round(a[l], (kbeg0 + l * L + i == cell) ? EAZ_XX_ONE : 0u);
+        } else if (cached_bits) {
+          for (int i = 0; i < L; ++i)
+#pragma unroll
+            for (int l = 0; l < 4; ++l) {
+              const int k = kbeg0 + l * L + i;
+              a[l] = xx_round(a[l], ((sbits[(k >> 5) * kTM + row] >> (k & 31)) & 1u) ? EAZ_XX_ONE : 0u);
+            }
         } else if (st) {
           const int w = env.obs_cols, ws = env.ws;
 #pragma unroll
@@ -254,14 +394,52 @@ __global__ void __launch_bounds__(160, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       }
     }
 
-    // ---- layer-3 epilogue
-    mbar_wait(&sh->acc_done[2], 0);
-    tc_fence_after();
+    // ---- layer 3 on the CUDA cores for narrow heads: y = relu(D2 + b2) @ W3, each producer group takes half of K
+    float y3[kSimtOutMax] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (simt3) {
+      if (!waited[1]) {
+        mbar_wait(&sh->acc_done[1], 0);
+        tc_fence_after();
+        waited[1] = true;
+      }
+      const int kbase = grp * (kH / 2);
+#pragma unroll 2
+      for (int kk = 0; kk < kH / 2; kk += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem + lane_base + 256u + kbase + kk, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int k = kbase + kk + i;
+          const float h = fmaxf(__fadd_rn(__uint_as_float(r[i]), sh->bias[1][k]), 0.0f);
+          const float4 w = *reinterpret_cast<const float4*>(sh->w3[k]);
+          y3[0] = __fmaf_rn(h, w.x, y3[0]);
+          y3[1] = __fmaf_rn(h, w.y, y3[1]);
+          y3[2] = __fmaf_rn(h, w.z, y3[2]);
+          y3[3] = __fmaf_rn(h, w.w, y3[3]);
+        }
+      }
+      if (grp == 1) *reinterpret_cast<float4*>(sh->part[row]) = make_float4(y3[0], y3[1], y3[2], y3[3]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps
+      if (grp == 0) {
+        const float4 o = *reinterpret_cast<const float4*>(sh->part[row]);
+        y3[0] = __fadd_rn(y3[0], o.x); y3[1] = __fadd_rn(y3[1], o.y); y3[2] = __fadd_rn(y3[2], o.z); y3[3] = __fadd_rn(y3[3], o.w);
+      }
+    } else {
+      mbar_wait(&sh->acc_done[2], 0);
+      tc_fence_after();
+    }
+    // ---- head epilogue
     float* logits = policy ? out.logits[head - EAZ_HEAD_EXPLOIT] : nullptr;
-    for (int n0 = 0; n0 < np3; n0 += 16) {
+    for (int n0 = 0; grp == 0 && n0 < np3; n0 += 16) {  // group 0 (warps 0-3) owns the outputs
       uint32_t r[16];
-      tmem_ld16(tmem + lane_base + n0, r);
-      tmem_ld_wait();
+      if (simt3) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) r[i] = i < kSimtOutMax ? __float_as_uint(y3[i < kSimtOutMax ? i : 0]) : 0u;
+      } else {
+        tmem_ld16(tmem + lane_base + n0, r);
+        tmem_ld_wait();
+      }
       if (!live) continue;
       if (policy) {
 #pragma unroll
@@ -285,14 +463,16 @@ __global__ void __launch_bounds__(160, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
+  if (warp == 8) tmem_dealloc(tmem, 512);
+  if (tr && threadIdx.x == 0) trace[1] = clock64();
 }
 
 // ---------------------------------------------------------------- host side
+static int k1pad_of(int D) { return (D + kCK - 1) / kCK * kCK; }
+
 size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env) {
-  const int k1pad = (net.D + kChunkK - 1) / kChunkK * kChunkK;
   const int np3 = (net.A + 15) & ~15;
-  const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? 0 : (size_t)k1pad * 2 * kH * 4;
+  const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? 0 : (size_t)k1pad_of(net.D) * 2 * kH * 4;
   const size_t l2 = (size_t)kH * 2 * kH * 4;
   const size_t per_head = l1 + l2 + (size_t)kH * 2 * np3 * 4;
   return 4 * ((per_head + 255) & ~(size_t)255);
@@ -303,7 +483,7 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     set_error("tensor network path needs hidden size %d (got %d); use mlp_mode EXACT", kH, net.H);
     return EAZ_ERR_UNSUPPORTED;
   }
-  const int k1pad = (net.D + kChunkK - 1) / kChunkK * kChunkK;
+  const int k1pad = k1pad_of(net.D);
   const bool has_l1 = env.kind != EAZ_ENV_DEEPSEA;
   const size_t l1 = has_l1 ? (size_t)k1pad * 2 * kH * 4 : 0, l2 = (size_t)kH * 2 * kH * 4;
   const size_t per_head = tensor_weights_bytes(net, env) / 4;
@@ -316,9 +496,9 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     if (!(heads_mask & (1 << h))) continue;
     const int nout = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
     if (has_l1)
-      if (int rc = launch_tile_weights(net.w[h][0], net.D, kH, k1pad, kH, (uint32_t*)p, st)) return rc;
-    if (int rc = launch_tile_weights(net.w[h][1], kH, kH, kH, kH, (uint32_t*)(p + l1), st)) return rc;
-    if (int rc = launch_tile_weights(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, (uint32_t*)(p + l1 + l2), st)) return rc;
+      if (int rc = launch_tile_weights(net.w[h][0], net.D, kH, k1pad, kH, (uint32_t*)p, st, kCK)) return rc;
+    if (int rc = launch_tile_weights(net.w[h][1], kH, kH, kH, kH, (uint32_t*)(p + l1), st, kCK)) return rc;
+    if (int rc = launch_tile_weights(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, (uint32_t*)(p + l1 + l2), st, kCK)) return rc;
   }
   return 0;
 }
@@ -329,16 +509,23 @@ int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& s
   for (int h = 0; h < 4; ++h)
     if (heads_mask & (1 << h)) hl.head[hl.n++] = h;
   if (hl.n == 0 || B == 0) return 0;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTensorSmemBytes);
+  const bool gather = env.kind == EAZ_ENV_DEEPSEA && src.compact != nullptr;
+  int bits_words = gather ? 0 : (tw.k1pad + 31) / 32;
+  if (bits_words > kBitsWordsMax) bits_words = 0;  // too wide for shared memory: bits are derived per chunk instead
+  const size_t smem = kTensorSmemFixed + (size_t)bits_words * kTM * 4;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(mlp_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(kTensorSmemFixed + kBitsWordsMax * kTM * 4));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mlp_tensor_kernel)");
-    attr_set = true;
+    attr_smem = kTensorSmemFixed + kBitsWordsMax * kTM * 4;
   }
   dim3 grid(ceil_div(B, kTM), hl.n);
-  mlp_tensor_kernel<<<grid, 160, kTensorSmemBytes, stream>>>(net, env, src, tw, B, hl, out);
+  mlp_tensor_kernel<<<grid, 320, smem, stream>>>(net, env, src, tw, B, hl, out, bits_words, g_mlp_trace);
   EAZ_CHECK_LAUNCH("mlp_tensor_kernel");
   return 0;
 }
 
 }  // namespace eaz
+
+// Debug hook (not in the public header): device buffer of >= 1024 u64 receiving the timeline of CTA (0,0).
+extern "C" void eaz_debug_set_mlp_trace(unsigned long long* device_buffer) { eaz::g_mlp_trace = device_buffer; }

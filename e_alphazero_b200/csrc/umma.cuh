@@ -28,6 +28,11 @@ constexpr int kKSteps = kChunkK / 8;           // MMAs per chunk per product
 __host__ __device__ inline int tile_offset(int row, int k) {  // bytes, within one [rows x 32] chunk
   return (row >> 3) * kRowGroupBytes + (k >> 2) * kCoreBytes + (row & 7) * 16 + (k & 3) * 4;
 }
+// same layout for a [rows x CK] chunk (CK = 16 or 32): the 8-row group stride (SBO) is CK/4 core matrices
+template <int CK>
+__host__ __device__ inline int tile_offset_ck(int row, int k) {
+  return (row >> 3) * (CK / 4) * kCoreBytes + (k >> 2) * kCoreBytes + (row & 7) * 16 + (k & 3) * 4;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -83,8 +88,8 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 // ---- descriptors
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46),
 // version=1 [46,48), layout_type=SWIZZLE_NONE [61,64)
-__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kCoreBytes >> 4) << 16) | ((uint64_t)(kRowGroupBytes >> 4) << 32) | (1ull << 46);
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t sbo_bytes = kRowGroupBytes) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(kCoreBytes >> 4) << 16) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46);
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor) for kind::tf32, fp32 accumulate, K-major A and B
 __host__ __device__ inline uint32_t idesc_tf32(int M, int N) {

@@ -11,6 +11,7 @@ using namespace umma;
 
 // W[K][N] (row-major, haiku layout) -> per K-chunk image [hi tile | lo tile], each tile [Npad x 32] in the
 // canonical K-major layout of umma.cuh.  out must hold (Kpad/32) * 2 * Npad * 32 words.
+template <int CK>
 __global__ void tile_weights_kernel(const float* __restrict__ W, int K, int N, int Kpad, int Npad, uint32_t* __restrict__ out) {
   const int total = Kpad * Npad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
@@ -18,16 +19,17 @@ __global__ void tile_weights_kernel(const float* __restrict__ W, int K, int N, i
     const float w = (k < K && n < N) ? W[(size_t)k * N + n] : 0.0f;
     uint32_t hi, lo;
     split_tf32(w, hi, lo);
-    const int c = k / kChunkK, kk = k % kChunkK;
-    const size_t base = (size_t)c * 2 * Npad * kChunkK;  // words
-    const int off = tile_offset(n, kk) >> 2;
+    const int c = k / CK, kk = k % CK;
+    const size_t base = (size_t)c * 2 * Npad * CK;  // words
+    const int off = tile_offset_ck<CK>(n, kk) >> 2;
     out[base + off] = hi;
-    out[base + (size_t)Npad * kChunkK + off] = lo;
+    out[base + (size_t)Npad * CK + off] = lo;
   }
 }
 
-int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st) {
-  tile_weights_kernel<<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, out);
+int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st, int chunk_k) {
+  if (chunk_k == 16) tile_weights_kernel<16><<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, out);
+  else tile_weights_kernel<32><<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, out);
   EAZ_CHECK_LAUNCH("tile_weights_kernel");
   return 0;
 }
@@ -140,7 +142,7 @@ extern "C" int eaz_debug_umma_gemm(const float* A, const float* W, float* D, int
   EAZ_CHECK_ARG(A && W && D && wtiles && K > 0 && K % umma::kChunkK == 0 && N >= 1 && N <= 256, "eaz_debug_umma_gemm: bad arguments");
   const int Npad = (N + 15) / 16 * 16;
   cudaStream_t st = (cudaStream_t)stream;
-  if (int rc = launch_tile_weights(W, K, N, K, Npad, (uint32_t*)wtiles, st)) return rc;
+  if (int rc = launch_tile_weights(W, K, N, K, Npad, (uint32_t*)wtiles, st, 32)) return rc;
   const size_t smem = 2 * (2 * 128 * umma::kChunkK * 4) + 2 * (2 * Npad * umma::kChunkK * 4) + sizeof(GemmSmem) + 1024;
   cudaError_t e = cudaFuncSetAttribute(umma_gemm_test_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(umma_gemm_test_kernel)");
