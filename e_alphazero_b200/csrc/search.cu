@@ -48,13 +48,21 @@ struct ProfScope {
   }
 };
 
+// Tree records (array of 32-byte structs, node-major): one or two 16-byte vector accesses fetch everything a
+// level of the descent / backward needs, instead of one scalar access per emctx array.
+// Indices are stored +1 so that an all-zero workspace is the empty tree (0 == UNVISITED / NO_PARENT).
+struct __align__(16) NodeRec {
+  int visits; float val, var; int pad0;       // half 0: backward operands (node_visits, node_values, node_values_epistemic_variance)
+  float raw, rawvar; int parent1, action1;    // half 1: raw_values, raw_values_epistemic_variance, parents+1, action_from_parent+1
+};
+struct __align__(16) EdgeRec {
+  int ci1, vis; float pl, rew;                // half 0: children_index+1, children_visits, children_prior_logits, children_rewards
+  float val, vvar, dis; int pad1;             // half 1: children_values, children_values_epistemic_variance, children_discounts
+};
 struct Tree {
   int B, N, A, S;
-  int32_t* node_visits;
-  float *raw_values, *node_values, *raw_var, *node_var;
-  int2* link;
-  int32_t *children_index, *children_visits;
-  float *prior, *rewards, *discounts, *values, *values_var;
+  NodeRec* nodes;  // [N][B]
+  EdgeRec* edges;  // [N][B][A]
   uint8_t* states;
   // scratch
   float *gumbel, *net_logits, *net_value, *net_ube, *reward;
@@ -80,23 +88,12 @@ static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, 
   int i = 0;
   auto put = [&](size_t bytes) { L->off[i++] = o; o = align_up(o + bytes); };
   L->zero_begin = o;
-  put(nb * 4);   // 0 node_visits
-  put(nb * 4);   // 1 raw_values
-  put(nb * 4);   // 2 node_values
-  put(nb * 4);   // 3 raw_var
-  put(nb * 4);   // 4 node_var
-  put(nba * 4);  // 5 children_visits
-  put(nba * 4);  // 6 prior
-  put(nba * 4);  // 7 rewards
-  put(nba * 4);  // 8 discounts
-  put(nba * 4);  // 9 values
-  put(nba * 4);  // 10 values_var
-  put(nb * S);   // 11 states
+  put(nb * sizeof(NodeRec));   // 0 nodes
+  put(nba * sizeof(EdgeRec));  // 1 edges
+  put(nb * S);                 // 2 states
   L->zero_end = o;
-  L->ones_begin = o;
-  put(nb * 8);   // 12 link
-  put(nba * 4);  // 13 children_index
-  L->ones_end = o;
+  L->ones_begin = L->ones_end = o;
+  for (int k = 3; k < 14; ++k) put(0);  // (slots kept so that the scratch offsets below stay stable)
   put((size_t)B * A * 4);  // 14 gumbel
   put((size_t)B * A * 4);  // 15 net_logits
   put((size_t)B * 4);      // 16 net_value
@@ -117,20 +114,9 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
   uint8_t* p = (uint8_t*)ws;
   Tree t;
   t.B = B; t.N = N; t.A = A; t.S = S;
-  t.node_visits = (int32_t*)(p + L.off[0]);
-  t.raw_values = (float*)(p + L.off[1]);
-  t.node_values = (float*)(p + L.off[2]);
-  t.raw_var = (float*)(p + L.off[3]);
-  t.node_var = (float*)(p + L.off[4]);
-  t.children_visits = (int32_t*)(p + L.off[5]);
-  t.prior = (float*)(p + L.off[6]);
-  t.rewards = (float*)(p + L.off[7]);
-  t.discounts = (float*)(p + L.off[8]);
-  t.values = (float*)(p + L.off[9]);
-  t.values_var = (float*)(p + L.off[10]);
-  t.states = p + L.off[11];
-  t.link = (int2*)(p + L.off[12]);
-  t.children_index = (int32_t*)(p + L.off[13]);
+  t.nodes = (NodeRec*)(p + L.off[0]);
+  t.edges = (EdgeRec*)(p + L.off[1]);
+  t.states = p + L.off[2];
   t.gumbel = (float*)(p + L.off[14]);
   t.net_logits = (float*)(p + L.off[15]);
   t.net_value = (float*)(p + L.off[16]);
@@ -209,23 +195,34 @@ struct Edge {
 };
 
 template <int G, int J>
-__device__ __forceinline__ void load_edges(const Tree& t, size_t node_slot, int gl, bool active, Edge<G, J>& e) {
+__device__ __forceinline__ void load_edges(const Tree& t, unsigned node_slot, int gl, bool active, Edge<G, J>& e) {
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int a = gl + G * j;
     if (active && a < t.A) {
-      const size_t o = node_slot * t.A + a;
-      e.ci[j] = t.children_index[o];
-      e.vis[j] = t.children_visits[o];
-      e.pl[j] = t.prior[o];
-      e.rew[j] = t.rewards[o];
-      e.dis[j] = t.discounts[o];
-      e.val[j] = t.values[o];
-      e.vvar[j] = t.values_var[o];
+      const uint4* p = reinterpret_cast<const uint4*>(t.edges + (size_t)(node_slot * (unsigned)t.A + (unsigned)a));
+      const uint4 h0 = p[0], h1 = p[1];
+      e.ci[j] = (int)h0.x - 1;
+      e.vis[j] = (int)h0.y;
+      e.pl[j] = __uint_as_float(h0.z);
+      e.rew[j] = __uint_as_float(h0.w);
+      e.val[j] = __uint_as_float(h1.x);
+      e.vvar[j] = __uint_as_float(h1.y);
+      e.dis[j] = __uint_as_float(h1.z);
     } else {
       e.ci[j] = -1; e.vis[j] = 0;
       e.pl[j] = 0.0f; e.rew[j] = 0.0f; e.dis[j] = 0.0f; e.val[j] = 0.0f; e.vvar[j] = 0.0f;
     }
+  }
+}
+// raw_values / raw_values_epistemic_variance of a node (second half of its record)
+__device__ __forceinline__ void load_node_raw(const Tree& t, unsigned node_slot, bool active, float& raw, float& raw_var) {
+  raw = 0.0f;
+  raw_var = 0.0f;
+  if (active) {
+    const uint4 h1 = reinterpret_cast<const uint4*>(t.nodes + node_slot)[1];
+    raw = __uint_as_float(h1.x);
+    raw_var = __uint_as_float(h1.y);
   }
 }
 
@@ -355,13 +352,14 @@ __global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp,
     if (!valid[j]) continue;
     const int a = gl + G * j;
     const bool inv = invalid && invalid[(size_t)b * t.A + a];
-    t.prior[(size_t)b * t.A + a] = inv ? EAZ_F32_MIN : __fsub_rn(lg[j], m);  // _mask_invalid_actions (reanalyze.py:16-29)
+    t.edges[(size_t)b * t.A + a].pl = inv ? EAZ_F32_MIN : __fsub_rn(lg[j], m);  // _mask_invalid_actions (reanalyze.py:16-29)
     t.gumbel[(size_t)b * t.A + a] = __fmul_rn(sp.gumbel_scale, gumbel[(size_t)b * t.A + a]);
   }
   if (gl == 0) {
-    t.raw_values[b] = t.node_values[b] = value[b];
-    t.raw_var[b] = t.node_var[b] = var[b];
-    t.node_visits[b] = 1;
+    NodeRec r;
+    r.visits = 1; r.val = value[b]; r.var = var[b]; r.pad0 = 0;
+    r.raw = r.val; r.rawvar = r.var; r.parent1 = 0; r.action1 = 0;
+    t.nodes[b] = r;
   }
 }
 
@@ -445,8 +443,9 @@ __global__ void __launch_bounds__(128) finalize_kernel(Tree t, SearchParams sp, 
     inval[j] = (in_range && valid[j] && invalid) ? (invalid[(size_t)b * t.A + a] != 0) : false;
   }
   Edge<G, J> e;
-  load_edges<G, J>(t, (size_t)b, gl, in_range, e);
-  const float raw = in_range ? t.raw_values[b] : 0.0f, raw_var = in_range ? t.raw_var[b] : 0.0f;
+  load_edges<G, J>(t, (unsigned)(in_range ? b : 0), gl, in_range, e);
+  float raw, raw_var;
+  load_node_raw(t, (unsigned)(in_range ? b : 0), in_range, raw, raw_var);
   float cq[J];
   int sumN, maxN;
   qtransform<G, J>(sp, e, valid, raw, raw_var, beta, (sp.flags & EAZ_FLAG_BETA_FINAL) != 0, cq, sumN, maxN);
@@ -466,8 +465,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(Tree t, SearchParams sp, 
   if (!in_range) return;
   if (gl == 0) {
     out.action[b] = act;
-    if (out.value) out.value[b] = t.node_values[b];
-    if (out.value_std) out.value_std[b] = __fsqrt_rn(t.node_var[b]);
+    if (out.value) out.value[b] = t.nodes[b].val;
+    if (out.value_std) out.value_std[b] = __fsqrt_rn(t.nodes[b].var);
   }
 #pragma unroll
   for (int j = 0; j < J; ++j) {
@@ -495,29 +494,30 @@ __global__ void export_tree_kernel(Tree t, TreeOut o) {
   const size_t stride = (size_t)gridDim.x * blockDim.x, tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   for (size_t i = tid0; i < nb; i += stride) {  // i indexes the OUTPUT [B][N]
     const size_t b = i / t.N, n = i % t.N, s = n * t.B + b;
-    if (o.node_visits) o.node_visits[i] = t.node_visits[s];
-    if (o.raw_values) o.raw_values[i] = t.raw_values[s];
-    if (o.node_values) o.node_values[i] = t.node_values[s];
-    if (o.raw_var) o.raw_var[i] = t.raw_var[s];
-    if (o.node_var) o.node_var[i] = t.node_var[s];
-    const int2 l = t.link[s];
-    if (o.parents) o.parents[i] = l.x;
-    if (o.action_from_parent) o.action_from_parent[i] = l.y;
+    const NodeRec r = t.nodes[s];
+    if (o.node_visits) o.node_visits[i] = r.visits;
+    if (o.raw_values) o.raw_values[i] = r.raw;
+    if (o.node_values) o.node_values[i] = r.val;
+    if (o.raw_var) o.raw_var[i] = r.rawvar;
+    if (o.node_var) o.node_var[i] = r.var;
+    if (o.parents) o.parents[i] = r.parent1 - 1;
+    if (o.action_from_parent) o.action_from_parent[i] = r.action1 - 1;
     if (o.embeddings) {
-      const bool live = t.node_visits[s] > 0;
+      const bool live = r.visits > 0;
       for (int k = 0; k < t.S; ++k) o.embeddings[i * t.S + k] = live ? t.states[s * t.S + k] : 0;
     }
   }
   for (size_t i = tid0; i < nba; i += stride) {  // output [B][N][A]
     const size_t a = i % t.A, bn = i / t.A, b = bn / t.N, n = bn % t.N, s = (n * t.B + b) * t.A + a;
-    if (o.children_index) o.children_index[i] = t.children_index[s];
-    if (o.children_visits) o.children_visits[i] = t.children_visits[s];
-    if (o.prior) o.prior[i] = t.prior[s];
-    if (o.rewards) o.rewards[i] = t.rewards[s];
-    if (o.discounts) o.discounts[i] = t.discounts[s];
-    if (o.values) o.values[i] = t.values[s];
+    const EdgeRec e = t.edges[s];
+    if (o.children_index) o.children_index[i] = e.ci1 - 1;
+    if (o.children_visits) o.children_visits[i] = e.vis;
+    if (o.prior) o.prior[i] = e.pl;
+    if (o.rewards) o.rewards[i] = e.rew;
+    if (o.discounts) o.discounts[i] = e.dis;
+    if (o.values) o.values[i] = e.val;
     if (o.rewards_var) o.rewards_var[i] = 0.0f;  // context.py:149
-    if (o.values_var) o.values_var[i] = t.values_var[s];
+    if (o.values_var) o.values_var[i] = e.vvar;
   }
 }
 
@@ -540,7 +540,8 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   for (int sim = 0; sim <= sp.n; ++sim) {
     {  // backward of simulation sim-1 fused with the descent of simulation sim
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
-      tree_step_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, env, sim, sim > 0, sim < sp.n, in->beta, in->invalid_actions);
+      tree_step_kernel<G, J><<<ceil_div(t.B, 4), 128, 0, st>>>(  // one warp per tree
+          t, sp, env, sim, sim > 0, sim < sp.n, in->beta, in->invalid_actions);
     }
     EAZ_CHECK_LAUNCH("tree_step_kernel");
     if (sim == sp.n) break;
@@ -582,6 +583,10 @@ static int check_search(const eaz_search_config* cfg, const eaz_search_inputs* i
   EAZ_CHECK_ARG(in->prior_logits && in->value && in->value_epistemic_variance && in->gumbel && in->embedding,
                 "search inputs: prior_logits / value / value_epistemic_variance / gumbel / embedding must be non-NULL");
   EAZ_CHECK_ARG(out->action != nullptr, "search outputs: action must be non-NULL");
+  if ((size_t)(cfg->num_simulations + 1) * cfg->batch * env->num_actions >= ((size_t)1 << 31)) {
+    set_error("tree of %d nodes x %d envs x %d actions exceeds 2^31 edges: shard the batch", cfg->num_simulations + 1, cfg->batch, env->num_actions);
+    return EAZ_ERR_UNSUPPORTED;
+  }
   return 0;
 }
 
@@ -640,8 +645,8 @@ int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env
   if (!cfg || make_env_desc(env, &d)) return -1;
   const int per_sim = 1 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
   const int prep = cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * (d.kind == EAZ_ENV_DEEPSEA ? 2 : 3) : 0;  // weight tiling, 3 heads
-  // 2 memsets + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
-  return 2 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1 + 1;
+  // 1 memset + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
+  return 1 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1 + 1;
 }
 
 int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
@@ -664,7 +669,6 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
                   cfg->flags};
   ProfScope* init_scope = new ProfScope(CLS_INIT, st);
   cudaError_t e = cudaMemsetAsync((uint8_t*)workspace + L.zero_begin, 0, L.zero_end - L.zero_begin, st);
-  if (e == cudaSuccess) e = cudaMemsetAsync((uint8_t*)workspace + L.ones_begin, 0xFF, L.ones_end - L.ones_begin, st);
   if (e != cudaSuccess) return cuda_fail(e, "search memset");
   seq_halving_table_kernel<<<ceil_div(cfg->max_num_considered_actions + 1, 32), 32, 0, st>>>(cfg->max_num_considered_actions, n, t.table);
   EAZ_CHECK_LAUNCH("seq_halving_table_kernel");

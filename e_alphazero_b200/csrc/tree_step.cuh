@@ -1,227 +1,216 @@
 // tree_step.cuh -- the per-simulation tree kernel of the search (included by search.cu after the
-// lane-group helpers).  One launch does, for every tree:
-//   part 1  expand (mctx search.py expand / update_tree_node, glue of context.py:132-154) and backward
-//           (A.5) for the leaf selected in the previous launch, using the network outputs;
-//   part 2  simulate (A.3) for the next simulation [+ the DeepSea transition, context.py:127].
-// The descent records its path (node, action per level) so that backward does not chase parent links:
-// all levels' operands are independent loads issued together, and only the short value / variance
-// recurrences are sequential.  For A == 2 (DeepSea) the descent prefetches both children of the current
-// node while the node's scores are being computed, hiding the dependent-load latency of each level.
+// lane-group helpers).  ONE WARP PER TREE.  One launch does, for its tree:
+//   1. expand  (mctx search.py expand / update_tree_node + the glue of context.py:132-154) for the leaf chosen
+//              by the previous launch, using the network outputs;
+//   2. backward (A.5) along the recorded path: lane l owns level l; the value / variance recurrences run as a
+//              short uniform loop over levels (exact op order), the per-level running means (the divisions)
+//              are computed by all levels in parallel;
+//   3. action refresh: every node whose statistics just changed (the path + the new leaf) gets its NEXT action
+//              selection recomputed NOW -- qtransform + seq-halving root score / interior score (A.3, A.6, A.7) --
+//              32/G nodes at a time, G lanes per node, and cached in the node record together with the child it
+//              leads to.  This is the same arithmetic on the same inputs the descent would evaluate, but all
+//              levels are independent here, so they run in parallel instead of one after the other;
+//   4. simulate (A.3) for the next simulation: a pure pointer chase over the cached (action, child) pairs, one
+//              16-byte load per level, recording the path;  [+ the DeepSea transition, context.py:127].
 #pragma once
 
 namespace eaz {
 
-constexpr int kBackChunk = 8;
+// cached selection in NodeRec.pad0: bits 0..7 action, bits 8.. child index + 1 (0 = unvisited)
+__device__ __forceinline__ int pack_next(int action, int child) { return action | ((child + 1) << 8); }
 
 template <int G, int J>
 __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
                                                          const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid) {
-  EAZ_GROUP_PROLOGUE();
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tree
+  if (b >= t.B) return;                                        // warp-uniform
+  const unsigned uB = (unsigned)t.B, uA = (unsigned)t.A, ub = (unsigned)b;
+  constexpr int kLevelsPerRound = 32 / G;
+  const int gl = lane & (G - 1), glev = lane / G;
+  bool valid[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) valid[j] = (gl + G * j) < t.A;
 
-  // ======================================================================== part 1: expand + backward
+  int L = 0, leaf = 0;
   if (do_backward) {
-    float lg[J];
+    // ------------------------------------------------------------------ 1. expand
+    leaf = t.leaf[b];
+    L = t.path_len[b];
+    const unsigned lslot = (unsigned)leaf * uB + ub;
     float m = -INFINITY;
+    for (int a = lane; a < t.A; a += 32) m = fmaxf(m, t.net_logits[ub * uA + a]);
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      lg[j] = (in_range && valid[j]) ? t.net_logits[(size_t)b * t.A + gl + G * j] : 0.0f;
-      if (valid[j]) m = fmaxf(m, lg[j]);
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));  // context.py:135
+    for (int a = lane; a < t.A; a += 32)
+      t.edges[(size_t)(lslot * uA + a)].pl = __fsub_rn(t.net_logits[ub * uA + a], m);  // legal_action_mask is all True (:137)
+    int term;
+    if (env.kind == EAZ_ENV_DEEPSEA) term = EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot]);
+    else term = t.states[(size_t)lslot * t.S + 35] & EAZ_SQ_FLAG_TERM;
+    const float value = term ? 0.0f : t.net_value[b];  // :140
+    const float var = term ? 0.0f : t.net_ube[b];      // :141
+    float disc = sp.discount;
+    if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
+    if (term) disc = 0.0f;                              // :144
+    const int2 last = t.path[(unsigned)(L - 1) * uB + ub];
+    EdgeRec* pe0 = t.edges + (size_t)(((unsigned)last.x * uB + ub) * uA + (unsigned)last.y);
+    if (lane == 0) {
+      // update_tree_node: the leaf's record (visits + 1: a leaf can be re-expanded under a max_depth cut-off)
+      uint4* ln = reinterpret_cast<uint4*>(t.nodes + lslot);
+      const int old_visits = (int)ln[0].x;
+      ln[0] = make_uint4((unsigned)(old_visits + 1), __float_as_uint(value), __float_as_uint(var), 0u);
+      ln[1] = make_uint4(__float_as_uint(value), __float_as_uint(var), (unsigned)(last.x + 1), (unsigned)(last.y + 1));
+      pe0->ci1 = leaf + 1;
+      pe0->rew = t.reward[b];  // :139
+      pe0->dis = disc;
     }
-    m = group_max<G>(m);  // context.py:135
-    if (in_range) {
-      const int leaf = t.leaf[b];
-      const size_t lslot = (size_t)leaf * t.B + b;
-#pragma unroll
-      for (int j = 0; j < J; ++j)
-        if (valid[j]) t.prior[lslot * t.A + gl + G * j] = __fsub_rn(lg[j], m);  // legal_action_mask is all True (:137)
-      if (gl == 0) {
-        int term;
-        if (env.kind == EAZ_ENV_DEEPSEA) term = EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot]);
-        else term = t.states[lslot * t.S + 35] & EAZ_SQ_FLAG_TERM;
-        const float value = term ? 0.0f : t.net_value[b];  // :140
-        const float var = term ? 0.0f : t.net_ube[b];      // :141
-        float disc = sp.discount;
-        if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
-        if (term) disc = 0.0f;                              // :144
-        const int L = t.path_len[b];
-        const int2 last = t.path[(size_t)(L - 1) * t.B + b];
-        // update_tree_node + edge (parent, action)
-        t.raw_values[lslot] = value;
-        t.node_values[lslot] = value;
-        t.raw_var[lslot] = var;
-        t.node_var[lslot] = var;
-        t.node_visits[lslot] = t.node_visits[lslot] + 1;
-        t.link[lslot] = last;
-        const size_t pe0 = ((size_t)last.x * t.B + b) * t.A + last.y;
-        t.children_index[pe0] = leaf;
-        t.rewards[pe0] = t.reward[b];  // :139
-        t.discounts[pe0] = disc;
-        // backward: levels L-1 .. 0, kBackChunk levels of independent loads at a time
-        const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
-        float leaf_value = value, leaf_var = std_backup ? __fsqrt_rn(var) : var;
-        float cur_val = value, cur_var = var;
-        for (int hi = L; hi > 0; hi -= kBackChunk) {
-          const int cnt = min(kBackChunk, hi);
-          int2 pa[kBackChunk];
-#pragma unroll
-          for (int i = 0; i < kBackChunk; ++i)
-            if (i < cnt) pa[i] = t.path[(size_t)(hi - 1 - i) * t.B + b];
-          float nval[kBackChunk], nvar[kBackChunk], rr[kBackChunk], dd[kBackChunk];
-          int nvis[kBackChunk], cvis[kBackChunk];
-#pragma unroll
-          for (int i = 0; i < kBackChunk; ++i)
-            if (i < cnt) {
-              const size_t pslot = (size_t)pa[i].x * t.B + b, pe = pslot * t.A + pa[i].y;
-              nvis[i] = t.node_visits[pslot];
-              nval[i] = t.node_values[pslot];
-              nvar[i] = t.node_var[pslot];
-              cvis[i] = t.children_visits[pe];
-              rr[i] = t.rewards[pe];
-              dd[i] = t.discounts[pe];
-            }
-#pragma unroll
-          for (int i = 0; i < kBackChunk; ++i)
-            if (i < cnt) {
-              const size_t pslot = (size_t)pa[i].x * t.B + b, pe = pslot * t.A + pa[i].y;
-              const float count = (float)nvis[i], d = dd[i];
-              leaf_value = __fadd_rn(rr[i], __fmul_rn(d, leaf_value));
-              const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(nval[i], count), leaf_value), __fadd_rn(count, 1.0f));
-              float pvar;
-              if (std_backup) {
-                leaf_var = __fadd_rn(0.0f, __fmul_rn(fabsf(d), leaf_var));
-                const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(nvar[i]), count), leaf_var), __fadd_rn(count, 1.0f));
-                pvar = __fmul_rn(ps, ps);
-              } else {
-                leaf_var = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(d, d), leaf_var));  // reward variance == 0 (context.py:149)
-                pvar = __fdiv_rn(__fadd_rn(__fmul_rn(nvar[i], count), leaf_var), __fadd_rn(count, 1.0f));
-              }
-              t.node_values[pslot] = pv;
-              t.node_var[pslot] = pvar;
-              t.node_visits[pslot] = nvis[i] + 1;
-              t.values[pe] = cur_val;  // the child's CURRENT mean (already updated)
-              t.values_var[pe] = cur_var;
-              t.children_visits[pe] = cvis[i] + 1;
-              cur_val = pv;
-              cur_var = pvar;
-            }
-        }
+    __syncwarp();
+
+    // ------------------------------------------------------------------ 2. backward (levels L-1 .. 0)
+    const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
+    float lv = value, lvar = std_backup ? __fsqrt_rn(var) : var;  // running leaf_value / leaf variance (or std)
+    float below_val = value, below_var = var;                     // updated mean / variance of the node one level deeper
+    for (int hi = L; hi > 0; hi -= 32) {                          // rounds of 32 levels, deepest first
+      const int lo = max(hi - 32, 0), cnt = hi - lo;
+      const int lev = lo + lane;                                  // this lane's level
+      const bool have = lane < cnt;
+      int2 pa = make_int2(0, 0);
+      uint4 nrec = make_uint4(0u, 0u, 0u, 0u);
+      float rr = 0.0f, dd = 0.0f;
+      int cvis = 0;
+      unsigned pslot = 0;
+      EdgeRec* pe = nullptr;
+      if (have) {
+        pa = t.path[(unsigned)lev * uB + ub];
+        pslot = (unsigned)pa.x * uB + ub;
+        pe = t.edges + (size_t)(pslot * uA + (unsigned)pa.y);
+        nrec = reinterpret_cast<const uint4*>(t.nodes + pslot)[0];
+        cvis = pe->vis;
+        rr = pe->rew;
+        dd = pe->dis;
       }
+      // the recurrences: a uniform loop over this round's levels, deepest first, in the reference's op order
+      float my_lv = 0.0f, my_lvar = 0.0f;
+      for (int i = cnt - 1; i >= 0; --i) {
+        const float r = __shfl_sync(0xffffffffu, rr, i), d = __shfl_sync(0xffffffffu, dd, i);
+        lv = __fadd_rn(r, __fmul_rn(d, lv));
+        lvar = std_backup ? __fadd_rn(0.0f, __fmul_rn(fabsf(d), lvar)) : __fadd_rn(0.0f, __fmul_rn(__fmul_rn(d, d), lvar));
+        if (lane == i) { my_lv = lv; my_lvar = lvar; }
+      }
+      // running means, all levels in parallel
+      const int nvis = (int)nrec.x;
+      const float nval = __uint_as_float(nrec.y), nvar = __uint_as_float(nrec.z);
+      const float count = (float)nvis;
+      const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(nval, count), my_lv), __fadd_rn(count, 1.0f));
+      float pvar;
+      if (std_backup) {
+        const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(nvar), count), my_lvar), __fadd_rn(count, 1.0f));
+        pvar = __fmul_rn(ps, ps);
+      } else {
+        pvar = __fdiv_rn(__fadd_rn(__fmul_rn(nvar, count), my_lvar), __fadd_rn(count, 1.0f));
+      }
+      // children_values[parent, a] = the child's CURRENT (already updated) mean: one level deeper
+      float cval = __shfl_down_sync(0xffffffffu, pv, 1), cvarr = __shfl_down_sync(0xffffffffu, pvar, 1);
+      if (lane == cnt - 1) { cval = below_val; cvarr = below_var; }
+      if (have) {
+        reinterpret_cast<uint4*>(t.nodes + pslot)[0] = make_uint4((unsigned)(nvis + 1), __float_as_uint(pv), __float_as_uint(pvar), 0u);
+        pe->vis = cvis + 1;
+        *reinterpret_cast<float2*>(&pe->val) = make_float2(cval, cvarr);
+      }
+      below_val = __shfl_sync(0xffffffffu, pv, 0);
+      below_var = __shfl_sync(0xffffffffu, pvar, 0);
     }
-    __syncwarp();  // lane 0's tree updates are visible to the group's lanes below
+    __syncwarp();
   }
   if (!do_select) return;
 
-  // ======================================================================== part 2: simulate
-  const float beta = (in_range && beta_in) ? beta_in[b] : 0.0f;
-  float gum[J];
-  bool inval[J];
-  int num_valid = 0;
+  // -------------------------------------------------------------------- 3. refresh the cached selections
+  // nodes: path levels 0..L-1 and the new leaf (index L); before the first simulation only the root.
+  {
+    const float beta = beta_in ? beta_in[b] : 0.0f;
+    const int nrefresh = do_backward ? L + 1 : 1;
+    for (int base = 0; base < nrefresh; base += kLevelsPerRound) {
+      const int lev = base + glev;
+      const bool act_on = lev < nrefresh;
+      int node = 0;
+      if (act_on && do_backward) node = lev < L ? t.path[(unsigned)lev * uB + ub].x : leaf;
+      const unsigned slot = (unsigned)node * uB + ub;
+      Edge<G, J> e;
+      float raw, raw_var;
+      load_edges<G, J>(t, slot, gl, act_on, e);
+      load_node_raw(t, slot, act_on, raw, raw_var);
+      float cq[J];
+      int sumN, maxN, act;
+      const bool is_root = act_on && node == 0;
+      const bool use_beta = is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0;
+      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, use_beta, cq, sumN, maxN);
+      if (__any_sync(0xffffffffu, is_root)) {  // gumbel_muzero_root_action_selection (node 0 is level 0 of round 0)
+        float gum[J];
+        bool inval[J];
+        int num_valid = 0;
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    const int a = gl + G * j;
-    gum[j] = (in_range && valid[j]) ? t.gumbel[(size_t)b * t.A + a] : 0.0f;
-    inval[j] = (in_range && valid[j] && invalid) ? (invalid[(size_t)b * t.A + a] != 0) : false;
-    num_valid += (valid[j] && !inval[j]) ? 1 : 0;
-  }
-  num_valid = group_sum_i<G>(num_valid);
-  const int num_considered = min(sp.max_considered, num_valid);
-  constexpr bool kPrefetch = (G == 2 && J == 1);
-
-  int node = 0, parent = 0, action = 0, next = 0, depth = 0, mylen = 0;
-  bool cont = in_range;
-  Edge<G, J> e;
-  float raw = 0.0f, raw_var = 0.0f;
-  if (kPrefetch) {
-    load_edges<G, J>(t, (size_t)b, gl, cont, e);
-    raw = cont ? t.raw_values[b] : 0.0f;
-    raw_var = cont ? t.raw_var[b] : 0.0f;
-  }
-  while (__any_sync(0xffffffffu, cont)) {
-    Edge<G, J> ec[2];
-    float craw[2] = {0.0f, 0.0f}, cvar[2] = {0.0f, 0.0f};
-    int child[2] = {-1, -1};
-    if (kPrefetch) {  // both children of `node`, fetched while its scores are computed
-      const int other = __shfl_xor_sync(0xffffffffu, e.ci[0], 1);
-      child[0] = gl == 0 ? e.ci[0] : other;
-      child[1] = gl == 0 ? other : e.ci[0];
-      const bool deeper = cont && (depth + 1 < sp.max_depth);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const bool go = deeper && child[c] != -1;
-        const size_t cslot = (size_t)(go ? child[c] : 0) * t.B + b;
-        load_edges<G, J>(t, cslot, gl, go, ec[c]);
-        craw[c] = go ? t.raw_values[cslot] : 0.0f;
-        cvar[c] = go ? t.raw_var[cslot] : 0.0f;
+        for (int j = 0; j < J; ++j) {
+          const int a = gl + G * j;
+          gum[j] = (is_root && valid[j]) ? t.gumbel[ub * uA + a] : 0.0f;
+          inval[j] = (is_root && valid[j] && invalid) ? (invalid[ub * uA + a] != 0) : false;
+          num_valid += (valid[j] && !inval[j]) ? 1 : 0;
+        }
+        num_valid = group_sum_i<G>(num_valid);
+        const int num_considered = min(sp.max_considered, num_valid);
+        const int considered_visit = is_root ? t.table[num_considered * sp.n + min(sumN, sp.n - 1)] : 0;
+        act = root_argmax<G, J>(e, valid, gum, inval, cq, considered_visit, gl);
       }
-    } else {
-      const size_t slot = (size_t)node * t.B + b;
-      load_edges<G, J>(t, slot, gl, cont, e);
-      raw = cont ? t.raw_values[slot] : 0.0f;
-      raw_var = cont ? t.raw_var[slot] : 0.0f;
-    }
-    float cq[J];
-    int sumN, maxN, act;
-    if (depth == 0) {  // gumbel_muzero_root_action_selection (uniform: all trees start at the root together)
-      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, true, cq, sumN, maxN);
-      const int considered_visit = cont ? t.table[(size_t)num_considered * sp.n + min(sumN, sp.n - 1)] : 0;
-      act = root_argmax<G, J>(e, valid, gum, inval, cq, considered_visit, gl);
-    } else {  // gumbel_muzero_interior_action_selection
-      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0, cq, sumN, maxN);
-      float x[J], p[J];
+      int act_i;
+      {  // gumbel_muzero_interior_action_selection
+        float x[J], p[J];
 #pragma unroll
-      for (int j = 0; j < J; ++j) x[j] = __fadd_rn(e.pl[j], cq[j]);
-      group_softmax<G, J>(x, valid, p);
-      const float den = (float)(1 + sumN);
-      float best = -INFINITY;
-      int besti = 1 << 30;
+        for (int j = 0; j < J; ++j) x[j] = __fadd_rn(e.pl[j], cq[j]);
+        group_softmax<G, J>(x, valid, p);
+        const float den = (float)(1 + sumN);
+        float best = -INFINITY;
+        int besti = 1 << 30;
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const float s = valid[j] ? __fsub_rn(p[j], __fdiv_rn((float)e.vis[j], den)) : -INFINITY;
-        const int ia = valid[j] ? gl + G * j : (1 << 30);
-        if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
+        for (int j = 0; j < J; ++j) {
+          const float s = valid[j] ? __fsub_rn(p[j], __fdiv_rn((float)e.vis[j], den)) : -INFINITY;
+          const int ia = valid[j] ? gl + G * j : (1 << 30);
+          if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
+        }
+        act_i = group_argmax<G>(best, besti);
       }
-      act = group_argmax<G>(best, besti);
-    }
-    int nxt;
-    if (kPrefetch) {
-      nxt = child[act & 1];
-    } else {  // children_index[node, act]: owned by lane act % G, slot act / G
+      if (!is_root) act = act_i;
+      // children_index[node, act]: owned by lane act % G of the group, slot act / G
       int ci_sel = -1;
 #pragma unroll
       for (int j = 0; j < J; ++j) if (j == act / G) ci_sel = e.ci[j];
-      nxt = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
+      const int child = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
+      if (act_on && gl == 0) t.nodes[slot].pad0 = pack_next(act, child);
     }
-    if (cont) {
-      if (gl == 0) t.path[(size_t)depth * t.B + b] = make_int2(node, act);
-      parent = node;
-      action = act;
-      next = nxt;
-      mylen = depth + 1;
-    }
-    depth += 1;
-    if (cont) {
-      cont = (nxt != -1) && (depth < sp.max_depth);
-      if (cont) {
-        node = nxt;
-        if (kPrefetch) {
-          e = ec[act & 1];
-          raw = craw[act & 1];
-          raw_var = cvar[act & 1];
-        }
-      }
-    }
+    __syncwarp();
   }
-  if (!in_range || gl != 0) return;
-  const int leaf = next == -1 ? sim + 1 : next;  // search.py: node first expanded on simulation i gets index i+1
-  t.path_len[b] = mylen;  // levels recorded for this tree; the last one is the leaf's parent
-  t.parent[b] = parent;
-  t.action[b] = action;
-  t.leaf[b] = leaf;
-  if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
-    uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
-    float reward;
-    st[(size_t)leaf * t.B + b] = deepsea_step(st[(size_t)parent * t.B + b], action, env.size, env.action_map, &reward);
-    t.reward[b] = reward;
+
+  // -------------------------------------------------------------------- 4. simulate: follow the cached selections
+  if (lane == 0) {
+    int node = 0, depth = 0, action, child;
+    while (true) {
+      const int nx = t.nodes[(unsigned)node * uB + ub].pad0;
+      action = nx & 0xff;
+      child = (nx >> 8) - 1;
+      t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
+      depth += 1;
+      if (child < 0 || depth >= sp.max_depth) break;
+      node = child;
+    }
+    const int new_leaf = child < 0 ? sim + 1 : child;  // search.py: node first expanded on simulation i gets index i+1
+    t.path_len[b] = depth;
+    t.parent[b] = node;
+    t.action[b] = action;
+    t.leaf[b] = new_leaf;
+    if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
+      uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
+      float reward;
+      st[(unsigned)new_leaf * uB + ub] = deepsea_step(st[(unsigned)node * uB + ub], action, env.size, env.action_map, &reward);
+      t.reward[b] = reward;
+    }
   }
 }
 

@@ -67,7 +67,7 @@ def test_argument_validation_without_gpu(lib):
     assert lib.eaz_xxhash_indices(None, 1, 25, 24, None, None) == _abi.EAZ_ERR_INVALID_ARG  # hashes.py:210
     cfg = _abi.default_search_config(batch=4096, num_simulations=64)
     assert lib.eaz_search_workspace_bytes(C.byref(cfg), C.byref(env)) > 4096 * 65 * (7 * 2 * 4 + 7 * 4)
-    assert lib.eaz_search_num_launches(C.byref(cfg), C.byref(env)) == 2 + 4 + 2 * 64 + 2
+    assert lib.eaz_search_num_launches(C.byref(cfg), C.byref(env)) == 1 + 4 + 2 * 64 + 2
 
 
 def test_ops_fail_loudly_without_cuda():
