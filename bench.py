@@ -208,7 +208,8 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         dist.broadcast(net.binary_set, 0)
 
     # shard = this rank's envs (weak scaling: B per GPU fixed); directed exploration with beta = linspace(0,1,B) (UBE on)
-    runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=100 + rank)
+    runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=100 + rank,
+                            use_graph=not args.no_graph)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     states = ops.env_init(env, B, task_ids=torch.ones(B, dtype=torch.int32, device=dev) if kind == "subleq" else None, device=dev)
     A = env.num_actions
@@ -232,6 +233,8 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
 
     for _ in range(max(args.warmup, 3)):
         states, _ = one_step(states)
+    if runner.use_graph:  # step the graph's own state buffers in place from here on (no copies in / out)
+        states = runner.static_states()
     torch.cuda.synchronize()
 
     # ---- timed region: exactly K steps, CUDA events per step, L2 flushed between steps (outside the events)
@@ -268,7 +271,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
     res_names = ("action", "root_value", "root_epistemic_std", "value_prediction", "ube_prediction", "q_values_epistemic_variance")
     h2d = sum(v.numel() * v.element_size() for v in host_in.values())
     e2e_ms, d2h = 0.0, 0
-    dstates = {k: torch.empty_like(states[k]) for k in fields}
+    dstates = runner.static_states() if runner.use_graph else {k: torch.empty_like(states[k]) for k in fields}
     host_res = None
     for i in range(args.steps + 2):
         flush.zero_()
@@ -353,7 +356,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "envs_per_gpu": B, "num_simulations": n, "mlp_mode": "exact_fp32" if args.mlp_mode == 0 else "tensor",
-                       "l2": "flushed between timed steps (256 MiB write)", "directed_exploration": True, "beta": "linspace(0,1,B)",
+                       "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": not args.no_graph, "directed_exploration": True, "beta": "linspace(0,1,B)",
                        "multi_gpu": "envs sharded per rank, params broadcast once, compact trajectory all-gather per step" if world > 1 else "single GPU"},
             "simulations_per_s": value * n, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
@@ -370,8 +373,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--mlp-mode", type=int, default=0)
+    ap.add_argument("--mlp-mode", type=int, default=1, help="0 = fp32 FMA chains (bit-exact contract), 1 = tcgen05 3xTF32 (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")
     args = ap.parse_args()
     kind, kw, B, n, gamma, desc = WORKLOADS[args.workload]
     if args.impl == "reference":

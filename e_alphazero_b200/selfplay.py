@@ -26,7 +26,7 @@ class SelfplayRunner:
 
     def __init__(self, env_spec: ops.EnvSpec, net: ops.FcParams, batch: int, num_simulations: int, discount: float,
                  exploration_beta: float = 0.0, directed_exploration: bool = False, rescale_values: bool = True,
-                 mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0):
+                 mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0, use_graph: bool = False):
         torch = require_cuda()
         self.env, self.net, self.B, self.device = env_spec, net, batch, device
         self.directed = directed_exploration
@@ -40,6 +40,11 @@ class SelfplayRunner:
         self.A = env_spec.num_actions
         # launches per step: compact+mlp (root forward), search, env step
         self.launches_per_step = 2 + self.plan.num_launches + 1
+        # CUDA graph of one whole step (root forward -> search -> env step): the launch sequence is fixed and nothing
+        # synchronises or allocates, so it is captured once and replayed; the noise is drawn outside the graph.
+        self.use_graph = use_graph
+        self._graph = None
+        self._static = None
 
     def draw_gumbel(self):
         torch = require_cuda()
@@ -48,6 +53,46 @@ class SelfplayRunner:
 
     def step(self, states: dict, gumbel=None, task_ids=None):
         """states: device state dict (updated in place).  Returns (states, SelfplayOutput)."""
+        torch = require_cuda()
+        if self.use_graph:
+            return self._step_graph(states, gumbel, task_ids)
+        return self._step_eager(states, gumbel, task_ids)
+
+    def _step_graph(self, states, gumbel, task_ids):
+        torch = require_cuda()
+        if gumbel is None:
+            gumbel = self.draw_gumbel()
+        if task_ids is None and self.env.kind == _abi.ENV_SUBLEQ:
+            idx = torch.randint(0, self.tasks.numel(), (self.B,), device=self.device, generator=self.gen)
+            task_ids = self.tasks[idx]
+        if self._graph is None:
+            st = {k: v.clone() for k, v in states.items()}
+            sg = gumbel.clone()
+            stt = task_ids.clone() if task_ids is not None else None
+            self._step_eager({k: v.clone() for k, v in st.items()}, sg, stt)  # warm-up: one-time attribute setup / allocations
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                _, out = self._step_eager(st, sg, stt)
+            self._graph, self._static = g, (st, sg, stt, out)
+        st, sg, stt, out = self._static
+        for k in st:
+            if states[k].data_ptr() != st[k].data_ptr():
+                st[k].copy_(states[k])
+        sg.copy_(gumbel)
+        if stt is not None:
+            stt.copy_(task_ids)
+        self._graph.replay()
+        for k in st:
+            if states[k].data_ptr() != st[k].data_ptr():
+                states[k].copy_(st[k])
+        return states, out
+
+    def static_states(self):
+        """The graph's own state buffers (step them in place to avoid the copies in/out)."""
+        return self._static[0] if self._static else None
+
+    def _step_eager(self, states: dict, gumbel=None, task_ids=None):
         torch = require_cuda()
         ev = ops.mlp_forward_states(self.net, self.env, states)  # selfplay.py:89
         logits = ev["explore_logits"] if self.directed else ev["exploit_logits"]  # :93-95
