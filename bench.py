@@ -175,7 +175,7 @@ def run_reference(args, kind, kw, B, n, gamma, desc):
                              "sample": f"{B_sample} envs per step x {args.steps} steps ({n} simulations each)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "simulations_per_s": value * n, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 # ============================================================================== B200 arm
@@ -209,7 +209,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
 
     # shard = this rank's envs (weak scaling: B per GPU fixed); directed exploration with beta = linspace(0,1,B) (UBE on)
     runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=100 + rank,
-                            use_graph=not args.no_graph)
+                            use_graph=not args.no_graph, fused_root=not args.no_fused_root)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     states = ops.env_init(env, B, task_ids=torch.ones(B, dtype=torch.int32, device=dev) if kind == "subleq" else None, device=dev)
     A = env.num_actions
@@ -356,17 +356,35 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "envs_per_gpu": B, "num_simulations": n, "mlp_mode": "exact_fp32" if args.mlp_mode == 0 else "tensor",
-                       "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": not args.no_graph, "directed_exploration": True, "beta": "linspace(0,1,B)",
+                       "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": not args.no_graph, "fused_root": not args.no_fused_root, "directed_exploration": True, "beta": "linspace(0,1,B)",
                        "multi_gpu": "envs sharded per rank, params broadcast once, compact trajectory all-gather per step" if world > 1 else "single GPU"},
             "simulations_per_s": value * n, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": runner.launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict) -> None:
+    """The ONE JSON line goes to the process's real stdout; everything else (NCCL banners, warnings) was moved to stderr."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # C-level stdout (e.g. "NCCL version ...") -> stderr
+    sys.stdout = os.fdopen(os.dup(2), "w")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -375,6 +393,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mlp-mode", type=int, default=1, help="0 = fp32 FMA chains (bit-exact contract), 1 = tcgen05 3xTF32 (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fused-root", action="store_true", help="evaluate the root network with a separate eaz_mlp_forward_states call")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")
     args = ap.parse_args()
     kind, kw, B, n, gamma, desc = WORKLOADS[args.workload]

@@ -138,9 +138,12 @@ SEARCH_OUTPUT_FIELDS = [
     ("children_rewards_epistemic_variance", "f32", "BNA"),
     ("children_values_epistemic_variance", "f32", "BNA"),
     ("embeddings", "u8", "BNS"),
+    ("root_value", "f32", "B"),
+    ("root_ube", "f32", "B"),
 ]
 SUMMARY_FIELDS = [f for f in SEARCH_OUTPUT_FIELDS[:8]]
-TREE_FIELDS = [f for f in SEARCH_OUTPUT_FIELDS[8:]]
+TREE_FIELDS = [f for f in SEARCH_OUTPUT_FIELDS[8:24]]
+ROOT_FIELDS = [f for f in SEARCH_OUTPUT_FIELDS[24:]]  # fused-root mode
 
 
 class EazSearchOutputs(C.Structure):

@@ -163,17 +163,25 @@ struct SubleqSim {
   int cycles;
   int correct;
 };
+// Words are < 256, so a test vector (8 words) is one 64-bit register: byte i = element i.
+__device__ __forceinline__ unsigned long long sq_pack_vec(const SubleqVec& v, int ws) {
+  unsigned long long p = 0ull;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    if (i < v.len) p |= (unsigned long long)(unsigned)floormod(v.v[i], ws) << (8 * i);
+  return p;
+}
+// The interpreter keeps the input as (packed vector, cursor) instead of shifting an array, the output as
+// (packed bytes, count), and the "output == expected" test as `no mismatch so far && count == expected length`
+// (a written word is < ws, so it can never equal the pad token ws: the arrays are equal iff exactly the expected
+// words were written and all matched).  Results are expanded into SubleqSim at the end.
 template <typename MemT>
 __device__ __forceinline__ void subleq_simulate(int ws, MemT* mem, int trow, int k, SubleqSim& r) {
   const int AMAX = ws - 4, AIN = ws - 3, AOUT = ws - 2;
-  int tout[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    r.in[i] = sq_test_in(trow, k, i, ws);
-    tout[i] = sq_test_out(trow, k, i, ws);
-    r.out[i] = ws;  // :382
-  }
-  int out_cur = 0, cur = 0, bytes = 0, cycles = 0, halt = 0, err = 0;
+  const int in_len = c_sq_in[trow][k].len, out_len = c_sq_out[trow][k].len;
+  const unsigned long long tin = sq_pack_vec(c_sq_in[trow][k], ws), tout = sq_pack_vec(c_sq_out[trow][k], ws);
+  unsigned long long outp = 0ull;
+  int in_cur = 0, out_cur = 0, cur = 0, bytes = 0, cycles = 0, halt = 0, err = 0, bad = 0;
   while (!err && !halt && cycles < EAZ_SUBLEQ_MAX_CYCLES) {  // :297-299
     cycles += 1;
     if (cur + 2 >= ws) {  // :364-370
@@ -182,45 +190,42 @@ __device__ __forceinline__ void subleq_simulate(int ws, MemT* mem, int trow, int
     }
     bytes = max(bytes, cur + 3);  // :311
     const int a = mem[cur], b = mem[cur + 1], c = mem[cur + 2];
+    const int have_in = in_cur < in_len;  // input_state[0] < word_size (:197,218)
+    const int in0 = have_in ? (int)((tin >> (8 * in_cur)) & 0xffull) : 0;
     int va = 0, vb = 0, acc = 0, e = 0;
     if (a <= AMAX) va = mem[a];
-    else if (a == AIN) { if (r.in[0] >= ws) e = 1; else { va = r.in[0]; acc = 1; } }
+    else if (a == AIN) { if (!have_in) e = 1; else { va = in0; acc = 1; } }
     if (b <= AMAX) vb = mem[b];
-    else if (b == AIN) { if (r.in[0] >= ws) e = 1; else { vb = r.in[0]; acc = 1; } }
-    const int value = floormod(va - vb, ws);  // :322
-    int modified = 0;
+    else if (b == AIN) { if (!have_in) e = 1; else { vb = in0; acc = 1; } }
+    int value = va - vb;  // both in [0, ws): floor-mod is one conditional add (:322)
+    if (value < 0) value += ws;
+    int modified = 0, last_ok = 1;
     if (a <= AMAX) mem[a] = (MemT)value;
     else if (a == AOUT) {
       if (out_cur >= 8) e = 1;
       else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) if (i == out_cur) r.out[i] = value;
+        last_ok = (out_cur < out_len) && (value == (int)((tout >> (8 * out_cur)) & 0xffull));
+        outp |= (unsigned long long)(unsigned)value << (8 * out_cur);
         out_cur += 1;
         modified = 1;
+        bad |= !last_ok;
       }
     }
     const int jump = (value == 0) || (2 * value >= ws);  // :329
     cur = jump ? c : cur + 3;
-    if (acc) {  // :333-338
-#pragma unroll
-      for (int i = 0; i < 7; ++i) r.in[i] = r.in[i + 1];
-      r.in[7] = ws;
-    }
-    int all_eq = 1, last_ok = 1;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      all_eq &= (r.out[i] == tout[i]);
-      if (i == out_cur - 1) last_ok = (r.out[i] == tout[i]);
-    }
+    in_cur += acc;  // :333-338 (at most one word per instruction)
+    const int all_eq = !bad && out_cur == out_len;
     halt = ((((jump ? 1 : 0) & c) > AMAX) ? 1 : 0) | all_eq;  // :340-345, precedence as written
     err = e | (modified && !last_ok);                         // :346-350
   }
-  int all_eq = 1;
 #pragma unroll
-  for (int i = 0; i < 8; ++i) all_eq &= (r.out[i] == tout[i]);
+  for (int i = 0; i < 8; ++i) {
+    r.in[i] = (in_cur + i < in_len) ? (int)((tin >> (8 * (in_cur + i))) & 0xffull) : ws;
+    r.out[i] = i < out_cur ? (int)((outp >> (8 * i)) & 0xffull) : ws;
+  }
   r.bytes_used = bytes;
   r.cycles = cycles;
-  r.correct = (!err) && all_eq;  // :394
+  r.correct = (!err) && !bad && out_cur == out_len;  // :394
 }
 
 __device__ __forceinline__ float subleq_reward(int reward_fn, int solved, int bytes_used) {

@@ -336,7 +336,8 @@ __device__ __forceinline__ int root_argmax(const Edge<G, J>& e, const bool (&val
 template <int G, int J>
 __global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp, const float* __restrict__ prior_logits,
                                                          const float* __restrict__ value, const float* __restrict__ var,
-                                                         const float* __restrict__ gumbel, const uint8_t* __restrict__ invalid) {
+                                                         const float* __restrict__ gumbel, const uint8_t* __restrict__ invalid,
+                                                         float* __restrict__ out_value, float* __restrict__ out_ube) {
   EAZ_GROUP_PROLOGUE();
   float lg[J];
   float m = -INFINITY;
@@ -360,6 +361,8 @@ __global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp,
     r.visits = 1; r.val = value[b]; r.var = var[b]; r.pad0 = 0;
     r.raw = r.val; r.rawvar = r.var; r.parent1 = 0; r.action1 = 0;
     t.nodes[b] = r;
+    if (out_value) out_value[b] = r.val;  // selfplay.py:139-140 value_prediction / ube_prediction
+    if (out_ube) out_ube[b] = r.var;
   }
 }
 
@@ -524,19 +527,29 @@ __global__ void export_tree_kernel(Tree t, TreeOut o) {
 // ------------------------------------------------------------------ host side
 template <int G, int J>
 static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env, const NetDesc& net, const eaz_search_inputs* in,
-                      const SummaryOut& so, int mlp_mode, int exploration, const TensorWeights* tw, cudaStream_t st) {
+                      const SummaryOut& so, int mlp_mode, int exploration, const TensorWeights* tw, float* root_out_value, float* root_out_ube,
+                      cudaStream_t st) {
   const int envs_per_block = 4 * (32 / G);
   const int grid = ceil_div(t.B, envs_per_block);
-  {
-    ProfScope ps(CLS_INIT, st);
-    root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->prior_logits, in->value, in->value_epistemic_variance, in->gumbel, in->invalid_actions);
-  }
-  EAZ_CHECK_LAUNCH("root_init_kernel");
   const int lhead = exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;  // context.py:132
   const int mask = (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead);
   MlpSource src{nullptr, t.states, t.leaf, env.kind == EAZ_ENV_DEEPSEA ? t.ds_seen : nullptr};
   MlpOutputs mo{{nullptr, nullptr}, t.net_value, t.net_ube, nullptr};
   mo.logits[lhead - EAZ_HEAD_EXPLOIT] = t.net_logits;
+  const float *root_logits = in->prior_logits, *root_value = in->value, *root_var = in->value_epistemic_variance;
+  if (!root_logits) {  // fused root: forward.apply on the root states (node 0 = the first B compact states), selfplay.py:89
+    ProfScope ps(CLS_MLP, st);
+    MlpSource rsrc{nullptr, t.states, nullptr, src.ds_seen};
+    if (int rc = launch_mlp(net, env, rsrc, t.B, mask, mo, mlp_mode, st, tw)) return rc;
+    root_logits = t.net_logits;
+    root_value = t.net_value;
+    root_var = t.net_ube;
+  }
+  {
+    ProfScope ps(CLS_INIT, st);
+    root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, root_logits, root_value, root_var, in->gumbel, in->invalid_actions, root_out_value, root_out_ube);
+  }
+  EAZ_CHECK_LAUNCH("root_init_kernel");
   for (int sim = 0; sim <= sp.n; ++sim) {
     {  // backward of simulation sim-1 fused with the descent of simulation sim
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
@@ -580,8 +593,10 @@ static int check_search(const eaz_search_config* cfg, const eaz_search_inputs* i
   EAZ_CHECK_ARG(cfg->max_depth >= 0, "max_depth must be >= 0 (0 = None)");
   if (int rc = make_env_desc(in->env, env)) return rc;
   if (int rc = make_net_desc(in->net, env, net)) return rc;
-  EAZ_CHECK_ARG(in->prior_logits && in->value && in->value_epistemic_variance && in->gumbel && in->embedding,
-                "search inputs: prior_logits / value / value_epistemic_variance / gumbel / embedding must be non-NULL");
+  EAZ_CHECK_ARG(in->gumbel && in->embedding, "search inputs: gumbel / embedding must be non-NULL");
+  const bool fused_root = !in->prior_logits && !in->value && !in->value_epistemic_variance;
+  EAZ_CHECK_ARG(fused_root || (in->prior_logits && in->value && in->value_epistemic_variance),
+                "search inputs: prior_logits / value / value_epistemic_variance must be all non-NULL, or all NULL (fused root)");
   EAZ_CHECK_ARG(out->action != nullptr, "search outputs: action must be non-NULL");
   if ((size_t)(cfg->num_simulations + 1) * cfg->batch * env->num_actions >= ((size_t)1 << 31)) {
     set_error("tree of %d nodes x %d envs x %d actions exceeds 2^31 edges: shard the batch", cfg->num_simulations + 1, cfg->batch, env->num_actions);
@@ -646,7 +661,7 @@ int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env
   const int per_sim = 1 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
   const int prep = cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * (d.kind == EAZ_ENV_DEEPSEA ? 2 : 3) : 0;  // weight tiling, 3 heads
   // 1 memset + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
-  return 1 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1 + 1;
+  return 1 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1 + 1;  // (+1 network launch with a fused root)
 }
 
 int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
@@ -685,7 +700,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   SummaryOut so{out->action, out->action_weights, out->value, out->value_epistemic_std, out->visit_counts, out->visit_probs,
                 out->qvalues, out->qvalues_epistemic_variance};
   int rc;
-#define EAZ_RUN(G, J) rc = run_search<G, J>(t, sp, env, net, in, so, cfg->mlp_mode, cfg->exploration, cfg->mlp_mode == EAZ_MLP_TENSOR ? &tw : nullptr, st)
+#define EAZ_RUN(G, J) rc = run_search<G, J>(t, sp, env, net, in, so, cfg->mlp_mode, cfg->exploration, cfg->mlp_mode == EAZ_MLP_TENSOR ? &tw : nullptr, out->root_value, out->root_ube, st)
   if (A <= 2) EAZ_RUN(2, 1);
   else if (A <= 4) EAZ_RUN(4, 1);
   else if (A <= 8) EAZ_RUN(8, 1);

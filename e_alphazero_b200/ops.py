@@ -337,7 +337,7 @@ def mlp_forward_states(net: FcParams, env: EnvSpec, st: dict) -> dict:
 def alloc_search_outputs(B, N, A, S, want_tree, device) -> dict:
     torch = require_cuda()
     shp = {"B": (B,), "BA": (B, A), "BN": (B, N), "BNA": (B, N, A), "BNS": (B, N, S)}
-    fields = _abi.SEARCH_OUTPUT_FIELDS if want_tree else _abi.SUMMARY_FIELDS
+    fields = _abi.SUMMARY_FIELDS + (_abi.TREE_FIELDS if want_tree else []) + _abi.ROOT_FIELDS
     return {name: torch.empty(shp[kind], dtype=_dt()[dt], device=device) for name, dt, kind in fields}
 
 
@@ -380,7 +380,7 @@ class SearchPlan:
         if inv is not None and inv.dtype != u8:
             inv = inv.to(u8)
         e, n, s = self.env.struct(), self.net.struct(), state_struct(self.env, root["embedding"])
-        inp = _abi.EazSearchInputs(_ptr(root["prior_logits"], f32), _ptr(root["value"], f32), _ptr(root["value_epistemic_variance"], f32),
+        inp = _abi.EazSearchInputs(_ptr(root.get("prior_logits"), f32), _ptr(root.get("value"), f32), _ptr(root.get("value_epistemic_variance"), f32),
                                    _ptr(root["beta"], f32), C.pointer(s), _ptr(inv), _ptr(root["gumbel"], f32), C.pointer(e), C.pointer(n))
         o = _abi.EazSearchOutputs()
         for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
@@ -396,6 +396,6 @@ class SearchPlan:
 
 
 def search(cfg: _abi.EazSearchConfig, env: EnvSpec, net: FcParams, root: dict, want_tree=False) -> dict:
-    cfg.batch = root["prior_logits"].shape[0]
-    plan = SearchPlan(cfg, env, net, want_tree, device=str(root["prior_logits"].device))
+    cfg.batch = root["gumbel"].shape[0]
+    plan = SearchPlan(cfg, env, net, want_tree, device=str(root["gumbel"].device))
     return plan.run(root)

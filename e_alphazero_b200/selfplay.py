@@ -26,7 +26,7 @@ class SelfplayRunner:
 
     def __init__(self, env_spec: ops.EnvSpec, net: ops.FcParams, batch: int, num_simulations: int, discount: float,
                  exploration_beta: float = 0.0, directed_exploration: bool = False, rescale_values: bool = True,
-                 mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0, use_graph: bool = False):
+                 mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0, use_graph: bool = False, fused_root: bool = False):
         torch = require_cuda()
         self.env, self.net, self.B, self.device = env_spec, net, batch, device
         self.directed = directed_exploration
@@ -39,10 +39,11 @@ class SelfplayRunner:
         self.tasks = torch.tensor(list(tasks), dtype=torch.int32, device=device)
         self.A = env_spec.num_actions
         # launches per step: compact+mlp (root forward), search, env step
-        self.launches_per_step = 2 + self.plan.num_launches + 1
+        self.launches_per_step = 2 + self.plan.num_launches + 1  # (fused root: pack+mlp are replaced by one network launch inside the search)
         # CUDA graph of one whole step (root forward -> search -> env step): the launch sequence is fixed and nothing
         # synchronises or allocates, so it is captured once and replayed; the noise is drawn outside the graph.
         self.use_graph = use_graph
+        self.fused_root = fused_root  # let the search evaluate the root network itself (same kernels, one launch less path)
         self._graph = None
         self._static = None
 
@@ -94,11 +95,16 @@ class SelfplayRunner:
 
     def _step_eager(self, states: dict, gumbel=None, task_ids=None):
         torch = require_cuda()
-        ev = ops.mlp_forward_states(self.net, self.env, states)  # selfplay.py:89
-        logits = ev["explore_logits"] if self.directed else ev["exploit_logits"]  # :93-95
-        root = dict(prior_logits=logits, value=ev["value"], value_epistemic_variance=ev["ube"], beta=self.beta, embedding=states,
-                    gumbel=self.draw_gumbel() if gumbel is None else gumbel)
+        if self.fused_root:  # selfplay.py:89 inside the search call (policy head = the recurrent_fn's: main.py:262)
+            root = dict(beta=self.beta, embedding=states, gumbel=self.draw_gumbel() if gumbel is None else gumbel)
+        else:
+            ev = ops.mlp_forward_states(self.net, self.env, states)  # selfplay.py:89
+            logits = ev["explore_logits"] if self.directed else ev["exploit_logits"]  # :93-95
+            root = dict(prior_logits=logits, value=ev["value"], value_epistemic_variance=ev["ube"], beta=self.beta, embedding=states,
+                        gumbel=self.draw_gumbel() if gumbel is None else gumbel)
         out = self.plan.run(root)  # :107-117 (invalid_actions = ~legal_action_mask = none)
+        if self.fused_root:
+            ev = dict(value=out["root_value"], ube=out["root_ube"])
         if task_ids is None and self.env.kind == _abi.ENV_SUBLEQ:
             idx = torch.randint(0, self.tasks.numel(), (self.B,), device=self.device, generator=self.gen)
             task_ids = self.tasks[idx].contiguous()

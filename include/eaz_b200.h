@@ -213,7 +213,11 @@ enum {
 
 typedef struct eaz_search_inputs {
   /* EpistemicRootFnOutput, selfplay.py:100-106 */
-  const float* prior_logits;             /* [B,A] raw root logits */
+  const float* prior_logits;             /* [B,A] raw root logits.  NULL (together with value and
+                                            value_epistemic_variance) = FUSED ROOT: the library evaluates the root
+                                            itself, i.e. forward.apply on `embedding` (selfplay.py:89) with the policy
+                                            head the recurrent_fn uses (`exploration`), and reports the value / UBE
+                                            predictions in eaz_search_outputs.root_value / root_ube */
   const float* value;                    /* [B] */
   const float* value_epistemic_variance; /* [B] */
   const float* beta;                     /* [B] */
@@ -253,6 +257,9 @@ typedef struct eaz_search_outputs {
   float* children_rewards_epistemic_variance; /* [B,N,A] (identically 0, context.py:149) */
   float* children_values_epistemic_variance;  /* [B,N,A] */
   uint8_t* embeddings;                        /* [B,N,S] compact per-node env states, S = eaz_env_compact_bytes */
+  /* fused-root mode only (optional): the root network outputs, selfplay.py:139-140 value_prediction / ube_prediction */
+  float* root_value;                          /* [B] */
+  float* root_ube;                            /* [B] */
 } eaz_search_outputs;
 
 /* Bytes per compact (in-tree) env state. */

@@ -301,7 +301,7 @@ def alloc_search_outputs(B, N, A, S, want_tree=True) -> dict:
     out = {}
     dts = {"i32": np.int32, "f32": np.float32, "u8": np.uint8}
     shp = {"B": (B,), "BA": (B, A), "BN": (B, N), "BNA": (B, N, A), "BNS": (B, N, S)}
-    fields = _abi.SEARCH_OUTPUT_FIELDS if want_tree else _abi.SUMMARY_FIELDS
+    fields = _abi.SUMMARY_FIELDS + (_abi.TREE_FIELDS if want_tree else [])
     for name, dt, kind in fields:
         out[name] = np.zeros(shp[kind], dts[dt])
     return out

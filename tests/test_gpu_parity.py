@@ -193,7 +193,7 @@ def run_both(ops, env, net, root, cfg_kw):
 
 
 def assert_tree_equal(exp, got):
-    for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
+    for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
         H.assert_same_bits(got[name], exp[name], name)
 
 
@@ -275,3 +275,26 @@ def test_search_tensor_mode(ops, kind, kw, B, cfg_kw, root_kw):
     exp = O.search(_abi.default_search_config(**cfg_kw), env, None, root, want_tree=True, replay=replay)
     assert exp["replay_misses"] == 0
     assert_tree_equal(exp, got)
+
+
+@pytest.mark.parametrize("kind,kw,B,expl", [("deepsea", dict(size=10), 64, 0), ("subleq", dict(word_size=16), 40, 1)])
+def test_search_fused_root(ops, kind, kw, B, expl):
+    """prior_logits/value/variance == NULL: the library evaluates the root network itself (selfplay.py:89); with the
+    EXACT network this must equal the oracle's forward + search bit for bit."""
+    env = H.make_env(kind, seed=21, **kw)
+    net = H.make_net(env, seed=22, fill=0.5)
+    st = H.random_states(env, B, seed=23)
+    ev = O.mlp_forward_states(net, env, st)
+    rng = np.random.default_rng(5)
+    root = dict(prior_logits=ev["explore_logits"] if expl else ev["exploit_logits"], value=ev["value"], value_epistemic_variance=ev["ube"],
+                beta=np.linspace(0, 1, B).astype(np.float32), embedding=st, gumbel=rng.gumbel(size=(B, env.num_actions)).astype(np.float32))
+    kw_cfg = dict(num_simulations=24, discount=0.97, exploration=expl)
+    exp = O.search(_abi.default_search_config(**kw_cfg), env, net, root, want_tree=True)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    droot = H.device_root(env, denv, root)
+    for k in ("prior_logits", "value", "value_epistemic_variance"):
+        del droot[k]
+    got = {k: host(v) for k, v in ops.search(_abi.default_search_config(batch=B, **kw_cfg), denv, dnet, droot, want_tree=True).items()}
+    assert_tree_equal(exp, got)
+    H.assert_same_bits(got["root_value"], ev["value"], "root_value")
+    H.assert_same_bits(got["root_ube"], ev["ube"], "root_ube")
