@@ -33,6 +33,25 @@ int cuda_fail(cudaError_t e, const char* what);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Programmatic dependent launch (PDL): the kernel may start while its predecessor in the stream is still running;
+// everything before pdl_wait() must not touch data the predecessor produces.  pdl_trigger() lets the successor start.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ---------------------------------------------------------------- env description (by value into kernels)
 struct EnvDesc {
   int kind;

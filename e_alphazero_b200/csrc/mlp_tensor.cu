@@ -113,18 +113,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   if (tr && threadIdx.x == 0) trace[0] = clock64();
 
-  // per-row operands first: their dependent global loads (leaf index -> state -> W1 row) overlap the prologue below
-  const int row = threadIdx.x & (kTM - 1);
-  const bool live = row < nrows;
-  const int b = r0 + (live ? row : 0);
-  const uint8_t* st = nullptr;
-  int cell = 0, trow = 0;
-  if (src.compact) {
-    const size_t slot = src.node_index ? ((size_t)src.node_index[b] * B + b) : (size_t)b;
-    st = src.compact + slot * env.compact_bytes;
-    if (env.kind == EAZ_ENV_DEEPSEA) cell = deepsea_obs_index(*reinterpret_cast<const uint32_t*>(st), env.size);
-    else trow = sq_task_row(st[34]);
-  }
+  pdl_trigger();  // the next tree kernel may be scheduled; it blocks in pdl_wait() until this grid has finished
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sh->full_a[s], 4);  // one elected arrive per producer warp of the group
@@ -157,6 +146,21 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
+  // everything above reads only weights: under PDL it overlaps the tail of the previous kernel.  From here on the
+  // kernel consumes the previous kernel's outputs (leaf indices, states).
+  // The weight-copy and MMA-issue warps never read the previous kernel's data and do not wait.
+  const int row = threadIdx.x & (kTM - 1);
+  const bool live = row < nrows;
+  const int b = r0 + (live ? row : 0);
+  const uint8_t* st = nullptr;
+  int cell = 0, trow = 0;
+  if (warp < 8) pdl_wait();
+  if (warp < 8 && src.compact) {
+    const size_t slot = src.node_index ? ((size_t)src.node_index[b] * B + b) : (size_t)b;
+    st = src.compact + slot * env.compact_bytes;
+    if (env.kind == EAZ_ENV_DEEPSEA) cell = deepsea_obs_index(*reinterpret_cast<const uint32_t*>(st), env.size);
+    else trow = sq_task_row(st[34]);
+  }
 
   if (warp == 9) {
     // ================= weight-copy warp =================
@@ -520,8 +524,8 @@ int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& s
     attr_smem = kTensorSmemFixed + kBitsWordsMax * kTM * 4;
   }
   dim3 grid(ceil_div(B, kTM), hl.n);
-  mlp_tensor_kernel<<<grid, 320, smem, stream>>>(net, env, src, tw, B, hl, out, bits_words, g_mlp_trace);
-  EAZ_CHECK_LAUNCH("mlp_tensor_kernel");
+  cudaError_t le = launch_pdl(mlp_tensor_kernel, grid, dim3(320), smem, stream, net, env, src, tw, B, hl, out, bits_words, g_mlp_trace);
+  if (le != cudaSuccess) return cuda_fail(le, "mlp_tensor_kernel launch");
   return 0;
 }
 

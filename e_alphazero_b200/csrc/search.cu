@@ -553,8 +553,9 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   for (int sim = 0; sim <= sp.n; ++sim) {
     {  // backward of simulation sim-1 fused with the descent of simulation sim
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
-      tree_step_kernel<G, J><<<ceil_div(t.B, 4), 128, 0, st>>>(  // one warp per tree
-          t, sp, env, sim, sim > 0, sim < sp.n, in->beta, in->invalid_actions);
+      cudaError_t le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), 0, st,  // one warp per tree
+                                  t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions);
+      if (le != cudaSuccess) return cuda_fail(le, "tree_step_kernel launch");
     }
     EAZ_CHECK_LAUNCH("tree_step_kernel");
     if (sim == sp.n) break;

@@ -22,6 +22,8 @@ __device__ __forceinline__ int pack_next(int action, int child) { return action 
 template <int G, int J>
 __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
                                                          const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid) {
+  pdl_trigger();  // the next kernel (network / Subleq step) may begin its prologue now
+  pdl_wait();     // ... and this one starts only once the previous kernel's results are visible
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tree
   if (b >= t.B) return;                                        // warp-uniform
