@@ -330,7 +330,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         tree_gbs = (tree_bytes + io_bytes) / (tree_ms * 1e-3) / 1e9
         mlp_tfs = flops_fwd * B * n / (mlp_ms * 1e-3) / 1e12
         tree_obj = {"bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tree_gbs / hbm_peak, "traffic": None,
-                    "kernels": "select + expand_backward" + (" + subleq_tree_step" if kind == "subleq" else ""),
+                    "kernels": "tree_step_kernel (expand + backward + action refresh + descent)" + (" + subleq_tree_step_kernel" if kind == "subleq" else ""),
                     "algorithmic_bytes_per_search": tree_bytes + io_bytes, "ms_per_search": tree_ms,
                     "avg_launch_us": 1e3 * tree_ms / max(prof["select"][1] + prof["expand_backward"][1] + prof["env_step"][1], 1),
                     "edge_traversals": V, "peak_source": which}
@@ -338,6 +338,12 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
                    "kernels": "mlp_exact_kernel (fp32 FMA chains, bit-exact mode)" if args.mlp_mode == 0 else "mlp_tensor_kernel (tcgen05)",
                    "flops_per_search": flops_fwd * B * n, "ms_per_search": mlp_ms, "avg_launch_us": 1e3 * mlp_ms / max(prof["network"][1], 1),
                    "peak_source": which}
+        try:  # DRAM traffic per launch from the committed ncu --set full capture (profiles/r1_traffic.json)
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
+            tree_obj["traffic"] = traffic.get("tree_step_kernel")
+            mlp_obj["traffic"] = traffic.get("mlp_tensor_kernel") if args.mlp_mode == 1 else None
+        except (OSError, ValueError):
+            pass
         roofline = dict(mlp_obj if dominant == "network" else tree_obj)
         roofline["dominant"] = dominant
         roofline["share_of_search_time"] = (mlp_ms if dominant == "network" else tree_ms) / total_ms

@@ -191,17 +191,44 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
   }
 
   // -------------------------------------------------------------------- 4. simulate: follow the cached selections
-  if (lane == 0) {
-    int node = 0, depth = 0, action, child;
+  // Nodes 0..sim exist.  For trees of up to 32*kChaseSlots nodes every cached (action, child) word is fetched once
+  // (independent loads, lane i holds nodes i, i+32, ...) and the chase itself runs over registers with warp
+  // shuffles; larger trees chase through memory, one dependent 16-byte load per level.
+  constexpr int kChaseSlots = 9;
+  int node = 0, depth = 0, action = 0, child = -1;
+  if (sim < 32 * kChaseSlots) {
+    int nxw[kChaseSlots];
+#pragma unroll
+    for (int s = 0; s < kChaseSlots; ++s) {
+      const int nd = lane + 32 * s;
+      nxw[s] = (32 * s <= sim && nd <= sim) ? t.nodes[(unsigned)nd * uB + ub].pad0 : 0;
+    }
     while (true) {
-      const int nx = t.nodes[(unsigned)node * uB + ub].pad0;
+      const int slot = node >> 5;
+      int v = 0;
+#pragma unroll
+      for (int s = 0; s < kChaseSlots; ++s)
+        if (s == slot) v = nxw[s];
+      const int nx = __shfl_sync(0xffffffffu, v, node & 31);
       action = nx & 0xff;
       child = (nx >> 8) - 1;
-      t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
+      if (lane == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
       depth += 1;
       if (child < 0 || depth >= sp.max_depth) break;
       node = child;
     }
+  } else {
+    while (true) {
+      const int nx = t.nodes[(unsigned)node * uB + ub].pad0;
+      action = nx & 0xff;
+      child = (nx >> 8) - 1;
+      if (lane == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
+      depth += 1;
+      if (child < 0 || depth >= sp.max_depth) break;
+      node = child;
+    }
+  }
+  if (lane == 0) {
     const int new_leaf = child < 0 ? sim + 1 : child;  // search.py: node first expanded on simulation i gets index i+1
     t.path_len[b] = depth;
     t.parent[b] = node;
