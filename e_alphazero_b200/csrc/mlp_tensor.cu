@@ -2,8 +2,10 @@
 // (network/fully_connected.py:41-101) for the expand step of the search.
 //
 // One CTA = one head x 128 rows (nodes).  All three hk.Linear layers of the head run as
-// tcgen05.mma kind::tf32 with 3xTF32 split precision (umma.cuh) and fp32 accumulators in TMEM:
-//   D1 (TMEM cols   0..255) = x  @ W1      Subleq / dense observations only: x is 0/1, exact in TF32,
+// tcgen05.mma kind::f16 with scaled 3xFP16 split precision (umma.cuh: x*S = hi + lo, three products, S a power of
+// two removed exactly in the epilogue; same ~22-bit accuracy as 3xTF32 at half the bytes and twice the MMA rate)
+// and fp32 accumulators in TMEM:
+//   D1 (TMEM cols   0..255) = x  @ W1      Subleq / dense observations only: x is 0/1, exact in FP16,
 //                                          so two products (x*W1_hi + x*W1_lo) suffice.  One-hot DeepSea
 //                                          observations skip the GEMM: h1 = relu(W1[cell] + b1) is a row gather.
 //   D2 (TMEM cols 256..511) = h1 @ W2      h1 = relu(D1 + b1), read back with tcgen05.ld by the 4 worker warps
@@ -12,7 +14,7 @@
 // contiguous block fetched with a single 1-D bulk async copy (UBLKCP) that signals an mbarrier.
 // Warp roles: warps 0-7 = two producer groups (thread == row; group g produces chunks t % 2 == g, prefetching its
 // next chunk's operands before storing the current one) that also run the epilogue, warp 8 issues the MMAs,
-// warp 9 issues the weight copies.  4-stage mbarrier pipeline of K=16 chunks: A 16 KB + B 32 KB per stage, so
+// warp 9 issues the weight copies.  4-stage mbarrier pipeline of K=32 chunks: A 16 KB + B 32 KB per stage, so
 // three weight copies and three A chunks are in flight behind the MMAs of the current chunk.
 //
 // Accuracy: <= ~1e-6 relative to the fp32 EXACT contract (tests: 1e-5); NOT bit-identical to it, so search
@@ -23,15 +25,19 @@
 namespace eaz {
 using namespace umma;
 
-int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st, int chunk_k);
+int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, float scale, void* out, cudaStream_t st);
 
 constexpr int kTM = 128;                       // rows per CTA
-constexpr int kCK = 16;                        // K elements per pipeline stage
+constexpr int kCK = 32;                        // K elements (fp16) per pipeline stage: 64 B per row
 constexpr int kStages = 4;
-constexpr int kSBO = (kCK / 4) * kCoreBytes;   // 8-row group stride inside a chunk tile
-constexpr int kAHalf = kTM * kCK * 4;          // one of hi / lo
+constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 8-row group stride inside a chunk tile (512 B)
+constexpr int kAHalf = kTM * kCK * 2;          // one of hi / lo
 constexpr int kAStage = 2 * kAHalf;
-constexpr int kBStageMax = 2 * 256 * kCK * 4;  // hi + lo, N = 256
+constexpr int kBStageMax = 2 * 256 * kCK * 2;  // hi + lo, N = 256
+constexpr float kActScale = 16.0f;             // activations: |h| < 4094 representable, lo part normal down to 2^-7
+constexpr float kWScale = 256.0f;              // weights: |w| < 255
+constexpr float kUnscaleBits = 1.0f / kWScale;               // layer 1 on 0/1 observations: A unscaled
+constexpr float kUnscaleAct = 1.0f / (kActScale * kWScale);  // layers fed by activations
 constexpr int kH = 256;
 constexpr int kLayerChunks = kH / kCK;         // chunks of layers 2 and 3
 constexpr int kBitsWordsMax = 40;              // observation bit-strings cached in smem up to 40*32 bits per row
@@ -64,18 +70,22 @@ __device__ __forceinline__ int sq_bit_g(int v, int c, int w, int ws, int binary)
   return c == (v == ws ? ws : floormod(v, ws));
 }
 
-// write kCK fp32 values (one K-chunk of this thread's row) into the A stage as hi / lo tiles
+// write kCK values (one K-chunk of this thread's row), already scaled, into the A stage as fp16 hi / lo tiles
 __device__ __forceinline__ void store_a_chunk(uint8_t* stage, int row, const float (&v)[kCK], bool with_lo) {
 #pragma unroll
-  for (int q = 0; q < kCK / 4; ++q) {
-    uint4 h, l;
-    split_tf32(v[4 * q + 0], h.x, l.x);
-    split_tf32(v[4 * q + 1], h.y, l.y);
-    split_tf32(v[4 * q + 2], h.z, l.z);
-    split_tf32(v[4 * q + 3], h.w, l.w);
-    const int off = tile_offset_ck<kCK>(row, q * 4);
-    *reinterpret_cast<uint4*>(stage + off) = h;
-    if (with_lo) *reinterpret_cast<uint4*>(stage + kAHalf + off) = l;
+  for (int q = 0; q < kCK / 8; ++q) {  // one 16-byte core-matrix row (8 halves) per store
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      __half h0, l0, h1, l1;
+      split_f16(v[8 * q + 2 * i], h0, l0);
+      split_f16(v[8 * q + 2 * i + 1], h1, l1);
+      h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+      l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    }
+    const int off = tile_offset_h32(row, q * 8);
+    *reinterpret_cast<uint4*>(stage + off) = make_uint4(h[0], h[1], h[2], h[3]);
+    if (with_lo) *reinterpret_cast<uint4*>(stage + kAHalf + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
 
@@ -169,7 +179,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         const int s = t % kStages, ph = (t / kStages) & 1;
         const int layer = t < n1 ? 0 : (t < n1 + kLayerChunks ? 1 : 2);
         const int c = layer == 0 ? t : (layer == 1 ? t - n1 : t - n1 - kLayerChunks);
-        const uint32_t bbytes = (uint32_t)(2 * (layer == 2 ? np3 : kH) * kCK * 4);
+        const uint32_t bbytes = (uint32_t)(2 * (layer == 2 ? np3 : kH) * kCK * 2);
         mbar_wait(&sh->empty[s], ph ^ 1);
         mbar_arrive_expect_tx(&sh->full_b[s], bbytes);
         bulk_g2s(sB + s * kBStageMax, tw.img[head][layer] + (size_t)c * (bbytes / 4), bbytes, &sh->full_b[s]);
@@ -195,9 +205,9 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       for (int layer = 0; layer < 3; ++layer) {
         const int nchunks = layer == 0 ? n1 : ((layer == 2 && simt3) ? 0 : kLayerChunks);
         const int npad = layer == 2 ? np3 : kH;
-        const uint32_t idesc = idesc_tf32(kTM, npad);
+        const uint32_t idesc = idesc_f16(kTM, npad);
         const uint32_t d = tmem + (layer == 1 ? 256u : 0u);
-        const uint32_t blo_off = (uint32_t)(npad * kCK * 4) >> 4, alo_off = (uint32_t)kAHalf >> 4;
+        const uint32_t blo_off = (uint32_t)(npad * kCK * 2) >> 4, alo_off = (uint32_t)kAHalf >> 4;
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c, ++t) {
           const int s = t & (kStages - 1), ph = (t / kStages) & 1;
@@ -210,11 +220,11 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
           for (int q = 0; q < kStages; ++q)
             if (q == s) { al = a_lo32[q]; bl = b_lo32[q]; }
 #pragma unroll
-          for (int j = 0; j < kCK / 8; ++j) {
+          for (int j = 0; j < kCK / 16; ++j) {
             const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
-            mma_tf32(d, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
-            mma_tf32(d, mk(al + o), mk(bl + blo_off + o), idesc, 1);
-            if (layer != 0) mma_tf32(d, mk(al + alo_off + o), mk(bl + o), idesc, 1);  // x is exact in TF32: no lo part
+            mma_f16(d, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
+            mma_f16(d, mk(al + o), mk(bl + blo_off + o), idesc, 1);
+            if (layer != 0) mma_f16(d, mk(al + alo_off + o), mk(bl + o), idesc, 1);  // 0/1 inputs are exact in FP16: no lo part
           }
           mma_commit(&sh->empty[s]);
           if (tr) trace[520 + t] = clock64();
@@ -272,7 +282,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       if (layer == 0) {  // observation bits of K-chunk c
         const int k0 = c * kCK;
         if (cached_bits) {
-          const uint32_t wd = sbits[(k0 >> 5) * kTM + row] >> (k0 & 31);
+          const uint32_t wd = sbits[(k0 >> 5) * kTM + row];
 #pragma unroll
           for (int i = 0; i < kCK; ++i) r[i] = ((wd >> i) & 1u) ? 0x3F800000u : 0u;
         } else if (st) {
@@ -307,7 +317,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
           tc_fence_after();
           waited[layer - 1] = true;
         }
-        tmem_ld16(tmem + lane_base + (layer == 1 ? 0u : 256u) + c * kCK, r);
+        tmem_ld32(tmem + lane_base + (layer == 1 ? 0u : 256u) + c * kCK, r);
       }
     };
     // stage 2: bias + relu (layers 2, 3), split, store into the stage, signal the MMA warp
@@ -318,9 +328,15 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
 #pragma unroll
         for (int i = 0; i < kCK; ++i) v[i] = __uint_as_float(r[i]);
       } else {
-        if (!(layer == 1 && gather)) tmem_ld_wait();
+        const bool from_tmem = !(layer == 1 && gather);
+        if (from_tmem) tmem_ld_wait();
+        // accumulators carry the operand scales: layer 1 of bit inputs kWScale, everything else kActScale * kWScale
+        const float un = !from_tmem ? 1.0f : ((layer == 1) ? kUnscaleBits : kUnscaleAct);
 #pragma unroll
-        for (int i = 0; i < kCK; ++i) v[i] = live ? fmaxf(__fadd_rn(__uint_as_float(r[i]), sh->bias[layer - 1][c * kCK + i]), 0.0f) : 0.0f;
+        for (int i = 0; i < kCK; ++i) {
+          const float h = fmaxf(__fadd_rn(__fmul_rn(__uint_as_float(r[i]), un), sh->bias[layer - 1][c * kCK + i]), 0.0f);
+          v[i] = live ? fminf(__fmul_rn(h, kActScale), 65504.0f) : 0.0f;
+        }
       }
       mbar_wait(&sh->empty[s], ph ^ 1);
       store_a_chunk(sA + s * kAStage, row, v, layer != 0);
@@ -415,7 +431,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int k = kbase + kk + i;
-          const float h = fmaxf(__fadd_rn(__uint_as_float(r[i]), sh->bias[1][k]), 0.0f);
+          const float h = fmaxf(__fadd_rn(__fmul_rn(__uint_as_float(r[i]), kUnscaleAct), sh->bias[1][k]), 0.0f);
           const float4 w = *reinterpret_cast<const float4*>(sh->w3[k]);
           y3[0] = __fmaf_rn(h, w.x, y3[0]);
           y3[1] = __fmaf_rn(h, w.y, y3[1]);
@@ -448,7 +464,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       if (policy) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (n0 + i < nout) logits[(size_t)b * nout + n0 + i] = __fadd_rn(__uint_as_float(r[i]), sh->bias[2][n0 + i]);
+          if (n0 + i < nout) logits[(size_t)b * nout + n0 + i] = __fadd_rn(simt3 ? __uint_as_float(r[i]) : __fmul_rn(__uint_as_float(r[i]), kUnscaleAct), sh->bias[2][n0 + i]);
       } else {
         const float y = __fadd_rn(__uint_as_float(r[0]), sh->bias[2][0]);
         if (head == EAZ_HEAD_VALUE) {
@@ -476,9 +492,9 @@ static int k1pad_of(int D) { return (D + kCK - 1) / kCK * kCK; }
 
 size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env) {
   const int np3 = (net.A + 15) & ~15;
-  const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? 0 : (size_t)k1pad_of(net.D) * 2 * kH * 4;
-  const size_t l2 = (size_t)kH * 2 * kH * 4;
-  const size_t per_head = l1 + l2 + (size_t)kH * 2 * np3 * 4;
+  const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? 0 : (size_t)k1pad_of(net.D) * 2 * kH * 2;
+  const size_t l2 = (size_t)kH * 2 * kH * 2;
+  const size_t per_head = l1 + l2 + (size_t)kH * 2 * np3 * 2;
   return 4 * ((per_head + 255) & ~(size_t)255);
 }
 
@@ -489,7 +505,7 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
   }
   const int k1pad = k1pad_of(net.D);
   const bool has_l1 = env.kind != EAZ_ENV_DEEPSEA;
-  const size_t l1 = has_l1 ? (size_t)k1pad * 2 * kH * 4 : 0, l2 = (size_t)kH * 2 * kH * 4;
+  const size_t l1 = has_l1 ? (size_t)k1pad * 2 * kH * 2 : 0, l2 = (size_t)kH * 2 * kH * 2;
   const size_t per_head = tensor_weights_bytes(net, env) / 4;
   tw->k1pad = k1pad;
   for (int h = 0; h < 4; ++h) {
@@ -500,9 +516,9 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     if (!(heads_mask & (1 << h))) continue;
     const int nout = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
     if (has_l1)
-      if (int rc = launch_tile_weights(net.w[h][0], net.D, kH, k1pad, kH, (uint32_t*)p, st, kCK)) return rc;
-    if (int rc = launch_tile_weights(net.w[h][1], kH, kH, kH, kH, (uint32_t*)(p + l1), st, kCK)) return rc;
-    if (int rc = launch_tile_weights(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, (uint32_t*)(p + l1 + l2), st, kCK)) return rc;
+      if (int rc = launch_tile_weights_f16(net.w[h][0], net.D, kH, k1pad, kH, kWScale, p, st)) return rc;
+    if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, kWScale, p + l1, st)) return rc;
+    if (int rc = launch_tile_weights_f16(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, kWScale, p + l1 + l2, st)) return rc;
   }
   return 0;
 }

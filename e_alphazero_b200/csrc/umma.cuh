@@ -144,3 +144,33 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 
 }  // namespace umma
 }  // namespace eaz
+
+// ---- scaled 3xFP16 variant (mlp_tensor.cu): same byte geometry, 2-byte elements.
+// x*S = hi + lo (hi, lo fp16, ~22 significant bits); D += A_hi*B_hi + A_hi*B_lo + A_lo*B_hi; S is a power of two
+// removed exactly in the epilogue.  kind::f16 consumes K = 16 per instruction (two 16-byte core-matrix columns).
+#include <cuda_fp16.h>
+namespace eaz {
+namespace umma {
+__host__ __device__ inline uint32_t idesc_f16(int M, int N) {  // F16 x F16 -> F32, K-major A and B
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// byte offset of element (row, k) in a [rows x 32] fp16 chunk tile (64 B per row = 4 core-matrix columns)
+__host__ __device__ inline int tile_offset_h32(int row, int k) {
+  return (row >> 3) * 512 + (k >> 3) * kCoreBytes + (row & 7) * 16 + (k & 7) * 2;
+}
+__device__ __forceinline__ void split_f16(float xs, __half& hi, __half& lo) {  // xs already scaled and range-clamped
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(__fsub_rn(xs, __half2float(hi)));
+}
+}  // namespace umma
+}  // namespace eaz
