@@ -33,6 +33,15 @@ int cuda_fail(cudaError_t e, const char* what);
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// Optional launch timeline (eaz_debug_set_timeline): block 0 of the per-simulation kernels appends
+// {globaltimer at entry, after the PDL wait, at exit, kind} records; tl[0] is the record counter.
+extern unsigned long long* g_timeline;
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
 // Programmatic dependent launch (PDL): the kernel may start while its predecessor in the stream is still running;
 // everything before pdl_wait() must not touch data the predecessor produces.  pdl_trigger() lets the successor start.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -8,6 +8,7 @@
 
 namespace eaz {
 
+unsigned long long* g_timeline = nullptr;
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -303,3 +304,6 @@ int eaz_env_step(const eaz_env* env, eaz_state* state, const int32_t* action, in
 }
 
 }  // extern "C"
+
+// Debug hook (not in the public header): device buffer of >= 8 + 4*records u64; buf[0] must be zeroed by the caller.
+extern "C" void eaz_debug_set_timeline(unsigned long long* device_buffer) { eaz::g_timeline = device_buffer; }

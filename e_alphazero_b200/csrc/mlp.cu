@@ -373,7 +373,7 @@ int eaz_mlp_forward(const eaz_fc_params* net, const uint8_t* observation, int32_
   EAZ_CHECK_ARG(observation != nullptr && B >= 0, "eaz_mlp_forward: bad arguments");
   EnvDesc ed{};
   ed.kind = -1;
-  MlpSource src{observation, nullptr, nullptr, nullptr};
+  MlpSource src{observation, nullptr, nullptr, nullptr, nullptr};
   return mlp_entry(net, nullptr, src, B, exploit_logits, explore_logits, value, ube, novelty, ed, stream);
 }
 

@@ -20,6 +20,7 @@ struct MlpSource {
   const uint8_t* compact;     // compact env states or null
   const int32_t* node_index;  // optional [B]: row b's state is compact[(node_index[b]*B + b)*S]; null: compact[b*S]
   const uint8_t* ds_seen;     // optional DeepSea per-cell "seen" table [D] (replaces hashing the one-hot row)
+  const int32_t* cell_index;  // optional DeepSea observation cell of row b's leaf state (written by the tree kernel)
 };
 
 struct MlpOutputs {

@@ -46,7 +46,8 @@ constexpr int kSimtOutMax = 4;                 // heads with <= 4 outputs run la
 struct TensorSmem {
   uint64_t full_a[kStages], full_b[kStages], empty[kStages], acc_done[3];
   uint32_t tmem_base;
-  float bias[3][kH];
+  alignas(16) float bias[3][kH];
+  alignas(16) float bias_s[2][kH];  // b1, b2 pre-multiplied by kActScale: relu(acc*un + b) * S == relu(fma(acc, un*S, b*S)) exactly (S = 2^k)
   alignas(16) float w3[kH][kSimtOutMax];    // layer-3 weights of narrow heads
   alignas(16) float part[kTM][kSimtOutMax];  // partial dot products of producer group 1
 };
@@ -76,12 +77,13 @@ __device__ __forceinline__ void store_a_chunk(uint8_t* stage, int row, const flo
   for (int q = 0; q < kCK / 8; ++q) {  // one 16-byte core-matrix row (8 halves) per store
     uint32_t h[4], l[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      __half h0, l0, h1, l1;
-      split_f16(v[8 * q + 2 * i], h0, l0);
-      split_f16(v[8 * q + 2 * i + 1], h1, l1);
-      h[i] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-      l[i] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+    for (int i = 0; i < 4; ++i) {  // two elements per packed conversion (cvt.rn.f16x2.f32)
+      const float2 x = make_float2(v[8 * q + 2 * i], v[8 * q + 2 * i + 1]);
+      const __half2 hi = __float22half2_rn(x);
+      const float2 hf = __half22float2(hi);
+      const __half2 lo = __float22half2_rn(make_float2(__fsub_rn(x.x, hf.x), __fsub_rn(x.y, hf.y)));
+      h[i] = *reinterpret_cast<const uint32_t*>(&hi);
+      l[i] = *reinterpret_cast<const uint32_t*>(&lo);
     }
     const int off = tile_offset_h32(row, q * 8);
     *reinterpret_cast<uint4*>(stage + off) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -100,7 +102,10 @@ struct TensorHeads {
 static unsigned long long* g_mlp_trace = nullptr;
 
 __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc env, MlpSource src, TensorWeights tw, int B, TensorHeads heads,
-                                                            MlpOutputs out, int bits_words, unsigned long long* trace) {
+                                                            MlpOutputs out, int bits_words, unsigned long long* trace, unsigned long long* tl) {
+  const bool tl_on = tl && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0;
+  const unsigned long long tl_entry = tl_on ? globaltimer_ns() : 0ull;
+  unsigned long long tl_wait = 0ull;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sA = smem;
   uint8_t* sB = smem + kStages * kAStage;
@@ -145,6 +150,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
     }
     sh->bias[0][j] = b0;
     sh->bias[1][j] = b1;
+    sh->bias_s[0][j] = b0 * kActScale;
+    sh->bias_s[1][j] = b1 * kActScale;
     sh->bias[2][j] = b2;
     if (simt3) *reinterpret_cast<float4*>(sh->w3[j]) = make_float4(w[0], w[1], w[2], w[3]);
   }
@@ -165,10 +172,12 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   const uint8_t* st = nullptr;
   int cell = 0, trow = 0;
   if (warp < 8) pdl_wait();
+  if (tl_on) tl_wait = globaltimer_ns();
+  if (tr && threadIdx.x == 0) trace[2] = clock64();
   if (warp < 8 && src.compact) {
     const size_t slot = src.node_index ? ((size_t)src.node_index[b] * B + b) : (size_t)b;
     st = src.compact + slot * env.compact_bytes;
-    if (env.kind == EAZ_ENV_DEEPSEA) cell = deepsea_obs_index(*reinterpret_cast<const uint32_t*>(st), env.size);
+    if (env.kind == EAZ_ENV_DEEPSEA) cell = (src.cell_index && src.node_index) ? src.cell_index[b] : deepsea_obs_index(*reinterpret_cast<const uint32_t*>(st), env.size);
     else trow = sq_task_row(st[34]);
   }
 
@@ -331,11 +340,19 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         const bool from_tmem = !(layer == 1 && gather);
         if (from_tmem) tmem_ld_wait();
         // accumulators carry the operand scales: layer 1 of bit inputs kWScale, everything else kActScale * kWScale
-        const float un = !from_tmem ? 1.0f : ((layer == 1) ? kUnscaleBits : kUnscaleAct);
+        const float un = (!from_tmem ? 1.0f : ((layer == 1) ? kUnscaleBits : kUnscaleAct)) * kActScale;
+        const float4* bs = reinterpret_cast<const float4*>(&sh->bias_s[layer - 1][c * kCK]);
 #pragma unroll
-        for (int i = 0; i < kCK; ++i) {
-          const float h = fmaxf(__fadd_rn(__fmul_rn(__uint_as_float(r[i]), un), sh->bias[layer - 1][c * kCK + i]), 0.0f);
-          v[i] = live ? fminf(__fmul_rn(h, kActScale), 65504.0f) : 0.0f;
+        for (int q = 0; q < kCK / 4; ++q) {
+          const float4 bq = bs[q];
+          v[4 * q + 0] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 0]), un, bq.x), 0.0f), 65504.0f);
+          v[4 * q + 1] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 1]), un, bq.y), 0.0f), 65504.0f);
+          v[4 * q + 2] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 2]), un, bq.z), 0.0f), 65504.0f);
+          v[4 * q + 3] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 3]), un, bq.w), 0.0f), 65504.0f);
+        }
+        if (!live) {
+#pragma unroll
+          for (int i = 0; i < kCK; ++i) v[i] = 0.0f;
         }
       }
       mbar_wait(&sh->empty[s], ph ^ 1);
@@ -422,6 +439,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         tc_fence_after();
         waited[1] = true;
       }
+      if (tr && threadIdx.x == 0) trace[3] = clock64();
       const int kbase = grp * (kH / 2);
 #pragma unroll 2
       for (int kk = 0; kk < kH / 2; kk += 16) {
@@ -431,16 +449,22 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int k = kbase + kk + i;
-          const float h = fmaxf(__fadd_rn(__fmul_rn(__uint_as_float(r[i]), kUnscaleAct), sh->bias[1][k]), 0.0f);
-          const float4 w = *reinterpret_cast<const float4*>(sh->w3[k]);
-          y3[0] = __fmaf_rn(h, w.x, y3[0]);
-          y3[1] = __fmaf_rn(h, w.y, y3[1]);
-          y3[2] = __fmaf_rn(h, w.z, y3[2]);
-          y3[3] = __fmaf_rn(h, w.w, y3[3]);
+          const float h = fmaxf(__fmaf_rn(__uint_as_float(r[i]), kUnscaleAct, sh->bias[1][k]), 0.0f);
+          if (nout == 1) {  // value / UBE heads
+            y3[0] = __fmaf_rn(h, sh->w3[k][0], y3[0]);
+          } else {
+            const float4 w = *reinterpret_cast<const float4*>(sh->w3[k]);
+            y3[0] = __fmaf_rn(h, w.x, y3[0]);
+            y3[1] = __fmaf_rn(h, w.y, y3[1]);
+            y3[2] = __fmaf_rn(h, w.z, y3[2]);
+            y3[3] = __fmaf_rn(h, w.w, y3[3]);
+          }
         }
       }
       if (grp == 1) *reinterpret_cast<float4*>(sh->part[row]) = make_float4(y3[0], y3[1], y3[2], y3[3]);
+      if (tr && threadIdx.x == 0) trace[4] = clock64();
       asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 producer warps
+      if (tr && threadIdx.x == 0) trace[5] = clock64();
       if (grp == 0) {
         const float4 o = *reinterpret_cast<const float4*>(sh->part[row]);
         y3[0] = __fadd_rn(y3[0], o.x); y3[1] = __fadd_rn(y3[1], o.y); y3[2] = __fadd_rn(y3[2], o.z); y3[3] = __fadd_rn(y3[3], o.w);
@@ -485,6 +509,10 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   __syncthreads();
   if (warp == 8) tmem_dealloc(tmem, 512);
   if (tr && threadIdx.x == 0) trace[1] = clock64();
+  if (tl_on) {
+    const unsigned long long i = atomicAdd(tl, 1ull);
+    if (i < 2000) { tl[8 + 4 * i] = tl_entry; tl[9 + 4 * i] = tl_wait; tl[10 + 4 * i] = globaltimer_ns(); tl[11 + 4 * i] = 1; }
+  }
 }
 
 // ---------------------------------------------------------------- host side
@@ -540,7 +568,7 @@ int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& s
     attr_smem = kTensorSmemFixed + kBitsWordsMax * kTM * 4;
   }
   dim3 grid(ceil_div(B, kTM), hl.n);
-  cudaError_t le = launch_pdl(mlp_tensor_kernel, grid, dim3(320), smem, stream, net, env, src, tw, B, hl, out, bits_words, g_mlp_trace);
+  cudaError_t le = launch_pdl(mlp_tensor_kernel, grid, dim3(320), smem, stream, net, env, src, tw, B, hl, out, bits_words, g_mlp_trace, g_timeline);
   if (le != cudaSuccess) return cuda_fail(le, "mlp_tensor_kernel launch");
   return 0;
 }

@@ -67,6 +67,7 @@ struct Tree {
   // scratch
   float *gumbel, *net_logits, *net_value, *net_ube, *reward;
   int32_t *parent, *action, *leaf;
+  int32_t* cell;  // DeepSea: observation cell of the pending leaf (saves the network kernel a dependent load)
   int32_t* table;
   uint8_t* ds_seen;
   uint8_t* wimg;  // tensor-path weight images (mlp_mode TENSOR)
@@ -93,7 +94,8 @@ static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, 
   put(nb * S);                 // 2 states
   L->zero_end = o;
   L->ones_begin = L->ones_end = o;
-  for (int k = 3; k < 14; ++k) put(0);  // (slots kept so that the scratch offsets below stay stable)
+  put((size_t)B * 4);                   // 3 cell
+  for (int k = 4; k < 14; ++k) put(0);  // (slots kept so that the scratch offsets below stay stable)
   put((size_t)B * A * 4);  // 14 gumbel
   put((size_t)B * A * 4);  // 15 net_logits
   put((size_t)B * 4);      // 16 net_value
@@ -117,6 +119,7 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
   t.nodes = (NodeRec*)(p + L.off[0]);
   t.edges = (EdgeRec*)(p + L.off[1]);
   t.states = p + L.off[2];
+  t.cell = (int32_t*)(p + L.off[3]);
   t.gumbel = (float*)(p + L.off[14]);
   t.net_logits = (float*)(p + L.off[15]);
   t.net_value = (float*)(p + L.off[16]);
@@ -533,13 +536,13 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   const int grid = ceil_div(t.B, envs_per_block);
   const int lhead = exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;  // context.py:132
   const int mask = (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead);
-  MlpSource src{nullptr, t.states, t.leaf, env.kind == EAZ_ENV_DEEPSEA ? t.ds_seen : nullptr};
+  MlpSource src{nullptr, t.states, t.leaf, env.kind == EAZ_ENV_DEEPSEA ? t.ds_seen : nullptr, env.kind == EAZ_ENV_DEEPSEA ? t.cell : nullptr};
   MlpOutputs mo{{nullptr, nullptr}, t.net_value, t.net_ube, nullptr};
   mo.logits[lhead - EAZ_HEAD_EXPLOIT] = t.net_logits;
   const float *root_logits = in->prior_logits, *root_value = in->value, *root_var = in->value_epistemic_variance;
   if (!root_logits) {  // fused root: forward.apply on the root states (node 0 = the first B compact states), selfplay.py:89
     ProfScope ps(CLS_MLP, st);
-    MlpSource rsrc{nullptr, t.states, nullptr, src.ds_seen};
+    MlpSource rsrc{nullptr, t.states, nullptr, src.ds_seen, nullptr};
     if (int rc = launch_mlp(net, env, rsrc, t.B, mask, mo, mlp_mode, st, tw)) return rc;
     root_logits = t.net_logits;
     root_value = t.net_value;
@@ -554,7 +557,7 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     {  // backward of simulation sim-1 fused with the descent of simulation sim
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
       cudaError_t le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), 0, st,  // one warp per tree
-                                  t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions);
+                                  t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions, g_timeline);
       if (le != cudaSuccess) return cuda_fail(le, "tree_step_kernel launch");
     }
     EAZ_CHECK_LAUNCH("tree_step_kernel");
@@ -636,7 +639,7 @@ int eaz_mlp_forward_states(const eaz_fc_params* net, const eaz_env* env, const e
   }
   if (B == 0) return 0;
   if (int rc = eaz_env_compact(env, state, (uint8_t*)workspace, B, stream)) return rc;
-  MlpSource src{nullptr, (const uint8_t*)workspace, nullptr, nullptr};
+  MlpSource src{nullptr, (const uint8_t*)workspace, nullptr, nullptr, nullptr};
   MlpOutputs out{{exploit_logits, explore_logits}, value, ube, novelty};
   int mask = 0;
   if (value) mask |= 1 << EAZ_HEAD_VALUE;

@@ -21,9 +21,23 @@ __device__ __forceinline__ int pack_next(int action, int child) { return action 
 
 template <int G, int J>
 __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
-                                                         const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid) {
+                                                         const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid,
+                                                         unsigned long long* tl) {
+  unsigned long long t_entry = 0;
+  if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_entry = globaltimer_ns();
   pdl_trigger();  // the next kernel (network / Subleq step) may begin its prologue now
   pdl_wait();     // ... and this one starts only once the previous kernel's results are visible
+  unsigned long long t_wait = 0;
+  if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_wait = globaltimer_ns();
+  struct TlExit {  // records at every exit path of the first warp
+    unsigned long long *tl, a, b;
+    __device__ ~TlExit() {
+      if (tl && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long i = atomicAdd(tl, 1ull);
+        if (i < 2000) { tl[8 + 4 * i] = a; tl[9 + 4 * i] = b; tl[10 + 4 * i] = globaltimer_ns(); tl[11 + 4 * i] = 0; }
+      }
+    }
+  } tl_exit{tl, t_entry, t_wait};
   const int lane = threadIdx.x & 31;
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tree
   if (b >= t.B) return;                                        // warp-uniform
@@ -237,8 +251,10 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
     if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
       uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
       float reward;
-      st[(unsigned)new_leaf * uB + ub] = deepsea_step(st[(unsigned)node * uB + ub], action, env.size, env.action_map, &reward);
+      const uint32_t ns = deepsea_step(st[(unsigned)node * uB + ub], action, env.size, env.action_map, &reward);
+      st[(unsigned)new_leaf * uB + ub] = ns;
       t.reward[b] = reward;
+      t.cell[b] = deepsea_obs_index(ns, env.size);
     }
   }
 }
