@@ -128,7 +128,6 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   const bool tr = trace != nullptr && blockIdx.x == 0 && blockIdx.y == 0;
   if (tr && threadIdx.x == 0) trace[0] = clock64();
 
-  pdl_trigger();  // the next tree kernel may be scheduled; it blocks in pdl_wait() until this grid has finished
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(&sh->full_a[s], 4);  // one elected arrive per producer warp of the group
@@ -165,13 +164,16 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   const uint32_t tmem = sh->tmem_base;
   // everything above reads only weights: under PDL it overlaps the tail of the previous kernel.  From here on the
   // kernel consumes the previous kernel's outputs (leaf indices, states).
-  // The weight-copy and MMA-issue warps never read the previous kernel's data and do not wait.
   const int row = threadIdx.x & (kTM - 1);
   const bool live = row < nrows;
   const int b = r0 + (live ? row : 0);
   const uint8_t* st = nullptr;
   int cell = 0, trow = 0;
-  if (warp < 8) pdl_wait();
+  // Every thread waits for the previous kernel (the tree / env step of this simulation) and only THEN lets the next
+  // tree kernel launch: that kernel stages tree data before its own wait, which is safe only once the previous tree
+  // kernel is complete (tree_step.cuh).
+  pdl_wait();
+  pdl_trigger();
   if (tl_on) tl_wait = globaltimer_ns();
   if (tr && threadIdx.x == 0) trace[2] = clock64();
   if (warp < 8 && src.compact) {

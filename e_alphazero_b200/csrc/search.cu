@@ -30,6 +30,7 @@ struct Prof {
   std::vector<int> cls;
 };
 static thread_local Prof* tl_prof = nullptr;
+static long long* g_tree_trace = nullptr;  // eaz_debug_set_tree_trace
 struct ProfScope {
   cudaStream_t st;
   bool on;
@@ -553,11 +554,15 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, root_logits, root_value, root_var, in->gumbel, in->invalid_actions, root_out_value, root_out_ube);
   }
   EAZ_CHECK_LAUNCH("root_init_kernel");
+  // staging area of tree_step_kernel (tree_step.cuh): per warp, sized for the cached selections + states of all N nodes
+  const int chase_cap = (J == 1 && t.N <= 512) ? ((t.N + 2 + 7) & ~7) : 0;
+  const size_t stage_bytes = chase_cap ? (size_t)4 * Stage<G>::words(chase_cap) * sizeof(uint32_t) : 0;
   for (int sim = 0; sim <= sp.n; ++sim) {
     {  // backward of simulation sim-1 fused with the descent of simulation sim
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
-      cudaError_t le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), 0, st,  // one warp per tree
-                                  t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions, g_timeline);
+      cudaError_t le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), stage_bytes, st,  // one warp per tree
+                                  t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions, g_timeline, g_tree_trace,
+                                  chase_cap);
       if (le != cudaSuccess) return cuda_fail(le, "tree_step_kernel launch");
     }
     EAZ_CHECK_LAUNCH("tree_step_kernel");
@@ -753,5 +758,8 @@ int eaz_search_gumbel_profiled(const eaz_search_config* cfg, const eaz_search_in
   if (e != cudaSuccess) return cuda_fail(e, "profiled search sync");
   return rc;
 }
+
+// Debug hook (not in the public header): device buffer of (n+1)*B*8 int64 receiving per-tree section stamps of tree_step_kernel.
+void eaz_debug_set_tree_trace(long long* device_buffer) { eaz::g_tree_trace = device_buffer; }
 
 }  // extern "C"

@@ -10,8 +10,20 @@
 //              32/G nodes at a time, G lanes per node, and cached in the node record together with the child it
 //              leads to.  This is the same arithmetic on the same inputs the descent would evaluate, but all
 //              levels are independent here, so they run in parallel instead of one after the other;
-//   4. simulate (A.3) for the next simulation: a pure pointer chase over the cached (action, child) pairs, one
-//              16-byte load per level, recording the path;  [+ the DeepSea transition, context.py:127].
+//   4. simulate (A.3) for the next simulation: a pure pointer chase over the cached (action, child) pairs,
+//              recording the path;  [+ the DeepSea transition, context.py:127].
+//
+// Two code paths with identical arithmetic:
+//   * STAGED (the common case, A <= 32): the kernel is launched programmatically (PDL) while the network kernel of
+//     this simulation is still running.  Everything the steps above read EXCEPT the network outputs was written by
+//     earlier tree / env kernels, which are complete by then (the network kernel triggers its dependents only
+//     after its own grid-dependency wait).  So BEFORE griddepcontrol.wait the warp stages all of it -- path, node
+//     and edge records of the path nodes, cached selections and compact states of every node -- in its slice of
+//     shared memory (the wait invalidates L1, so an L1 prefetch would not survive: profiles/micro/pdl_l1.cu).
+//     After the wait the only global loads on the critical path are the network outputs; the backward's edge
+//     updates are patched into the staged copies in registers instead of being re-read from memory.
+//   * DIRECT: load-as-you-go, used for A > 32, for the first launch of a search, and for paths longer than the
+//     staging area.
 #pragma once
 
 namespace eaz {
@@ -19,14 +31,150 @@ namespace eaz {
 // cached selection in NodeRec.pad0: bits 0..7 action, bits 8.. child index + 1 (0 = unvisited)
 __device__ __forceinline__ int pack_next(int action, int child) { return action | ((child + 1) << 8); }
 
+// gumbel_muzero_root_action_selection / gumbel_muzero_interior_action_selection for the lane group's node
+// (mctx action_selection.py).  Returns the selected action; *child = children_index[node, act].
+template <int G, int J>
+__device__ __forceinline__ int select_action(const Tree& t, const SearchParams& sp, const Edge<G, J>& e, const bool (&valid)[J], float raw,
+                                             float raw_var, float beta, bool is_root, unsigned ub, unsigned uA,
+                                             const uint8_t* __restrict__ invalid, int lane, int gl, int* child) {
+  float cq[J];
+  int sumN, maxN, act = 0;
+  const bool use_beta = is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0;
+  qtransform<G, J>(sp, e, valid, raw, raw_var, beta, use_beta, cq, sumN, maxN);
+  if (__any_sync(0xffffffffu, is_root)) {  // gumbel_muzero_root_action_selection (node 0 is level 0 of round 0)
+    float gum[J];
+    bool inval[J];
+    int num_valid = 0;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int a = gl + G * j;
+      gum[j] = (is_root && valid[j]) ? t.gumbel[ub * uA + a] : 0.0f;
+      inval[j] = (is_root && valid[j] && invalid) ? (invalid[ub * uA + a] != 0) : false;
+      num_valid += (valid[j] && !inval[j]) ? 1 : 0;
+    }
+    num_valid = group_sum_i<G>(num_valid);
+    const int num_considered = min(sp.max_considered, num_valid);
+    const int considered_visit = is_root ? t.table[num_considered * sp.n + min(sumN, sp.n - 1)] : 0;
+    act = root_argmax<G, J>(e, valid, gum, inval, cq, considered_visit, gl);
+  }
+  int act_i;
+  {  // gumbel_muzero_interior_action_selection
+    float x[J], p[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) x[j] = __fadd_rn(e.pl[j], cq[j]);
+    group_softmax<G, J>(x, valid, p);
+    const float den = (float)(1 + sumN);
+    float best = -INFINITY;
+    int besti = 1 << 30;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float s = valid[j] ? __fsub_rn(p[j], __fdiv_rn((float)e.vis[j], den)) : -INFINITY;
+      const int ia = valid[j] ? gl + G * j : (1 << 30);
+      if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
+    }
+    act_i = group_argmax<G>(best, besti);
+  }
+  if (!is_root) act = act_i;
+  // children_index[node, act]: owned by lane act % G of the group, slot act / G
+  int ci_sel = -1;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (j == act / G) ci_sel = e.ci[j];
+  *child = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
+  return act;
+}
+
+// Staging area of one warp (uint32 words); kRounds refresh rounds = kNodes nodes (path + leaf) fit.
+template <int G>
+struct Stage {
+  static constexpr int kRounds = G == 2 ? 2 : 4;
+  static constexpr int kNodes = kRounds * (32 / G);
+  static constexpr int kEdgeWords = kRounds * 9 * 32;  // [round][ci1, vis, pl, rew, val, vvar, dis, raw, rawvar][lane]
+  static constexpr int kBackWords = 4 * 32;            // [node | action << 16, visits, value, variance][level]
+  static constexpr int kMiscWords = 8;                  // term flag of the leaf, its visits before this expansion, reward bits
+  static __host__ __device__ constexpr int words(int chase_cap) { return kEdgeWords + kBackWords + kMiscWords + 2 * chase_cap; }
+};
+
 template <int G, int J>
 __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
                                                          const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid,
-                                                         unsigned long long* tl) {
+                                                         unsigned long long* tl, long long* trace, int chase_cap) {
+  extern __shared__ __align__(16) uint32_t stage_smem[];
   unsigned long long t_entry = 0;
   if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_entry = globaltimer_ns();
-  pdl_trigger();  // the next kernel (network / Subleq step) may begin its prologue now
-  pdl_wait();     // ... and this one starts only once the previous kernel's results are visible
+  const int lane = threadIdx.x & 31;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tree
+  const bool in_batch = b < t.B;                               // warp-uniform
+  const unsigned uB = (unsigned)t.B, uA = (unsigned)t.A, ub = (unsigned)(in_batch ? b : 0);
+  constexpr int kLevelsPerRound = 32 / G;
+  const int gl = lane & (G - 1), glev = lane / G;
+  bool valid[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) valid[j] = (gl + G * j) < t.A;
+
+  // ==================================================================== staging (before the grid-dependency wait)
+  using SG = Stage<G>;
+  bool staged = false;
+  int L = 0, leaf = 0;
+  uint32_t* const sw = stage_smem + (threadIdx.x >> 5) * SG::words(chase_cap);
+  uint32_t* const s_edge = sw;
+  uint32_t* const s_back = sw + SG::kEdgeWords;
+  uint32_t* const s_misc = s_back + SG::kBackWords;
+  uint32_t* const s_next = s_misc + SG::kMiscWords;  // cached selection per node
+  uint32_t* const s_state = s_next + chase_cap;      // DeepSea: compact state per node
+  if constexpr (J == 1) {
+    if (in_batch && do_backward && chase_cap > sim + 1) {
+      leaf = t.leaf[b];
+      L = t.path_len[b];
+      if (L + 1 <= SG::kNodes && L <= 32) {
+        staged = true;
+        const unsigned lslot = (unsigned)leaf * uB + ub;
+        int2 pa = make_int2(0, 0);  // backward operands, lane = level
+        if (lane < L) pa = t.path[(unsigned)lane * uB + ub];
+        if (lane < L) {
+          const uint4 nrec = reinterpret_cast<const uint4*>(t.nodes + ((unsigned)pa.x * uB + ub))[0];
+          s_back[0 * 32 + lane] = (uint32_t)pa.x | ((uint32_t)pa.y << 16);
+          s_back[1 * 32 + lane] = nrec.x;
+          s_back[2 * 32 + lane] = nrec.y;
+          s_back[3 * 32 + lane] = nrec.z;
+        }
+        // refresh operands: group glev of round r holds entry r * kLevelsPerRound + glev of (path nodes..., leaf)
+#pragma unroll
+        for (int r = 0; r < SG::kRounds; ++r) {
+          const int lev = r * kLevelsPerRound + glev;
+          if (r * kLevelsPerRound <= L) {  // warp-uniform
+            const int node = __shfl_sync(0xffffffffu, pa.x, lev & 31);
+            if (lev <= L && gl < t.A) {
+              const unsigned slot = (unsigned)(lev < L ? node : leaf) * uB + ub;
+              const uint4* p = reinterpret_cast<const uint4*>(t.edges + (size_t)(slot * uA + (unsigned)gl));
+              const uint4 h0 = p[0], h1 = p[1];
+              const uint4 n1 = reinterpret_cast<const uint4*>(t.nodes + slot)[1];
+              uint32_t* se = s_edge + r * 9 * 32 + lane;
+              se[0 * 32] = h0.x; se[1 * 32] = h0.y; se[2 * 32] = h0.z; se[3 * 32] = h0.w;
+              se[4 * 32] = h1.x; se[5 * 32] = h1.y; se[6 * 32] = h1.z;
+              se[7 * 32] = n1.x; se[8 * 32] = n1.y;
+            }
+          }
+        }
+        if (lane == 0) {
+          s_misc[2] = env.kind == EAZ_ENV_DEEPSEA ? (uint32_t)EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot])
+                                                   : (uint32_t)(t.states[(size_t)lslot * t.S + 35] & EAZ_SQ_FLAG_TERM);
+          s_misc[3] = reinterpret_cast<const uint4*>(t.nodes + lslot)[0].x;  // visits of the leaf before this expansion
+          s_misc[4] = __float_as_uint(t.reward[b]);
+        }
+        if (do_select) {  // every existing node's cached selection (and DeepSea state) for the descent
+          for (int nd = lane; nd <= sim; nd += 32) {
+            s_next[nd] = (uint32_t)t.nodes[(unsigned)nd * uB + ub].pad0;
+            if (env.kind == EAZ_ENV_DEEPSEA) s_state[nd] = reinterpret_cast<const uint32_t*>(t.states)[(unsigned)nd * uB + ub];
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+
+  pdl_wait();     // the network kernel of this simulation has finished: its outputs are visible
+  pdl_trigger();  // the next kernel (Subleq step / network) may begin its prologue now
   unsigned long long t_wait = 0;
   if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_wait = globaltimer_ns();
   struct TlExit {  // records at every exit path of the first warp
@@ -38,17 +186,174 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
       }
     }
   } tl_exit{tl, t_entry, t_wait};
-  const int lane = threadIdx.x & 31;
-  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;  // one warp per tree
-  if (b >= t.B) return;                                        // warp-uniform
-  const unsigned uB = (unsigned)t.B, uA = (unsigned)t.A, ub = (unsigned)b;
-  constexpr int kLevelsPerRound = 32 / G;
-  const int gl = lane & (G - 1), glev = lane / G;
-  bool valid[J];
-#pragma unroll
-  for (int j = 0; j < J; ++j) valid[j] = (gl + G * j) < t.A;
+  if (!in_batch) return;
+  // optional per-tree section stamps (eaz_debug_set_tree_trace): [sim][b][8] = start, expand, backward, refresh, chase, depth, L, staged
+  long long* trc = (trace && lane == 0) ? trace + ((size_t)sim * t.B + b) * 8 : nullptr;
+  if (trc) { trc[0] = clock64(); trc[7] = staged; }
+  const float beta = beta_in ? beta_in[b] : 0.0f;
 
-  int L = 0, leaf = 0;
+  if constexpr (J == 1) {
+    if (staged) {
+      // ================================================================ STAGED path (lane a holds action a's logit)
+      const unsigned lslot = (unsigned)leaf * uB + ub;
+      // ---- 1. expand
+      const float lg = lane < t.A ? t.net_logits[ub * uA + lane] : -INFINITY;
+      const float nv = t.net_value[b], nu = t.net_ube[b];
+      float m = lg;
+#pragma unroll
+      for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));  // context.py:135
+      const float pl_leaf = __fsub_rn(lg, m);                                              // legal_action_mask is all True (:137)
+      if (lane < t.A) t.edges[(size_t)(lslot * uA + lane)].pl = pl_leaf;
+      const int term = (int)s_misc[2];
+      const float value = term ? 0.0f : nv;  // :140
+      const float var = term ? 0.0f : nu;    // :141
+      float disc = sp.discount;
+      if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
+      if (term) disc = 0.0f;                              // :144
+      const float reward = __uint_as_float(s_misc[4]);
+      const uint32_t my_pa = lane < L ? s_back[lane] : 0u;
+      const int my_node = (int)(my_pa & 0xffffu), my_act = (int)(my_pa >> 16);
+      const int last_node = __shfl_sync(0xffffffffu, my_node, L - 1), last_act = __shfl_sync(0xffffffffu, my_act, L - 1);
+      if (lane == 0) {
+        // update_tree_node: the leaf's record (visits + 1: a leaf can be re-expanded under a max_depth cut-off)
+        uint4* ln = reinterpret_cast<uint4*>(t.nodes + lslot);
+        ln[0] = make_uint4(s_misc[3] + 1u, __float_as_uint(value), __float_as_uint(var), 0u);
+        ln[1] = make_uint4(__float_as_uint(value), __float_as_uint(var), (unsigned)(last_node + 1), (unsigned)(last_act + 1));
+        EdgeRec* pe0 = t.edges + (size_t)(((unsigned)last_node * uB + ub) * uA + (unsigned)last_act);
+        pe0->ci1 = leaf + 1;
+        pe0->rew = reward;  // :139
+        pe0->dis = disc;
+      }
+      if (trc) trc[1] = clock64();
+
+      // ---- 2. backward (levels L-1 .. 0) in one round: lane = level
+      const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
+      float lv = value, lvar = std_backup ? __fsqrt_rn(var) : var;
+      const bool have = lane < L;
+      int nvis = 0, cvis = 0;
+      float nval = 0.0f, nvar = 0.0f, rr = 0.0f, dd = 0.0f;
+      if (have) {
+        nvis = (int)s_back[32 + lane];
+        nval = __uint_as_float(s_back[64 + lane]);
+        nvar = __uint_as_float(s_back[96 + lane]);
+        // the traversed edge (level, action) sits in the refresh staging: round level / kLPR, group level % kLPR, lane action
+        const uint32_t* se = s_edge + (lane / kLevelsPerRound) * 9 * 32 + (lane % kLevelsPerRound) * G + my_act;
+        cvis = (int)se[1 * 32];
+        rr = __uint_as_float(se[3 * 32]);
+        dd = __uint_as_float(se[6 * 32]);
+        if (lane == L - 1) { rr = reward; dd = disc; }  // written by the expand step above
+      }
+      float my_lv = 0.0f, my_lvar = 0.0f;
+      for (int i = L - 1; i >= 0; --i) {  // the recurrences, deepest level first, in the reference's op order
+        const float r = __shfl_sync(0xffffffffu, rr, i), d = __shfl_sync(0xffffffffu, dd, i);
+        lv = __fadd_rn(r, __fmul_rn(d, lv));
+        lvar = std_backup ? __fadd_rn(0.0f, __fmul_rn(fabsf(d), lvar)) : __fadd_rn(0.0f, __fmul_rn(__fmul_rn(d, d), lvar));
+        if (lane == i) { my_lv = lv; my_lvar = lvar; }
+      }
+      const float count = (float)nvis;
+      const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(nval, count), my_lv), __fadd_rn(count, 1.0f));
+      float pvar;
+      if (std_backup) {
+        const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(nvar), count), my_lvar), __fadd_rn(count, 1.0f));
+        pvar = __fmul_rn(ps, ps);
+      } else {
+        pvar = __fdiv_rn(__fadd_rn(__fmul_rn(nvar, count), my_lvar), __fadd_rn(count, 1.0f));
+      }
+      // children_values[parent, a] = the child's CURRENT (already updated) mean: one level deeper
+      float cval = __shfl_down_sync(0xffffffffu, pv, 1), cvarr = __shfl_down_sync(0xffffffffu, pvar, 1);
+      if (lane == L - 1) { cval = value; cvarr = var; }
+      if (have) {
+        const unsigned pslot = (unsigned)my_node * uB + ub;
+        EdgeRec* pe = t.edges + (size_t)(pslot * uA + (unsigned)my_act);
+        reinterpret_cast<uint4*>(t.nodes + pslot)[0] = make_uint4((unsigned)(nvis + 1), __float_as_uint(pv), __float_as_uint(pvar), 0u);
+        pe->vis = cvis + 1;
+        *reinterpret_cast<float2*>(&pe->val) = make_float2(cval, cvarr);
+      }
+      if (trc) { trc[2] = clock64(); trc[6] = L; }
+      if (!do_select) return;
+
+      // ---- 3. refresh the cached selections of the path nodes and the leaf: staged records + this backward's updates
+#pragma unroll
+      for (int r = 0; r < SG::kRounds; ++r) {
+        if (r * kLevelsPerRound > L) break;  // warp-uniform
+        const int lev = r * kLevelsPerRound + glev;
+        const bool act_on = lev <= L;
+        const int src = lev & 31;  // the lane that owned level `lev` in the backward
+        const int node_l = __shfl_sync(0xffffffffu, my_node, src), act_l = __shfl_sync(0xffffffffu, my_act, src);
+        const float cval_l = __shfl_sync(0xffffffffu, cval, src), cvar_l = __shfl_sync(0xffffffffu, cvarr, src);
+        const float pl_l = __shfl_sync(0xffffffffu, pl_leaf, gl);
+        const int node = act_on ? (lev < L ? node_l : leaf) : 0;
+        Edge<G, 1> e;
+        e.ci[0] = -1; e.vis[0] = 0;
+        e.pl[0] = 0.0f; e.rew[0] = 0.0f; e.dis[0] = 0.0f; e.val[0] = 0.0f; e.vvar[0] = 0.0f;
+        float raw = 0.0f, raw_var = 0.0f;
+        if (act_on) {
+          const uint32_t* sg0 = s_edge + r * 9 * 32 + (lane & ~(G - 1));  // the group's action-0 lane always holds raw / raw variance
+          raw = __uint_as_float(sg0[7 * 32]);
+          raw_var = __uint_as_float(sg0[8 * 32]);
+          if (lev == L) { raw = value; raw_var = var; }  // the leaf: fresh raw values
+          if (gl < t.A) {
+            const uint32_t* se = s_edge + r * 9 * 32 + lane;
+            e.ci[0] = (int)se[0] - 1;
+            e.vis[0] = (int)se[1 * 32];
+            e.pl[0] = __uint_as_float(se[2 * 32]);
+            e.rew[0] = __uint_as_float(se[3 * 32]);
+            e.val[0] = __uint_as_float(se[4 * 32]);
+            e.vvar[0] = __uint_as_float(se[5 * 32]);
+            e.dis[0] = __uint_as_float(se[6 * 32]);
+            if (lev == L) {
+              e.pl[0] = pl_l;  // fresh priors
+            } else if (gl == act_l) {  // the edge this simulation went through
+              e.vis[0] += 1;
+              e.val[0] = cval_l;
+              e.vvar[0] = cvar_l;
+              if (lev == L - 1) { e.ci[0] = leaf; e.rew[0] = reward; e.dis[0] = disc; }
+            }
+          }
+        }
+        int child;
+        const int act = select_action<G, 1>(t, sp, e, valid, raw, raw_var, beta, act_on && node == 0, ub, uA, invalid, lane, gl, &child);
+        if (act_on && gl == 0) {
+          const int packed = pack_next(act, child);
+          t.nodes[(unsigned)node * uB + ub].pad0 = packed;
+          s_next[node] = (uint32_t)packed;
+        }
+      }
+      __syncwarp();
+      if (trc) trc[3] = clock64();
+
+      // ---- 4. simulate: follow the cached selections through the staged copy
+      int node = 0, depth = 0, action = 0, child = -1;
+      while (true) {
+        const int nx = (int)s_next[node];
+        action = nx & 0xff;
+        child = (nx >> 8) - 1;
+        if (lane == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
+        depth += 1;
+        if (child < 0 || depth >= sp.max_depth) break;
+        node = child;
+      }
+      if (trc) { trc[4] = clock64(); trc[5] = depth; }
+      if (lane == 0) {
+        const int new_leaf = child < 0 ? sim + 1 : child;  // search.py: node first expanded on simulation i gets index i+1
+        t.path_len[b] = depth;
+        t.parent[b] = node;
+        t.action[b] = action;
+        t.leaf[b] = new_leaf;
+        if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
+          uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
+          float rw;
+          const uint32_t ns = deepsea_step(s_state[node], action, env.size, env.action_map, &rw);
+          st[(unsigned)new_leaf * uB + ub] = ns;
+          t.reward[b] = rw;
+          t.cell[b] = deepsea_obs_index(ns, env.size);
+        }
+      }
+      return;
+    }
+  }
+
+  // ==================================================================== DIRECT path
   if (do_backward) {
     // ------------------------------------------------------------------ 1. expand
     leaf = t.leaf[b];
@@ -81,6 +386,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
       pe0->dis = disc;
     }
     __syncwarp();
+    if (trc) trc[1] = clock64();
 
     // ------------------------------------------------------------------ 2. backward (levels L-1 .. 0)
     const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
@@ -137,13 +443,13 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
       below_var = __shfl_sync(0xffffffffu, pvar, 0);
     }
     __syncwarp();
+    if (trc) { trc[2] = clock64(); trc[6] = L; }
   }
   if (!do_select) return;
 
   // -------------------------------------------------------------------- 3. refresh the cached selections
   // nodes: path levels 0..L-1 and the new leaf (index L); before the first simulation only the root.
   {
-    const float beta = beta_in ? beta_in[b] : 0.0f;
     const int nrefresh = do_backward ? L + 1 : 1;
     for (int base = 0; base < nrefresh; base += kLevelsPerRound) {
       const int lev = base + glev;
@@ -155,53 +461,12 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
       float raw, raw_var;
       load_edges<G, J>(t, slot, gl, act_on, e);
       load_node_raw(t, slot, act_on, raw, raw_var);
-      float cq[J];
-      int sumN, maxN, act;
-      const bool is_root = act_on && node == 0;
-      const bool use_beta = is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0;
-      qtransform<G, J>(sp, e, valid, raw, raw_var, beta, use_beta, cq, sumN, maxN);
-      if (__any_sync(0xffffffffu, is_root)) {  // gumbel_muzero_root_action_selection (node 0 is level 0 of round 0)
-        float gum[J];
-        bool inval[J];
-        int num_valid = 0;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const int a = gl + G * j;
-          gum[j] = (is_root && valid[j]) ? t.gumbel[ub * uA + a] : 0.0f;
-          inval[j] = (is_root && valid[j] && invalid) ? (invalid[ub * uA + a] != 0) : false;
-          num_valid += (valid[j] && !inval[j]) ? 1 : 0;
-        }
-        num_valid = group_sum_i<G>(num_valid);
-        const int num_considered = min(sp.max_considered, num_valid);
-        const int considered_visit = is_root ? t.table[num_considered * sp.n + min(sumN, sp.n - 1)] : 0;
-        act = root_argmax<G, J>(e, valid, gum, inval, cq, considered_visit, gl);
-      }
-      int act_i;
-      {  // gumbel_muzero_interior_action_selection
-        float x[J], p[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) x[j] = __fadd_rn(e.pl[j], cq[j]);
-        group_softmax<G, J>(x, valid, p);
-        const float den = (float)(1 + sumN);
-        float best = -INFINITY;
-        int besti = 1 << 30;
-#pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const float s = valid[j] ? __fsub_rn(p[j], __fdiv_rn((float)e.vis[j], den)) : -INFINITY;
-          const int ia = valid[j] ? gl + G * j : (1 << 30);
-          if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
-        }
-        act_i = group_argmax<G>(best, besti);
-      }
-      if (!is_root) act = act_i;
-      // children_index[node, act]: owned by lane act % G of the group, slot act / G
-      int ci_sel = -1;
-#pragma unroll
-      for (int j = 0; j < J; ++j) if (j == act / G) ci_sel = e.ci[j];
-      const int child = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
+      int child;
+      const int act = select_action<G, J>(t, sp, e, valid, raw, raw_var, beta, act_on && node == 0, ub, uA, invalid, lane, gl, &child);
       if (act_on && gl == 0) t.nodes[slot].pad0 = pack_next(act, child);
     }
     __syncwarp();
+    if (trc) trc[3] = clock64();
   }
 
   // -------------------------------------------------------------------- 4. simulate: follow the cached selections
@@ -242,6 +507,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
       node = child;
     }
   }
+  if (trc) { trc[4] = clock64(); trc[5] = depth; }
   if (lane == 0) {
     const int new_leaf = child < 0 ? sim + 1 : child;  // search.py: node first expanded on simulation i gets index i+1
     t.path_len[b] = depth;
