@@ -35,7 +35,12 @@ struct MlpOutputs {
 struct TensorWeights {
   const uint32_t* img[4][3];
   int k1pad;
+  const void* h1[4];  // one-hot observations (DeepSea): pre-activated, pre-split layer-1 rows per cell (mlp_gather.cu)
 };
+size_t gather_table_bytes(const NetDesc& net);
+int prepare_gather_table(const NetDesc& net, int head, void* buf, cudaStream_t st);
+int launch_mlp_gather(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,
+                      const MlpOutputs& out, cudaStream_t stream);
 size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env);
 int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mask, void* buf, TensorWeights* tw, cudaStream_t st);
 int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,

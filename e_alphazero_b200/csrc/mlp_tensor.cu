@@ -522,7 +522,7 @@ static int k1pad_of(int D) { return (D + kCK - 1) / kCK * kCK; }
 
 size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env) {
   const int np3 = (net.A + 15) & ~15;
-  const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? 0 : (size_t)k1pad_of(net.D) * 2 * kH * 2;
+  const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? gather_table_bytes(net) : (size_t)k1pad_of(net.D) * 2 * kH * 2;
   const size_t l2 = (size_t)kH * 2 * kH * 2;
   const size_t per_head = l1 + l2 + (size_t)kH * 2 * np3 * 2;
   return 4 * ((per_head + 255) & ~(size_t)255);
@@ -535,7 +535,7 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
   }
   const int k1pad = k1pad_of(net.D);
   const bool has_l1 = env.kind != EAZ_ENV_DEEPSEA;
-  const size_t l1 = has_l1 ? (size_t)k1pad * 2 * kH * 2 : 0, l2 = (size_t)kH * 2 * kH * 2;
+  const size_t l1 = has_l1 ? (size_t)k1pad * 2 * kH * 2 : gather_table_bytes(net), l2 = (size_t)kH * 2 * kH * 2;
   const size_t per_head = tensor_weights_bytes(net, env) / 4;
   tw->k1pad = k1pad;
   for (int h = 0; h < 4; ++h) {
@@ -543,10 +543,14 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     tw->img[h][0] = (const uint32_t*)p;
     tw->img[h][1] = (const uint32_t*)(p + l1);
     tw->img[h][2] = (const uint32_t*)(p + l1 + l2);
+    tw->h1[h] = has_l1 ? nullptr : p;
     if (!(heads_mask & (1 << h))) continue;
     const int nout = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
-    if (has_l1)
+    if (has_l1) {
       if (int rc = launch_tile_weights_f16(net.w[h][0], net.D, kH, k1pad, kH, kWScale, p, st)) return rc;
+    } else {
+      if (int rc = prepare_gather_table(net, h, p, st)) return rc;
+    }
     if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, kWScale, p + l1, st)) return rc;
     if (int rc = launch_tile_weights_f16(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, kWScale, p + l1 + l2, st)) return rc;
   }
@@ -560,6 +564,7 @@ int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& s
     if (heads_mask & (1 << h)) hl.head[hl.n++] = h;
   if (hl.n == 0 || B == 0) return 0;
   const bool gather = env.kind == EAZ_ENV_DEEPSEA && src.compact != nullptr;
+  if (gather && net.A <= 4) return launch_mlp_gather(net, env, src, tw, B, heads_mask, out, stream);  // one-hot rows: mlp_gather.cu
   int bits_words = gather ? 0 : (tw.k1pad + 31) / 32;
   if (bits_words > kBitsWordsMax) bits_words = 0;  // too wide for shared memory: bits are derived per chunk instead
   const size_t smem = kTensorSmemFixed + (size_t)bits_words * kTM * 4;

@@ -668,7 +668,7 @@ int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env
   EnvDesc d;
   if (!cfg || make_env_desc(env, &d)) return -1;
   const int per_sim = 1 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
-  const int prep = cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * (d.kind == EAZ_ENV_DEEPSEA ? 2 : 3) : 0;  // weight tiling, 3 heads
+  const int prep = cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * 3 : 0;  // weight tiling / layer-1 row table, 3 heads
   // 1 memset + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
   return 1 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1 + 1;  // (+1 network launch with a fused root)
 }
