@@ -249,6 +249,8 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
     t_wall0 = time.time()
     for i in range(args.steps):
         flush.zero_()
+        if i % args.param_refresh == 0:  # a new selfplay() call = possibly new parameters: rebuild the parameter-derived tables
+            runner.params_updated()
         ev[i][0].record()
         states, out = one_step(states)
         ev[i][1].record()
@@ -276,6 +278,8 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
     for i in range(args.steps + 2):
         flush.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if i >= 2 and (i - 2) % args.param_refresh == 0:
+            runner.params_updated()
         a.record()
         for k in fields:
             dstates[k].copy_(host_in[k], non_blocking=True)
@@ -358,15 +362,18 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
             dist.destroy_process_group()
         return
     cpu = cpu_baseline(kind, kw, n, gamma) if world == 1 and not args.no_cpu_baseline else None
+    n_full = (args.steps + args.param_refresh - 1) // args.param_refresh  # steps that rebuilt the parameter-derived tables
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": desc, "envs_per_gpu": B, "num_simulations": n, "mlp_mode": "exact_fp32" if args.mlp_mode == 0 else "tensor",
                        "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": not args.no_graph, "fused_root": not args.no_fused_root, "directed_exploration": True, "beta": "linspace(0,1,B)",
+                       "param_refresh": f"weight images / novelty / seq-halving tables rebuilt every {args.param_refresh} steps (selfplay_steps of the reference, config.py:37,105), reused in between",
                        "multi_gpu": "envs sharded per rank, params broadcast once, compact trajectory all-gather per step" if world > 1 else "single GPU"},
             "simulations_per_s": value * n, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": runner.launches_per_step * args.steps, "roofline": roofline, "cpu_baseline": cpu}
+            "gpu_launches": n_full * runner.launches_per_step + (args.steps - n_full) * runner.launches_per_step_reuse, "roofline": roofline,
+            "cpu_baseline": cpu}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -399,6 +406,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mlp-mode", type=int, default=1, help="0 = fp32 FMA chains (bit-exact contract), 1 = tcgen05 3xTF32 (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--param-refresh", type=int, default=8,
+                    help="rebuild the parameter-derived tables every N steps (the reference runs selfplay_steps=8 DeepSea steps per model, config.py:105)")
     ap.add_argument("--no-fused-root", action="store_true", help="evaluate the root network with a separate eaz_mlp_forward_states call")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")
     args = ap.parse_args()

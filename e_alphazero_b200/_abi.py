@@ -27,6 +27,7 @@ FLAG_BETA_INTERIOR = 1 << 0
 FLAG_BETA_RAW = 1 << 1
 FLAG_BETA_FINAL = 1 << 2
 FLAG_BACKUP_STD = 1 << 3
+FLAG_REUSE_PREPARED = 1 << 4
 SEARCH_DEFAULT_FLAGS = FLAG_BETA_INTERIOR | FLAG_BETA_RAW | FLAG_BETA_FINAL
 
 MLP_EXACT = 0

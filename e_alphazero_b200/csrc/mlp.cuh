@@ -42,7 +42,8 @@ int prepare_gather_table(const NetDesc& net, int head, void* buf, cudaStream_t s
 int launch_mlp_gather(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,
                       const MlpOutputs& out, cudaStream_t stream);
 size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env);
-int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mask, void* buf, TensorWeights* tw, cudaStream_t st);
+// fill == false only recomputes the pointers into `buf` (the images written by an earlier call are reused)
+int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mask, void* buf, TensorWeights* tw, cudaStream_t st, bool fill = true);
 int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,
                       const MlpOutputs& out, cudaStream_t stream);
 

@@ -91,6 +91,13 @@ __device__ __forceinline__ void store_a_chunk(uint8_t* stage, int row, const flo
   }
 }
 
+// Barrier wait for a whole warp with ONE polling lane: hundreds of threads spinning on mbarrier.try_wait starve the
+// shared-memory pipe that the operand stores and TMEM loads of the other warps go through (measured in mlp_gather.cu).
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
+  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
+  __syncwarp();
+}
+
 struct TensorHeads {
   int n;
   int head[4];
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         }
       } else {  // previous layer's accumulator from TMEM
         if (!waited[layer - 1]) {
-          mbar_wait(&sh->acc_done[layer - 1], 0);
+          warp_wait(&sh->acc_done[layer - 1], 0);
           tc_fence_after();
           waited[layer - 1] = true;
         }
@@ -357,7 +364,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
           for (int i = 0; i < kCK; ++i) v[i] = 0.0f;
         }
       }
-      mbar_wait(&sh->empty[s], ph ^ 1);
+      warp_wait(&sh->empty[s], ph ^ 1);
       store_a_chunk(sA + s * kAStage, row, v, layer != 0);
       fence_proxy_async();
       __syncwarp();
@@ -437,7 +444,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
     float y3[kSimtOutMax] = {0.0f, 0.0f, 0.0f, 0.0f};
     if (simt3) {
       if (!waited[1]) {
-        mbar_wait(&sh->acc_done[1], 0);
+        warp_wait(&sh->acc_done[1], 0);
         tc_fence_after();
         waited[1] = true;
       }
@@ -472,7 +479,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         y3[0] = __fadd_rn(y3[0], o.x); y3[1] = __fadd_rn(y3[1], o.y); y3[2] = __fadd_rn(y3[2], o.z); y3[3] = __fadd_rn(y3[3], o.w);
       }
     } else {
-      mbar_wait(&sh->acc_done[2], 0);
+      warp_wait(&sh->acc_done[2], 0);
       tc_fence_after();
     }
     // ---- head epilogue
@@ -528,7 +535,7 @@ size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env) {
   return 4 * ((per_head + 255) & ~(size_t)255);
 }
 
-int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mask, void* buf, TensorWeights* tw, cudaStream_t st) {
+int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mask, void* buf, TensorWeights* tw, cudaStream_t st, bool fill) {
   if (net.H != kH) {
     set_error("tensor network path needs hidden size %d (got %d); use mlp_mode EXACT", kH, net.H);
     return EAZ_ERR_UNSUPPORTED;
@@ -544,7 +551,7 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     tw->img[h][1] = (const uint32_t*)(p + l1);
     tw->img[h][2] = (const uint32_t*)(p + l1 + l2);
     tw->h1[h] = has_l1 ? nullptr : p;
-    if (!(heads_mask & (1 << h))) continue;
+    if (!fill || !(heads_mask & (1 << h))) continue;
     const int nout = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
     if (has_l1) {
       if (int rc = launch_tile_weights_f16(net.w[h][0], net.D, kH, k1pad, kH, kWScale, p, st)) return rc;

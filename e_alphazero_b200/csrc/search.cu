@@ -668,9 +668,10 @@ int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env
   EnvDesc d;
   if (!cfg || make_env_desc(env, &d)) return -1;
   const int per_sim = 1 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
-  const int prep = cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * 3 : 0;  // weight tiling / layer-1 row table, 3 heads
-  // 1 memset + seq-halving table + pack + root init (+ DeepSea seen table) + finalize
-  return 1 + 3 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0) + prep + per_sim * cfg->num_simulations + 1 + 1;  // (+1 network launch with a fused root)
+  const bool build_tables = (cfg->flags & EAZ_FLAG_REUSE_PREPARED) == 0;
+  const int prep = (cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * 3 : 0) + 1 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0);  // weight images, seq-halving + seen tables
+  // 1 memset + pack + root init + [tables] + per simulation + last tree step + finalize  (+1 network launch with a fused root)
+  return 1 + 2 + (build_tables ? prep : 0) + per_sim * cfg->num_simulations + 1 + 1;
 }
 
 int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
@@ -694,15 +695,18 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   ProfScope* init_scope = new ProfScope(CLS_INIT, st);
   cudaError_t e = cudaMemsetAsync((uint8_t*)workspace + L.zero_begin, 0, L.zero_end - L.zero_begin, st);
   if (e != cudaSuccess) return cuda_fail(e, "search memset");
-  seq_halving_table_kernel<<<ceil_div(cfg->max_num_considered_actions + 1, 32), 32, 0, st>>>(cfg->max_num_considered_actions, n, t.table);
-  EAZ_CHECK_LAUNCH("seq_halving_table_kernel");
+  const bool build_tables = (cfg->flags & EAZ_FLAG_REUSE_PREPARED) == 0;  // parameter-derived tables: once per model, not per search
+  if (build_tables) {
+    seq_halving_table_kernel<<<ceil_div(cfg->max_num_considered_actions + 1, 32), 32, 0, st>>>(cfg->max_num_considered_actions, n, t.table);
+    EAZ_CHECK_LAUNCH("seq_halving_table_kernel");
+  }
   if (int rc = eaz_env_compact(in->env, in->embedding, t.states, B, stream)) return rc;  // node 0 = roots
-  if (env.kind == EAZ_ENV_DEEPSEA)
+  if (env.kind == EAZ_ENV_DEEPSEA && build_tables)
     if (int rc = launch_deepsea_seen_table(net, env, t.ds_seen, st)) return rc;
   TensorWeights tw{};
   if (cfg->mlp_mode == EAZ_MLP_TENSOR) {
     const int lhead = cfg->exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;
-    if (int rc = prepare_tensor_weights(net, env, (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead), t.wimg, &tw, st)) return rc;
+    if (int rc = prepare_tensor_weights(net, env, (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead), t.wimg, &tw, st, build_tables)) return rc;
   }
   delete init_scope;
 

@@ -353,6 +353,7 @@ class SearchPlan:
     workspace: object = None
     out: dict = field(default_factory=dict)
     num_launches: int = 0
+    num_launches_reuse: int = 0
 
     def __post_init__(self):
         torch = require_cuda()
@@ -367,10 +368,17 @@ class SearchPlan:
         B, N, A = self.cfg.batch, self.cfg.num_simulations + 1, self.env.num_actions
         self.out = alloc_search_outputs(B, N, A, self.env.compact_bytes, self.want_tree, self.device)
         self.num_launches = load().eaz_search_num_launches(C.byref(self.cfg), C.byref(e))
+        cfg_reuse = _abi.EazSearchConfig.from_buffer_copy(self.cfg)
+        cfg_reuse.flags |= _abi.FLAG_REUSE_PREPARED
+        self.num_launches_reuse = load().eaz_search_num_launches(C.byref(cfg_reuse), C.byref(e))
 
     PROFILE_CLASSES = ("init", "select", "env_step", "network", "expand_backward", "finalize", "export")
 
-    def run(self, root: dict, profile: bool = False):
+    def invalidate(self):
+        """The model (weights / hash set) changed: the next run rebuilds the parameter-derived tables in the workspace."""
+        self._prepared = False
+
+    def run(self, root: dict, profile: bool = False, reuse_prepared: bool | None = None):
         """root: prior_logits [B,A], value [B], value_epistemic_variance [B], beta [B], embedding (state dict),
         gumbel [B,A] pre-drawn standard Gumbel noise, optional invalid_actions [B,A] (bool/uint8)."""
         import torch
@@ -385,13 +393,19 @@ class SearchPlan:
         o = _abi.EazSearchOutputs()
         for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
             setattr(o, name, _ptr(self.out.get(name)))
+        # parameter-derived tables (seq-halving table, seen table, weight images) live in the workspace across runs
+        reuse = getattr(self, "_prepared", False) if reuse_prepared is None else reuse_prepared
+        cfg = _abi.EazSearchConfig.from_buffer_copy(self.cfg)
+        if reuse:
+            cfg.flags |= _abi.FLAG_REUSE_PREPARED
+        self._prepared = True
         if profile:  # measurement aid: synchronises; returns (outputs, {class: (ms, launches)})
             ms = (C.c_float * len(self.PROFILE_CLASSES))()
             cnt = (C.c_int32 * len(self.PROFILE_CLASSES))()
-            check(load().eaz_search_gumbel_profiled(C.byref(self.cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream(), ms, cnt),
+            check(load().eaz_search_gumbel_profiled(C.byref(cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream(), ms, cnt),
                   "eaz_search_gumbel_profiled")
             return self.out, {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
-        check(load().eaz_search_gumbel(C.byref(self.cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream()), "eaz_search_gumbel")
+        check(load().eaz_search_gumbel(C.byref(cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream()), "eaz_search_gumbel")
         return self.out
 
 

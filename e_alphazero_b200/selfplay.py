@@ -40,50 +40,74 @@ class SelfplayRunner:
         self.A = env_spec.num_actions
         # launches per step: compact+mlp (root forward), search, env step
         self.launches_per_step = 2 + self.plan.num_launches + 1  # (fused root: pack+mlp are replaced by one network launch inside the search)
-        # CUDA graph of one whole step (root forward -> search -> env step): the launch sequence is fixed and nothing
-        # synchronises or allocates, so it is captured once and replayed; the noise is drawn outside the graph.
+        self.launches_per_step_reuse = 2 + self.plan.num_launches_reuse + 1  # steps that reuse the parameter-derived tables
+        # CUDA graph of one whole step (noise draw -> root forward -> search -> env step): the launch sequence is fixed and
+        # nothing synchronises or allocates, so it is captured once and replayed.  Two variants exist: the first step
+        # after a parameter update rebuilds the parameter-derived tables (weight images, novelty table, seq-halving
+        # table), the others reuse them (EAZ_FLAG_REUSE_PREPARED) -- the model is constant within one selfplay() scan.
         self.use_graph = use_graph
         self.fused_root = fused_root  # let the search evaluate the root network itself (same kernels, one launch less path)
-        self._graph = None
+        self._graphs = {}
         self._static = None
+        self._stale = True
+
+    def params_updated(self):
+        """Call after the network parameters / hash set changed (learner update, broadcast)."""
+        self.plan.invalidate()
+        self._stale = True
 
     def draw_gumbel(self):
         torch = require_cuda()
         u = torch.rand((self.B, self.A), device=self.device, generator=self.gen).clamp_(1e-20, 1.0 - 1e-7)
         return (-(-u.log()).log()).contiguous()
 
+    def _draw_tasks(self):
+        torch = require_cuda()
+        idx = torch.randint(0, self.tasks.numel(), (self.B,), device=self.device, generator=self.gen)
+        return self.tasks[idx].contiguous()
+
     def step(self, states: dict, gumbel=None, task_ids=None):
         """states: device state dict (updated in place).  Returns (states, SelfplayOutput)."""
-        torch = require_cuda()
         if self.use_graph:
             return self._step_graph(states, gumbel, task_ids)
-        return self._step_eager(states, gumbel, task_ids)
+        reuse = not self._stale
+        self._stale = False
+        return self._step_eager(states, gumbel, task_ids, reuse_prepared=reuse)
 
     def _step_graph(self, states, gumbel, task_ids):
         torch = require_cuda()
-        if gumbel is None:
-            gumbel = self.draw_gumbel()
-        if task_ids is None and self.env.kind == _abi.ENV_SUBLEQ:
-            idx = torch.randint(0, self.tasks.numel(), (self.B,), device=self.device, generator=self.gen)
-            task_ids = self.tasks[idx]
-        if self._graph is None:
+        subleq = self.env.kind == _abi.ENV_SUBLEQ
+        if self._static is None:
             st = {k: v.clone() for k, v in states.items()}
-            sg = gumbel.clone()
-            stt = task_ids.clone() if task_ids is not None else None
-            self._step_eager({k: v.clone() for k, v in st.items()}, sg, stt)  # warm-up: one-time attribute setup / allocations
+            sg = torch.zeros((self.B, self.A), dtype=torch.float32, device=self.device)
+            stt = torch.ones(self.B, dtype=torch.int32, device=self.device) if subleq else None
+            self._step_eager({k: v.clone() for k, v in st.items()}, self.draw_gumbel(), self._draw_tasks() if subleq else None,
+                             reuse_prepared=False)  # warm-up: one-time attribute setup / allocations
             torch.cuda.synchronize()
+            self._static = (st, sg, stt)
+        st, sg, stt = self._static
+        draw = gumbel is None and (task_ids is None or not subleq)  # noise drawn inside the graph unless the caller supplies it
+        key = (not self._stale, draw)
+        if key not in self._graphs:
             g = torch.cuda.CUDAGraph()
+            g.register_generator_state(self.gen)
             with torch.cuda.graph(g):
-                _, out = self._step_eager(st, sg, stt)
-            self._graph, self._static = g, (st, sg, stt, out)
-        st, sg, stt, out = self._static
+                if draw:
+                    sg.copy_(self.draw_gumbel())
+                    if subleq:
+                        stt.copy_(self._draw_tasks())
+                _, out = self._step_eager(st, sg, stt, reuse_prepared=key[0])
+            self._graphs[key] = (g, out)
+        g, out = self._graphs[key]
         for k in st:
             if states[k].data_ptr() != st[k].data_ptr():
                 st[k].copy_(states[k])
-        sg.copy_(gumbel)
-        if stt is not None:
-            stt.copy_(task_ids)
-        self._graph.replay()
+        if not draw:
+            sg.copy_(gumbel if gumbel is not None else self.draw_gumbel())
+            if subleq:
+                stt.copy_(task_ids if task_ids is not None else self._draw_tasks())
+        g.replay()
+        self._stale = False
         for k in st:
             if states[k].data_ptr() != st[k].data_ptr():
                 states[k].copy_(st[k])
@@ -93,7 +117,7 @@ class SelfplayRunner:
         """The graph's own state buffers (step them in place to avoid the copies in/out)."""
         return self._static[0] if self._static else None
 
-    def _step_eager(self, states: dict, gumbel=None, task_ids=None):
+    def _step_eager(self, states: dict, gumbel=None, task_ids=None, reuse_prepared=None):
         torch = require_cuda()
         if self.fused_root:  # selfplay.py:89 inside the search call (policy head = the recurrent_fn's: main.py:262)
             root = dict(beta=self.beta, embedding=states, gumbel=self.draw_gumbel() if gumbel is None else gumbel)
@@ -102,12 +126,11 @@ class SelfplayRunner:
             logits = ev["explore_logits"] if self.directed else ev["exploit_logits"]  # :93-95
             root = dict(prior_logits=logits, value=ev["value"], value_epistemic_variance=ev["ube"], beta=self.beta, embedding=states,
                         gumbel=self.draw_gumbel() if gumbel is None else gumbel)
-        out = self.plan.run(root)  # :107-117 (invalid_actions = ~legal_action_mask = none)
+        out = self.plan.run(root, reuse_prepared=reuse_prepared)  # :107-117 (invalid_actions = ~legal_action_mask = none)
         if self.fused_root:
             ev = dict(value=out["root_value"], ube=out["root_ube"])
         if task_ids is None and self.env.kind == _abi.ENV_SUBLEQ:
-            idx = torch.randint(0, self.tasks.numel(), (self.B,), device=self.device, generator=self.gen)
-            task_ids = self.tasks[idx].contiguous()
+            task_ids = self._draw_tasks()
         ops.env_step_(self.env, states, out["action"], auto_reset=True, task_ids=task_ids)  # :135
         return states, SelfplayOutput(state=states, root_value=out["value"], root_epistemic_std=out["value_epistemic_std"],
                                       value_prediction=ev["value"], ube_prediction=ev["ube"],

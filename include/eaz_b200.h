@@ -183,6 +183,11 @@ enum {
   EAZ_FLAG_BETA_RAW = 1 << 1,      /* mixed value built from raw + beta*sqrt(raw_var) */
   EAZ_FLAG_BETA_FINAL = 1 << 2,    /* final action / action_weights use the beta-adjusted qtransform */
   EAZ_FLAG_BACKUP_STD = 1 << 3,    /* back up a running mean of std instead of variance */
+  /* Not an emctx switch: the workspace still holds the parameter-derived tables (sequential-halving table, DeepSea
+   * per-cell novelty table, tensor-path weight images) that an earlier eaz_search_gumbel call with the same cfg / env /
+   * net wrote into THIS workspace -- skip rebuilding them.  The model is constant across the steps of one selfplay()
+   * scan (selfplay.py:148) and one reanalyze() call; the caller clears the flag after every learner update. */
+  EAZ_FLAG_REUSE_PREPARED = 1 << 4,
   EAZ_SEARCH_DEFAULT_FLAGS = (1 << 0) | (1 << 1) | (1 << 2)
 };
 

@@ -298,3 +298,52 @@ def test_search_fused_root(ops, kind, kw, B, expl):
     assert_tree_equal(exp, got)
     H.assert_same_bits(got["root_value"], ev["value"], "root_value")
     H.assert_same_bits(got["root_ube"], ev["ube"], "root_ube")
+
+
+@pytest.mark.parametrize("mlp_mode", [_abi.MLP_EXACT, _abi.MLP_TENSOR])
+def test_search_reuse_prepared_tables(ops, mlp_mode):
+    """EAZ_FLAG_REUSE_PREPARED: a second search on the same workspace that skips rebuilding the parameter-derived tables
+    (weight images, novelty table, seq-halving table) returns exactly what a full search returns."""
+    env = H.make_env("deepsea", seed=5, size=10)
+    net = H.make_net(env, seed=6, fill=0.5)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(batch=64, num_simulations=32, mlp_mode=mlp_mode)
+    plan = ops.SearchPlan(cfg, denv, dnet, want_tree=True)
+    fresh = ops.SearchPlan(cfg, denv, dnet, want_tree=True)
+    for seed in (1, 2, 3):
+        root = H.device_root(env, denv, H.make_root(env, net, 64, seed=seed))
+        got = {k: host(v).copy() for k, v in plan.run(root).items()}                      # seeds 2, 3 reuse the tables
+        ref = {k: host(v).copy() for k, v in fresh.run(root, reuse_prepared=False).items()}
+        for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
+            H.assert_same_bits(got[name], ref[name], f"seed {seed} {name}")
+
+
+@pytest.mark.parametrize("kind,kw,B", [("deepsea", dict(size=10), 96), ("subleq", dict(word_size=16), 64)])
+def test_selfplay_runner_graph_equals_eager(ops, kind, kw, B):
+    """SelfplayRunner: CUDA-graph replay (both graph variants: tables rebuilt / reused) == eager launches, given the same noise."""
+    import torch
+
+    from e_alphazero_b200.selfplay import SelfplayRunner
+
+    env = H.make_env(kind, seed=3, **kw)
+    net = H.make_net(env, seed=4, fill=0.5)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    runs = {}
+    for mode in ("eager", "graph"):
+        r = SelfplayRunner(denv, dnet, B, 16, 0.97, exploration_beta=1.0, directed_exploration=True, mlp_mode=_abi.MLP_TENSOR, use_graph=(mode == "graph"),
+                           fused_root=True, seed=1)
+        st = ops.env_init(denv, B, task_ids=torch.ones(B, dtype=torch.int32, device="cuda") if kind == "subleq" else None)
+        gen = torch.Generator(device="cuda").manual_seed(9)
+        acts = []
+        for step in range(5):
+            if step == 3:
+                r.params_updated()
+            u = torch.rand((B, env.num_actions), device="cuda", generator=gen).clamp_(1e-20, 1.0 - 1e-7)
+            tasks = torch.ones(B, dtype=torch.int32, device="cuda") if kind == "subleq" else None
+            st, out = r.step(st, gumbel=(-(-u.log()).log()).contiguous(), task_ids=tasks)
+            acts.append(host(out.action).copy())
+        runs[mode] = (acts, {k: host(v).copy() for k, v in st.items()})
+    for a, b in zip(runs["eager"][0], runs["graph"][0]):
+        assert (a == b).all()
+    for k in runs["eager"][1]:
+        H.assert_same_bits(runs["eager"][1][k], runs["graph"][1][k], k)
