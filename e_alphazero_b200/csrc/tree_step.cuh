@@ -84,15 +84,79 @@ __device__ __forceinline__ int select_action(const Tree& t, const SearchParams& 
   return act;
 }
 
+// STAGED path: the same selection with everything that does not depend on this simulation's network output precomputed
+// before the grid-dependency wait: p = max(tiny, softmax(prior logits)) of the node (the priors of an expanded node never
+// change) and, for the root, g2 = gumbel + (logit - max logit), the invalid flags and the considered-visit count.
+// Identical operations in identical order to qtransform / root_argmax / select_action above (J == 1).
+template <int G>
+__device__ __forceinline__ int select_action_staged(const SearchParams& sp, const Edge<G, 1>& e, bool valid, float raw, float raw_var, float p,
+                                                    float beta, bool is_root, float g2, bool inval, int considered_visit, int lane, int gl, int* child) {
+  const bool use_beta = is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0;
+  float q = __fadd_rn(e.rew[0], __fmul_rn(e.dis[0], e.val[0]));
+  if (use_beta) {
+    const float qv = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(e.dis[0], e.dis[0]), e.vvar[0]));  // reward variance == 0 (context.py:149)
+    q = __fadd_rn(q, __fmul_rn(beta, __fsqrt_rn(qv)));
+  }
+  const int sumN = group_sum_i<G>(valid ? e.vis[0] : 0);
+  const int maxN = group_max_i<G>(valid ? e.vis[0] : 0);
+  if (use_beta && (sp.flags & EAZ_FLAG_BETA_RAW)) raw = __fadd_rn(raw, __fmul_rn(beta, __fsqrt_rn(raw_var)));
+  float value = raw;
+  if (sp.mixed) {  // _compute_mixed_value with the staged prior probabilities
+    const bool vis_on = valid && e.vis[0] > 0;
+    const float sP = group_sum<G>(__fadd_rn(0.0f, vis_on ? p : 0.0f));
+    const float wq = group_sum<G>(__fadd_rn(0.0f, vis_on ? __fdiv_rn(__fmul_rn(p, q), sP) : 0.0f));
+    value = __fdiv_rn(__fadd_rn(raw, __fmul_rn((float)sumN, wq)), (float)(sumN + 1));
+  }
+  float c = e.vis[0] > 0 ? q : value;  // _complete_qvalues (reanalyze.py:32-40)
+  if (sp.rescale) {                     // _rescale_qvalues
+    const float lo = group_min<G>(valid ? c : INFINITY), hi = group_max<G>(valid ? c : -INFINITY);
+    c = __fdiv_rn(__fsub_rn(c, lo), eaz_max(__fsub_rn(hi, lo), sp.epsilon));
+  }
+  const float cq = __fmul_rn(__fmul_rn(__fadd_rn(sp.maxvisit_init, (float)maxN), sp.value_scale), c);
+  int act = 0;
+  if (__any_sync(0xffffffffu, is_root)) {  // seq_halving.score_considered + masked_argmax on the staged root terms
+    float sc = -INFINITY;
+    if (is_root && valid) {
+      sc = eaz_max(-1e9f, __fadd_rn(g2, cq));
+      sc = __fadd_rn(sc, e.vis[0] == considered_visit ? 0.0f : -INFINITY);
+      if (inval) sc = -INFINITY;
+    }
+    const int ia = valid ? gl : (1 << 30);
+    float best = -INFINITY;
+    int besti = 1 << 30;
+    if (sc > best || (sc == best && ia < besti)) { best = sc; besti = ia; }
+    act = group_argmax<G>(best, besti);
+  }
+  int act_i;
+  {  // gumbel_muzero_interior_action_selection
+    const float x = __fadd_rn(e.pl[0], cq);
+    const float m = group_max<G>(valid ? x : -INFINITY);
+    const float ex = valid ? eaz_exp(__fsub_rn(x, m)) : 0.0f;
+    const float sm = group_sum<G>(__fadd_rn(0.0f, ex));
+    const float pr = __fdiv_rn(ex, sm);
+    const float sc = valid ? __fsub_rn(pr, __fdiv_rn((float)e.vis[0], (float)(1 + sumN))) : -INFINITY;
+    const int ia = valid ? gl : (1 << 30);
+    float best = -INFINITY;
+    int besti = 1 << 30;
+    if (sc > best || (sc == best && ia < besti)) { best = sc; besti = ia; }
+    act_i = group_argmax<G>(best, besti);
+  }
+  if (!is_root) act = act_i;
+  *child = __shfl_sync(0xffffffffu, e.ci[0], (lane & ~(G - 1)) + (act & (G - 1)));
+  return act;
+}
+
 // Staging area of one warp (uint32 words); kRounds refresh rounds = kNodes nodes (path + leaf) fit.
 template <int G>
 struct Stage {
   static constexpr int kRounds = G == 2 ? 2 : 4;
   static constexpr int kNodes = kRounds * (32 / G);
-  static constexpr int kEdgeWords = kRounds * 9 * 32;  // [round][ci1, vis, pl, rew, val, vvar, dis, raw, rawvar][lane]
+  static constexpr int kLaneWords = 10;                 // ci1, vis, pl, rew, val, vvar, dis, raw, rawvar, prior probability
+  static constexpr int kEdgeWords = kRounds * kLaneWords * 32;  // [round][word][lane]
   static constexpr int kBackWords = 4 * 32;            // [node | action << 16, visits, value, variance][level]
-  static constexpr int kMiscWords = 8;                  // term flag of the leaf, its visits before this expansion, reward bits
-  static __host__ __device__ constexpr int words(int chase_cap) { return kEdgeWords + kBackWords + kMiscWords + 2 * chase_cap; }
+  static constexpr int kRootWords = 2 * 32;            // lanes 0..G-1: gumbel + (logit - max logit), invalid flag
+  static constexpr int kMiscWords = 8;                  // term flag of the leaf, reward bits, root considered-visit
+  static __host__ __device__ constexpr int words(int chase_cap) { return kEdgeWords + kBackWords + kRootWords + kMiscWords + 2 * chase_cap; }
 };
 
 template <int G, int J>
@@ -119,16 +183,18 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
   uint32_t* const sw = stage_smem + (threadIdx.x >> 5) * SG::words(chase_cap);
   uint32_t* const s_edge = sw;
   uint32_t* const s_back = sw + SG::kEdgeWords;
-  uint32_t* const s_misc = s_back + SG::kBackWords;
+  uint32_t* const s_root = s_back + SG::kBackWords;
+  uint32_t* const s_misc = s_root + SG::kRootWords;
   uint32_t* const s_next = s_misc + SG::kMiscWords;  // cached selection per node
   uint32_t* const s_state = s_next + chase_cap;      // DeepSea: compact state per node
   if constexpr (J == 1) {
     if (in_batch && do_backward && chase_cap > sim + 1) {
       leaf = t.leaf[b];
       L = t.path_len[b];
-      if (L + 1 <= SG::kNodes && L <= 32) {
+      const unsigned lslot = (unsigned)leaf * uB + ub;
+      // (a leaf that already has visits is being re-expanded under a max_depth cut-off: its priors change -> DIRECT path)
+      if (L + 1 <= SG::kNodes && L <= 32 && reinterpret_cast<const uint4*>(t.nodes + lslot)[0].x == 0u) {
         staged = true;
-        const unsigned lslot = (unsigned)leaf * uB + ub;
         int2 pa = make_int2(0, 0);  // backward operands, lane = level
         if (lane < L) pa = t.path[(unsigned)lane * uB + ub];
         if (lane < L) {
@@ -144,22 +210,43 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
           const int lev = r * kLevelsPerRound + glev;
           if (r * kLevelsPerRound <= L) {  // warp-uniform
             const int node = __shfl_sync(0xffffffffu, pa.x, lev & 31);
-            if (lev <= L && gl < t.A) {
+            const bool on = lev <= L && gl < t.A;
+            uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0, n1 = h0;
+            if (on) {
               const unsigned slot = (unsigned)(lev < L ? node : leaf) * uB + ub;
               const uint4* p = reinterpret_cast<const uint4*>(t.edges + (size_t)(slot * uA + (unsigned)gl));
-              const uint4 h0 = p[0], h1 = p[1];
-              const uint4 n1 = reinterpret_cast<const uint4*>(t.nodes + slot)[1];
-              uint32_t* se = s_edge + r * 9 * 32 + lane;
+              h0 = p[0];
+              h1 = p[1];
+              n1 = reinterpret_cast<const uint4*>(t.nodes + slot)[1];
+            }
+            // p = max(tiny, softmax(prior logits)) of _compute_mixed_value (the priors of an expanded node never change)
+            const float xl[1] = {__uint_as_float(h0.z)};
+            float pr[1];
+            group_softmax<G, 1>(xl, valid, pr);
+            if (on) {
+              uint32_t* se = s_edge + r * SG::kLaneWords * 32 + lane;
               se[0 * 32] = h0.x; se[1 * 32] = h0.y; se[2 * 32] = h0.z; se[3 * 32] = h0.w;
               se[4 * 32] = h1.x; se[5 * 32] = h1.y; se[6 * 32] = h1.z;
               se[7 * 32] = n1.x; se[8 * 32] = n1.y;
+              se[9 * 32] = __float_as_uint(eaz_max(EAZ_F32_TINY, pr[0]));
+            }
+            if (r == 0) {  // the root is level 0 of every path: its seq-halving score terms (mctx seq_halving.score_considered)
+              const bool rt = glev == 0 && gl < t.A;
+              const float gum = rt ? t.gumbel[ub * uA + gl] : 0.0f;
+              const bool inval = rt && invalid && invalid[ub * uA + gl] != 0;
+              const float m = group_max<G>(gl < t.A ? xl[0] : -INFINITY);
+              const int num_valid = group_sum_i<G>((gl < t.A && !inval) ? 1 : 0);
+              if (rt) {
+                s_root[lane] = __float_as_uint(__fadd_rn(gum, __fsub_rn(xl[0], m)));
+                s_root[32 + lane] = inval ? 1u : 0u;
+              }
+              if (lane == 0) s_misc[5] = (uint32_t)t.table[min(sp.max_considered, num_valid) * sp.n + min(sim, sp.n - 1)];
             }
           }
         }
         if (lane == 0) {
           s_misc[2] = env.kind == EAZ_ENV_DEEPSEA ? (uint32_t)EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot])
                                                    : (uint32_t)(t.states[(size_t)lslot * t.S + 35] & EAZ_SQ_FLAG_TERM);
-          s_misc[3] = reinterpret_cast<const uint4*>(t.nodes + lslot)[0].x;  // visits of the leaf before this expansion
           s_misc[4] = __float_as_uint(t.reward[b]);
         }
         if (do_select) {  // every existing node's cached selection (and DeepSea state) for the descent
@@ -217,7 +304,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
       if (lane == 0) {
         // update_tree_node: the leaf's record (visits + 1: a leaf can be re-expanded under a max_depth cut-off)
         uint4* ln = reinterpret_cast<uint4*>(t.nodes + lslot);
-        ln[0] = make_uint4(s_misc[3] + 1u, __float_as_uint(value), __float_as_uint(var), 0u);
+        ln[0] = make_uint4(1u, __float_as_uint(value), __float_as_uint(var), 0u);  // a fresh leaf (staging condition)
         ln[1] = make_uint4(__float_as_uint(value), __float_as_uint(var), (unsigned)(last_node + 1), (unsigned)(last_act + 1));
         EdgeRec* pe0 = t.edges + (size_t)(((unsigned)last_node * uB + ub) * uA + (unsigned)last_act);
         pe0->ci1 = leaf + 1;
@@ -237,7 +324,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
         nval = __uint_as_float(s_back[64 + lane]);
         nvar = __uint_as_float(s_back[96 + lane]);
         // the traversed edge (level, action) sits in the refresh staging: round level / kLPR, group level % kLPR, lane action
-        const uint32_t* se = s_edge + (lane / kLevelsPerRound) * 9 * 32 + (lane % kLevelsPerRound) * G + my_act;
+        const uint32_t* se = s_edge + (lane / kLevelsPerRound) * SG::kLaneWords * 32 + (lane % kLevelsPerRound) * G + my_act;
         cvis = (int)se[1 * 32];
         rr = __uint_as_float(se[3 * 32]);
         dd = __uint_as_float(se[6 * 32]);
@@ -286,14 +373,14 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
         Edge<G, 1> e;
         e.ci[0] = -1; e.vis[0] = 0;
         e.pl[0] = 0.0f; e.rew[0] = 0.0f; e.dis[0] = 0.0f; e.val[0] = 0.0f; e.vvar[0] = 0.0f;
-        float raw = 0.0f, raw_var = 0.0f;
+        float raw = 0.0f, raw_var = 0.0f, prior_p = 0.0f;
         if (act_on) {
-          const uint32_t* sg0 = s_edge + r * 9 * 32 + (lane & ~(G - 1));  // the group's action-0 lane always holds raw / raw variance
+          const uint32_t* sg0 = s_edge + r * SG::kLaneWords * 32 + (lane & ~(G - 1));  // the group's action-0 lane always holds raw / raw variance
           raw = __uint_as_float(sg0[7 * 32]);
           raw_var = __uint_as_float(sg0[8 * 32]);
           if (lev == L) { raw = value; raw_var = var; }  // the leaf: fresh raw values
           if (gl < t.A) {
-            const uint32_t* se = s_edge + r * 9 * 32 + lane;
+            const uint32_t* se = s_edge + r * SG::kLaneWords * 32 + lane;
             e.ci[0] = (int)se[0] - 1;
             e.vis[0] = (int)se[1 * 32];
             e.pl[0] = __uint_as_float(se[2 * 32]);
@@ -301,6 +388,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
             e.val[0] = __uint_as_float(se[4 * 32]);
             e.vvar[0] = __uint_as_float(se[5 * 32]);
             e.dis[0] = __uint_as_float(se[6 * 32]);
+            prior_p = __uint_as_float(se[9 * 32]);  // (unused for the fresh leaf: none of its children has visits)
             if (lev == L) {
               e.pl[0] = pl_l;  // fresh priors
             } else if (gl == act_l) {  // the edge this simulation went through
@@ -311,8 +399,17 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
             }
           }
         }
+        const bool is_root = act_on && node == 0;
+        float g2 = 0.0f;
+        bool inval = false;
+        int considered_visit = 0;
+        if (r == 0 && is_root && gl < t.A) {
+          g2 = __uint_as_float(s_root[lane]);
+          inval = s_root[32 + lane] != 0u;
+          considered_visit = (int)s_misc[5];
+        }
         int child;
-        const int act = select_action<G, 1>(t, sp, e, valid, raw, raw_var, beta, act_on && node == 0, ub, uA, invalid, lane, gl, &child);
+        const int act = select_action_staged<G>(sp, e, valid[0], raw, raw_var, prior_p, beta, is_root, g2, inval, considered_visit, lane, gl, &child);
         if (act_on && gl == 0) {
           const int packed = pack_next(act, child);
           t.nodes[(unsigned)node * uB + ub].pad0 = packed;
