@@ -99,6 +99,15 @@ class EazSearchConfig(C.Structure):
     ]
 
 
+class EazReanalyzeConfig(C.Structure):
+    _fields_ = [
+        ("discount", C.c_float),
+        ("exploration_beta", C.c_float),
+        ("exploration_ube_target", C.c_int32),
+        ("exploration_policy_target_temperature", C.c_float),
+    ]
+
+
 class EazSearchInputs(C.Structure):
     _fields_ = [
         ("prior_logits", _p),

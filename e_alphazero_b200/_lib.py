@@ -25,6 +25,7 @@ EXPORTS = [
     "eaz_xxhash_indices", "eaz_hash_lookup", "eaz_hash_update",
     "eaz_mlp_forward", "eaz_mlp_forward_states",
     "eaz_search_workspace_bytes", "eaz_search_gumbel", "eaz_search_gumbel_profiled", "eaz_search_num_launches",
+    "eaz_reanalyze_targets",
 ]
 
 

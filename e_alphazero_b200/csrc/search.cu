@@ -488,6 +488,71 @@ __global__ void __launch_bounds__(128) finalize_kernel(Tree t, SearchParams sp, 
   }
 }
 
+// ------------------------------------------------------------------ reanalyze targets (reanalyze.py:86-129)
+struct ReanalyzeArgs {
+  const int32_t* action;
+  const float *qvalues, *qvar, *visit_counts, *value, *value_std, *next_value, *next_rewards;
+  const uint8_t *next_terminated, *terminated, *invalid;
+  float *value_target, *ube_target, *policy_target;
+};
+
+template <int G, int J>
+__global__ void __launch_bounds__(128) reanalyze_targets_kernel(eaz_reanalyze_config cfg, int B, int A, ReanalyzeArgs r) {
+  const int lane = threadIdx.x & 31;
+  const int gl = lane & (G - 1);
+  const int b = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * (32 / G) + (lane / G);
+  const bool in_range = b < B;
+  const size_t row = (size_t)(in_range ? b : 0) * A;
+  bool valid[J];
+  float q[J], qv[J], x[J], p[J];
+  const int act = in_range ? r.action[b] : 0;
+  const float vfill = in_range ? __fadd_rn(r.value[b], __fmul_rn(cfg.exploration_beta, r.value_std[b])) : 0.0f;  // :116
+  float qmax = -INFINITY, m = -INFINITY, q_act = 0.0f, qv_act = 0.0f;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int a = gl + G * j;
+    valid[j] = a < A;
+    q[j] = (in_range && valid[j]) ? r.qvalues[row + a] : 0.0f;
+    qv[j] = (in_range && valid[j]) ? r.qvar[row + a] : 0.0f;
+    const float vc = (in_range && valid[j]) ? r.visit_counts[row + a] : 0.0f;
+    const float qs = __fadd_rn(q[j], __fmul_rn(cfg.exploration_beta, __fsqrt_rn(qv[j])));  // :114
+    x[j] = vc > 0.0f ? qs : vfill;                                                            // complete_qs :32-40
+    if (valid[j]) {
+      qmax = fmaxf(qmax, qv[j]);
+      m = fmaxf(m, x[j]);
+    }
+  }
+  qmax = group_max<G>(qmax);
+  m = group_max<G>(m);
+  {  // broadcast the chosen action's entries from their owner (lane act % G, slot act / G) -- bit-exact, unlike a sum with zeros
+    float qa = 0.0f, qva = 0.0f;
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      if (j == act / G) { qa = q[j]; qva = qv[j]; }
+    const int owner = (lane & ~(G - 1)) + (act & (G - 1));
+    q_act = __shfl_sync(0xffffffffu, qa, owner);
+    qv_act = __shfl_sync(0xffffffffu, qva, owner);
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {  // mask_invalid_actions :16-29, then the temperature :121
+    const bool inv = in_range && valid[j] && r.invalid && r.invalid[row + gl + G * j] != 0;
+    x[j] = __fmul_rn(inv ? EAZ_F32_MIN : __fsub_rn(x[j], m), cfg.exploration_policy_target_temperature);
+  }
+  group_softmax<G, J>(x, valid, p);  // :120
+  if (!in_range) return;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (valid[j]) r.policy_target[row + gl + G * j] = p[j];
+  if (gl == 0) {
+    const float not_term_next = r.next_terminated[b] ? 0.0f : 1.0f, not_term = r.terminated[b] ? 0.0f : 1.0f;
+    const float from_td = __fadd_rn(r.next_rewards[b], __fmul_rn(__fmul_rn(cfg.discount, r.next_value[b]), not_term_next));  // :94-95
+    const float vt = eaz_max(q_act, from_td);                                                                                 // :101
+    const float ut = cfg.exploration_ube_target ? qmax : qv_act;                                                              // :102-106
+    r.value_target[b] = __fmul_rn(vt, not_term);                                                                              // :109-110
+    r.ube_target[b] = __fmul_rn(ut, not_term);
+  }
+}
+
 // ------------------------------------------------------------------ optional tree export: node-major -> emctx [B,N,...]
 struct TreeOut {
   int32_t *node_visits, *parents, *action_from_parent, *children_index, *children_visits;
@@ -739,6 +804,33 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
     export_tree_kernel<<<148 * 8, 256, 0, st>>>(t, to);
     EAZ_CHECK_LAUNCH("export_tree_kernel");
   }
+  return 0;
+}
+
+int eaz_reanalyze_targets(const eaz_reanalyze_config* cfg, int32_t B, int32_t A, const int32_t* action, const float* qvalues,
+                          const float* qvalues_epistemic_variance, const float* visit_counts, const float* value,
+                          const float* value_epistemic_std, const float* next_state_value, const float* next_rewards,
+                          const uint8_t* next_terminated, const uint8_t* terminated, const uint8_t* invalid_actions,
+                          float* value_target, float* ube_target, float* exploration_policy_target, void* stream) {
+  EAZ_CHECK_ARG(cfg != nullptr && B >= 0 && A >= 1 && A <= 256, "eaz_reanalyze_targets: bad cfg / B / A (1 <= A <= 256)");
+  EAZ_CHECK_ARG(action && qvalues && qvalues_epistemic_variance && visit_counts && value && value_epistemic_std && next_state_value &&
+                    next_rewards && next_terminated && terminated && value_target && ube_target && exploration_policy_target,
+                "eaz_reanalyze_targets: NULL array");
+  if (B == 0) return 0;
+  ReanalyzeArgs r{action, qvalues, qvalues_epistemic_variance, visit_counts, value, value_epistemic_std, next_state_value, next_rewards,
+                  next_terminated, terminated, invalid_actions, value_target, ube_target, exploration_policy_target};
+  cudaStream_t st = (cudaStream_t)stream;
+#define EAZ_RUN(G, J) reanalyze_targets_kernel<G, J><<<ceil_div(B, 4 * (32 / G)), 128, 0, st>>>(*cfg, B, A, r)
+  if (A <= 2) EAZ_RUN(2, 1);
+  else if (A <= 4) EAZ_RUN(4, 1);
+  else if (A <= 8) EAZ_RUN(8, 1);
+  else if (A <= 16) EAZ_RUN(16, 1);
+  else if (A <= 32) EAZ_RUN(32, 1);
+  else if (A <= 64) EAZ_RUN(32, 2);
+  else if (A <= 128) EAZ_RUN(32, 4);
+  else EAZ_RUN(32, 8);
+#undef EAZ_RUN
+  EAZ_CHECK_LAUNCH("reanalyze_targets_kernel");
   return 0;
 }
 

@@ -165,7 +165,7 @@ def epistemic_gumbel_muzero_policy(params, rng_key, root: EpistemicRootFnOutput,
               beta=f32(beta.reshape(B)), embedding=emb, gumbel=_draw_gumbel(rng_key, (B, A), dev))
     if invalid_actions is not None:
         rd["invalid_actions"] = invalid_actions.to(torch.uint8).contiguous()
-    out = plan.run(rd)
+    out = plan.run(rd)  # (tables are rebuilt on every call: the facade cannot know whether `params` changed in place)
     out = {k: v.clone() for k, v in out.items()}  # the plan's buffers are reused by the next call
     tree = EpistemicTree(out, A, int(num_simulations))
     return PolicyOutput(action=out["action"], action_weights=out["action_weights"], search_tree=tree)

@@ -374,11 +374,7 @@ class SearchPlan:
 
     PROFILE_CLASSES = ("init", "select", "env_step", "network", "expand_backward", "finalize", "export")
 
-    def invalidate(self):
-        """The model (weights / hash set) changed: the next run rebuilds the parameter-derived tables in the workspace."""
-        self._prepared = False
-
-    def run(self, root: dict, profile: bool = False, reuse_prepared: bool | None = None):
+    def run(self, root: dict, profile: bool = False, reuse_prepared: bool = False):
         """root: prior_logits [B,A], value [B], value_epistemic_variance [B], beta [B], embedding (state dict),
         gumbel [B,A] pre-drawn standard Gumbel noise, optional invalid_actions [B,A] (bool/uint8)."""
         import torch
@@ -394,9 +390,11 @@ class SearchPlan:
         for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
             setattr(o, name, _ptr(self.out.get(name)))
         # parameter-derived tables (seq-halving table, seen table, weight images) live in the workspace across runs
-        reuse = getattr(self, "_prepared", False) if reuse_prepared is None else reuse_prepared
+        # (reuse_prepared=True is the caller's promise that env / net are unchanged since an earlier run on this plan)
         cfg = _abi.EazSearchConfig.from_buffer_copy(self.cfg)
-        if reuse:
+        if reuse_prepared:
+            if not getattr(self, "_prepared", False):
+                raise EazError("reuse_prepared=True before any search built the tables in this plan's workspace")
             cfg.flags |= _abi.FLAG_REUSE_PREPARED
         self._prepared = True
         if profile:  # measurement aid: synchronises; returns (outputs, {class: (ms, launches)})
@@ -407,6 +405,26 @@ class SearchPlan:
             return self.out, {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CLASSES)}
         check(load().eaz_search_gumbel(C.byref(cfg), C.byref(inp), C.byref(o), self._ws_ptr, self._ws_bytes, _stream()), "eaz_search_gumbel")
         return self.out
+
+
+def reanalyze_targets(discount, exploration_beta, exploration_ube_target, temperature, action, qvalues, qvalues_epistemic_variance, visit_counts,
+                      value, value_epistemic_std, next_state_value, next_rewards, next_terminated, terminated, invalid_actions=None, out=None) -> dict:
+    """eaz_reanalyze_targets (reanalyze.py:86-129) on device tensors; `out` may hold pre-allocated result tensors."""
+    torch = require_cuda()
+    f32, u8, i32 = torch.float32, torch.uint8, torch.int32
+    B, A = qvalues.shape
+    dev = qvalues.device
+    if out is None:
+        out = dict(value_target=torch.empty(B, dtype=f32, device=dev), ube_target=torch.empty(B, dtype=f32, device=dev),
+                   exploration_policy_target=torch.empty((B, A), dtype=f32, device=dev))
+    cfg = _abi.EazReanalyzeConfig(float(discount), float(exploration_beta), int(bool(exploration_ube_target)), float(temperature))
+    c = lambda t, dt: t.to(dtype=dt).contiguous()
+    keep = [c(action, i32), c(qvalues, f32), c(qvalues_epistemic_variance, f32), c(visit_counts, f32), c(value, f32), c(value_epistemic_std, f32),
+            c(next_state_value, f32), c(next_rewards.reshape(B), f32), c(next_terminated, u8), c(terminated, u8),
+            c(invalid_actions, u8) if invalid_actions is not None else None]
+    check(load().eaz_reanalyze_targets(C.byref(cfg), B, A, *[_ptr(k) for k in keep], _ptr(out["value_target"], f32), _ptr(out["ube_target"], f32),
+                                       _ptr(out["exploration_policy_target"], f32), _stream()), "eaz_reanalyze_targets")
+    return out
 
 
 def search(cfg: _abi.EazSearchConfig, env: EnvSpec, net: FcParams, root: dict, want_tree=False) -> dict:

@@ -53,7 +53,6 @@ class SelfplayRunner:
 
     def params_updated(self):
         """Call after the network parameters / hash set changed (learner update, broadcast)."""
-        self.plan.invalidate()
         self._stale = True
 
     def draw_gumbel(self):

@@ -290,6 +290,31 @@ int eaz_search_gumbel_profiled(const eaz_search_config* cfg, const eaz_search_in
  * gpu_launches accounting). */
 int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env);
 
+/* ------------------------------------------------------------------------ */
+/* reanalyze target computation (reanalyze.py:86-129) on the summary of a      */
+/* finished search: the epilogue that follows epistemic_gumbel_muzero_policy   */
+/* in reanalyze().                                                             */
+
+typedef struct eaz_reanalyze_config {
+  float discount;                              /* config.discount (reanalyze.py:94) */
+  float exploration_beta;                      /* config.exploration_beta (:114-116) */
+  int32_t exploration_ube_target;              /* config.exploration_ube_target (:106): max child uncertainty vs the chosen child's */
+  float exploration_policy_target_temperature; /* config.exploration_policy_target_temperature (:121) */
+} eaz_reanalyze_config;
+
+/* Inputs: policy_output.action [B]; search_summary.qvalues / qvalues_epistemic_variance / visit_counts [B,A],
+ * value / value_epistemic_std [B]; next_state_value [B] = forward.apply(...) on experience_pair.second.observation
+ * (:90-92); next_rewards = second.rewards.squeeze() [B]; next_terminated = second.terminated [B]; terminated =
+ * states.terminated [B]; invalid_actions = ~states.legal_action_mask [B,A] (NULL = none invalid).
+ * Outputs: value_target [B] = max(q[action], r' + discount * v(s') * !term') * !term (:87-111),
+ * ube_target [B] (:103-111), exploration_policy_target [B,A] = softmax(mask_invalid(complete_qs(q + beta*sqrt(qvar),
+ * visits, value + beta*std)) * temperature) (:113-122).  exploitation_policy_target is policy_output.action_weights. */
+int eaz_reanalyze_targets(const eaz_reanalyze_config* cfg, int32_t B, int32_t A, const int32_t* action, const float* qvalues,
+                          const float* qvalues_epistemic_variance, const float* visit_counts, const float* value,
+                          const float* value_epistemic_std, const float* next_state_value, const float* next_rewards,
+                          const uint8_t* next_terminated, const uint8_t* terminated, const uint8_t* invalid_actions,
+                          float* value_target, float* ube_target, float* exploration_policy_target, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

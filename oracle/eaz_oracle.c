@@ -1021,6 +1021,39 @@ int orc_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
 }
 
 /* eaz_math.h probes for the accuracy tests */
+/* ------------------------------------------------------------------------ */
+/* reanalyze targets: /root/reference/src/reanalyze.py:86-129                  */
+int orc_reanalyze_targets(const eaz_reanalyze_config* cfg, int32_t B, int32_t A, const int32_t* action, const float* qvalues,
+                          const float* qvar, const float* visit_counts, const float* value, const float* value_std,
+                          const float* next_state_value, const float* next_rewards, const uint8_t* next_terminated,
+                          const uint8_t* terminated, const uint8_t* invalid, float* value_target, float* ube_target,
+                          float* exploration_policy_target) {
+  if (!cfg || B < 0 || A < 1 || A > 256) return EAZ_ERR_INVALID_ARG;
+  for (int b = 0; b < B; ++b) {
+    const float* q = qvalues + (size_t)b * A;
+    const float* qv = qvar + (size_t)b * A;
+    const float* vc = visit_counts + (size_t)b * A;
+    const float from_tree = q[action[b]];                                                                  /* :87 */
+    const float not_term_next = next_terminated[b] ? 0.0f : 1.0f;
+    const float from_td = eaz_add(next_rewards[b], eaz_mul(eaz_mul(cfg->discount, next_state_value[b]), not_term_next)); /* :94-95 */
+    const float vt = eaz_max(from_tree, from_td);                                                           /* :101 jnp.maximum */
+    const float ut = cfg->exploration_ube_target ? orc_maxv(qv, A) : qv[action[b]];                         /* :102-106 */
+    const float not_term = terminated[b] ? 0.0f : 1.0f;
+    value_target[b] = eaz_mul(vt, not_term);                                                                /* :109-110 */
+    ube_target[b] = eaz_mul(ut, not_term);
+    float sc[256], masked[256];
+    const float vfill = eaz_add(value[b], eaz_mul(cfg->exploration_beta, value_std[b]));                    /* :116 */
+    for (int a = 0; a < A; ++a) {
+      const float qs = eaz_add(q[a], eaz_mul(cfg->exploration_beta, eaz_sqrt(qv[a])));                      /* :114 */
+      sc[a] = vc[a] > 0.0f ? qs : vfill;                                                                    /* complete_qs :32-40 */
+    }
+    orc_mask_invalid(sc, invalid ? invalid + (size_t)b * A : NULL, A, masked);                              /* :16-29 */
+    for (int a = 0; a < A; ++a) masked[a] = eaz_mul(masked[a], cfg->exploration_policy_target_temperature); /* :121 */
+    orc_softmax(masked, A, exploration_policy_target + (size_t)b * A);                                      /* :120 */
+  }
+  return 0;
+}
+
 float orc_expf(float x) { return eaz_exp(x); }
 float orc_tanhf(float x) { return eaz_tanh(x); }
 void orc_softmax_probe(const float* x, int32_t A, float* p) { orc_softmax(x, A, p); }

@@ -293,7 +293,71 @@ def gen_net():
     print("fcnet.npz", len(out))
 
 
+# ----------------------------------------------------------------------------- reanalyze targets (reanalyze.py:52-131)
+def gen_reanalyze():
+    """Runs the reference's reanalyze() itself.  Its two externals are stubbed with seeded arrays: the search
+    (emctx.epistemic_gumbel_muzero_policy -- not in /root/reference) returns a fixed PolicyOutput / summary, and
+    context.forward.apply returns fixed network outputs, so what is pinned is the target arithmetic :86-129."""
+    import types
+
+    import emctx as shim_emctx
+
+    rng = np.random.default_rng(11)
+    out = {}
+    cases = [(2, 33, 0.997, 0.0, True, 1.0), (16, 21, 0.97, 0.7, False, 0.5), (6, 40, 0.9, 1.5, True, 2.0)]
+    for ci, (A, B, gamma, ebeta, ube_expl, temp) in enumerate(cases):
+        visits = rng.integers(0, 4, (B, A)).astype(np.float32)
+        visits[rng.random(B) < 0.15] = 0  # rows without any visited action
+        summ = types.SimpleNamespace(
+            qvalues=jnp.array(rng.standard_normal((B, A)).astype(np.float32)),
+            qvalues_epistemic_variance=jnp.array((rng.random((B, A)) ** 2).astype(np.float32)),
+            visit_counts=jnp.array(visits),
+            value=jnp.array(rng.standard_normal(B).astype(np.float32)),
+            value_epistemic_std=jnp.array(rng.random(B).astype(np.float32)))
+        action = rng.integers(0, A, B).astype(np.int32)
+        w = rng.random((B, A)).astype(np.float32)
+        pol = types.SimpleNamespace(action=jnp.array(action), action_weights=jnp.array(w / w.sum(1, keepdims=True)),
+                                    search_tree=types.SimpleNamespace(epistemic_summary=lambda summ=summ: summ))
+        shim_emctx.epistemic_gumbel_muzero_policy = lambda pol=pol, **kw: pol
+        shim_emctx.epistemic_qtransform_completed_by_mix_value = object()
+        next_value = rng.standard_normal(B).astype(np.float32)
+        zeros = jnp.zeros((B, A), jnp.float32)
+
+        class _Forward:  # forward.apply(params, state, observation, is_training=False) -> ((exploit, explore, value, ube, rvar), state)
+            calls = 0
+
+            def apply(self, params, state, observation, is_training=False):
+                type(self).calls += 1
+                v = jnp.zeros(B, jnp.float32) if type(self).calls == 1 else jnp.array(next_value)
+                return (zeros, zeros, v, jnp.zeros(B, jnp.float32), jnp.zeros(B, jnp.float32)), state
+
+        legal = rng.random((B, A)) < 0.8
+        legal[:, 0] |= ~legal.any(1)
+        term = rng.random(B) < 0.2
+        nterm = rng.random(B) < 0.3
+        nrew = (rng.random(B) < 0.3).astype(np.float32).reshape(B, 1)
+        first = types.SimpleNamespace(observation=jnp.zeros((B, 4), bool), legal_action_mask=jnp.array(legal), terminated=jnp.array(term))
+        second = types.SimpleNamespace(observation=jnp.zeros((B, 4), bool), rewards=jnp.array(nrew), terminated=jnp.array(nterm))
+        config = types.SimpleNamespace(reanalyze_beta=0.0, reanalyze_simulations_per_step=8, discount=gamma, exploration_ube_target=ube_expl,
+                                       exploration_beta=ebeta, exploration_policy_target_temperature=temp)
+        context = types.SimpleNamespace(forward=_Forward(), reanalyze_recurrent_fn=None)
+        ro = rrean.reanalyze((None, None), config, context, types.SimpleNamespace(first=first, second=second), KEY)
+        p = f"c{ci}_"
+        out[p + "cfg"] = np.array([gamma, ebeta, float(ube_expl), temp], np.float64)
+        for k, v in (("action", action), ("qvalues", summ.qvalues), ("qvar", summ.qvalues_epistemic_variance), ("visit_counts", visits),
+                     ("value", summ.value), ("value_std", summ.value_epistemic_std), ("next_value", next_value), ("next_rewards", nrew[:, 0]),
+                     ("next_terminated", nterm.astype(np.uint8)), ("terminated", term.astype(np.uint8)), ("invalid", (~legal).astype(np.uint8)),
+                     ("value_target", np_(ro.value_target, np.float32)), ("ube_target", np_(ro.ube_target, np.float32)),
+                     ("exploration_policy_target", np_(ro.exploration_policy_target, np.float32)),
+                     ("exploitation_policy_target", np_(ro.exploitation_policy_target, np.float32))):
+            out[p + k] = np.asarray(v)
+    out["num_cases"] = np.int32(len(cases))
+    np.savez_compressed(os.path.join(OUT, "reanalyze.npz"), **out)
+    print("reanalyze.npz", len(out))
+
+
 if __name__ == "__main__":
+    gen_reanalyze()
     gen_deepsea()
     gen_hash()
     gen_net()

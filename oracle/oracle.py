@@ -339,6 +339,23 @@ def search(cfg: _abi.EazSearchConfig, env: Env, net: FcNet | None, root: dict, w
     return out
 
 
+def reanalyze_targets(discount, exploration_beta, exploration_ube_target, temperature, action, qvalues, qvar, visit_counts, value, value_std,
+                      next_state_value, next_rewards, next_terminated, terminated, invalid_actions=None) -> dict:
+    """reanalyze.py:86-129 on host arrays; returns value_target [B], ube_target [B], exploration_policy_target [B,A]."""
+    f = lambda a: np.ascontiguousarray(a, np.float32)
+    u = lambda a: np.ascontiguousarray(a, np.uint8)
+    q = f(qvalues)
+    B, A = q.shape
+    cfg = _abi.EazReanalyzeConfig(float(discount), float(exploration_beta), int(bool(exploration_ube_target)), float(temperature))
+    keep = [np.ascontiguousarray(action, np.int32), q, f(qvar), f(visit_counts), f(value), f(value_std), f(next_state_value), f(next_rewards),
+            u(next_terminated), u(terminated), u(invalid_actions) if invalid_actions is not None else None]
+    out = dict(value_target=np.zeros(B, np.float32), ube_target=np.zeros(B, np.float32), exploration_policy_target=np.zeros((B, A), np.float32))
+    rc = lib().orc_reanalyze_targets(C.byref(cfg), B, A, *[_ptr(k) for k in keep], _ptr(out["value_target"]), _ptr(out["ube_target"]),
+                                     _ptr(out["exploration_policy_target"]))
+    _chk(rc, "reanalyze_targets")
+    return out
+
+
 def expf(x: float) -> float:
     return lib().orc_expf(float(x))
 

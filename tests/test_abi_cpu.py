@@ -39,6 +39,7 @@ def test_struct_sizes_match_header():
         int main(void) {
           printf("%zu %zu %zu %zu %zu %zu ", sizeof(eaz_env), sizeof(eaz_state), sizeof(eaz_fc_params), sizeof(eaz_search_config),
                  sizeof(eaz_search_inputs), sizeof(eaz_search_outputs));
+          printf("%zu %zu ", sizeof(eaz_reanalyze_config), offsetof(eaz_reanalyze_config, exploration_policy_target_temperature));
           printf("%zu %zu %zu %zu\\n", offsetof(eaz_fc_params, binary_set), offsetof(eaz_fc_params, novelty_scale),
                  offsetof(eaz_search_config, mlp_mode), offsetof(eaz_search_outputs, embeddings));
           return 0;
@@ -48,7 +49,8 @@ def test_struct_sizes_match_header():
         subprocess.run(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), os.path.join(d, "t.c"), "-o", os.path.join(d, "t")], check=True)
         got = [int(x) for x in subprocess.run([os.path.join(d, "t")], capture_output=True, text=True, check=True).stdout.split()]
     exp = [C.sizeof(_abi.EazEnv), C.sizeof(_abi.EazState), C.sizeof(_abi.EazFcParams), C.sizeof(_abi.EazSearchConfig),
-           C.sizeof(_abi.EazSearchInputs), C.sizeof(_abi.EazSearchOutputs), _abi.EazFcParams.binary_set.offset,
+           C.sizeof(_abi.EazSearchInputs), C.sizeof(_abi.EazSearchOutputs), C.sizeof(_abi.EazReanalyzeConfig),
+           _abi.EazReanalyzeConfig.exploration_policy_target_temperature.offset, _abi.EazFcParams.binary_set.offset,
            _abi.EazFcParams.novelty_scale.offset, _abi.EazSearchConfig.mlp_mode.offset, _abi.EazSearchOutputs.embeddings.offset]
     assert got == exp
 

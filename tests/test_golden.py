@@ -173,3 +173,27 @@ def test_mask_invalid_actions(golden_dir):
     exp = g["mask_out"]
     got = np.where(inv > 0, np.float32(np.finfo(np.float32).min), lg - lg.max(1, keepdims=True))
     assert (got == exp).all()
+
+
+def _reanalyze_case(g, i):
+    p = f"c{i}_"
+    gamma, ebeta, ube_expl, temp = (float(x) for x in g[p + "cfg"])
+    args = dict(discount=gamma, exploration_beta=ebeta, exploration_ube_target=bool(ube_expl), temperature=temp, action=g[p + "action"],
+                qvalues=g[p + "qvalues"], qvar=g[p + "qvar"], visit_counts=g[p + "visit_counts"], value=g[p + "value"], value_std=g[p + "value_std"],
+                next_state_value=g[p + "next_value"], next_rewards=g[p + "next_rewards"], next_terminated=g[p + "next_terminated"],
+                terminated=g[p + "terminated"], invalid_actions=g[p + "invalid"])
+    exp = {k: g[p + k] for k in ("value_target", "ube_target", "exploration_policy_target")}
+    return args, exp
+
+
+def test_reanalyze_targets(golden_dir):
+    """Oracle vs the outputs of the reference's own reanalyze() (reanalyze.py:52-131) run on stubbed search / network
+    outputs: value and UBE targets bit for bit, the softmax policy target to 1e-6 (numpy's exp vs the eaz_math.h exp)."""
+    g = np.load(os.path.join(golden_dir, "reanalyze.npz"))
+    for i in range(int(g["num_cases"])):
+        args, exp = _reanalyze_case(g, i)
+        got = O.reanalyze_targets(**args)
+        assert (got["value_target"].view(np.uint32) == exp["value_target"].view(np.uint32)).all(), i
+        assert (got["ube_target"].view(np.uint32) == exp["ube_target"].view(np.uint32)).all(), i
+        np.testing.assert_allclose(got["exploration_policy_target"], exp["exploration_policy_target"], rtol=1e-6, atol=1e-7)
+        assert (got["exploration_policy_target"][args["invalid_actions"].astype(bool)] == 0).all()

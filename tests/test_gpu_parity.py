@@ -312,7 +312,7 @@ def test_search_reuse_prepared_tables(ops, mlp_mode):
     fresh = ops.SearchPlan(cfg, denv, dnet, want_tree=True)
     for seed in (1, 2, 3):
         root = H.device_root(env, denv, H.make_root(env, net, 64, seed=seed))
-        got = {k: host(v).copy() for k, v in plan.run(root).items()}                      # seeds 2, 3 reuse the tables
+        got = {k: host(v).copy() for k, v in plan.run(root, reuse_prepared=seed > 1).items()}  # seeds 2, 3 reuse the tables
         ref = {k: host(v).copy() for k, v in fresh.run(root, reuse_prepared=False).items()}
         for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
             H.assert_same_bits(got[name], ref[name], f"seed {seed} {name}")
@@ -347,3 +347,76 @@ def test_selfplay_runner_graph_equals_eager(ops, kind, kw, B):
         assert (a == b).all()
     for k in runs["eager"][1]:
         H.assert_same_bits(runs["eager"][1][k], runs["graph"][1][k], k)
+
+
+# ----------------------------------------------------------------------------- reanalyze (reanalyze.py:52-131)
+@pytest.mark.parametrize("B,A", [(1, 2), (257, 2), (100, 16), (33, 40), (9, 256)])
+def test_reanalyze_targets_bit_exact(ops, B, A):
+    rng = np.random.default_rng(A + B)
+    vis = rng.integers(0, 3, (B, A)).astype(np.float32)
+    args = dict(discount=0.97, exploration_beta=0.8, exploration_ube_target=bool(B % 2), temperature=1.5, action=rng.integers(0, A, B).astype(np.int32),
+                qvalues=rng.standard_normal((B, A)).astype(np.float32), qvar=(rng.random((B, A)) ** 2).astype(np.float32), visit_counts=vis,
+                value=rng.standard_normal(B).astype(np.float32), value_std=rng.random(B).astype(np.float32),
+                next_state_value=rng.standard_normal(B).astype(np.float32), next_rewards=rng.random(B).astype(np.float32),
+                next_terminated=(rng.random(B) < 0.3).astype(np.uint8), terminated=(rng.random(B) < 0.2).astype(np.uint8),
+                invalid_actions=(rng.random((B, A)) < 0.25).astype(np.uint8))
+    args["invalid_actions"][args["invalid_actions"].all(1), 0] = 0  # (all-invalid rows overflow to NaN under temperature > 1, as in the reference)
+    exp = O.reanalyze_targets(**args)
+    d = {k: H.to_device(v) if isinstance(v, np.ndarray) else v for k, v in args.items()}
+    got = ops.reanalyze_targets(d["discount"], d["exploration_beta"], d["exploration_ube_target"], d["temperature"], d["action"], d["qvalues"], d["qvar"],
+                                d["visit_counts"], d["value"], d["value_std"], d["next_state_value"], d["next_rewards"], d["next_terminated"],
+                                d["terminated"], d["invalid_actions"])
+    for k in exp:
+        H.assert_same_bits(host(got[k]), exp[k], k)
+
+
+def test_reanalyze_targets_golden(ops, golden_dir):
+    import os
+
+    from tests.test_golden import _reanalyze_case
+
+    g = np.load(os.path.join(golden_dir, "reanalyze.npz"))
+    for i in range(int(g["num_cases"])):
+        a, exp = _reanalyze_case(g, i)
+        d = {k: H.to_device(np.ascontiguousarray(v)) if isinstance(v, np.ndarray) else v for k, v in a.items()}
+        got = ops.reanalyze_targets(d["discount"], d["exploration_beta"], d["exploration_ube_target"], d["temperature"], d["action"], d["qvalues"], d["qvar"],
+                                    d["visit_counts"], d["value"], d["value_std"], d["next_state_value"], d["next_rewards"], d["next_terminated"],
+                                    d["terminated"], d["invalid_actions"])
+        H.assert_same_bits(host(got["value_target"]), exp["value_target"], "value_target")
+        H.assert_same_bits(host(got["ube_target"]), exp["ube_target"], "ube_target")
+        np.testing.assert_allclose(host(got["exploration_policy_target"]), exp["exploration_policy_target"], rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("kind,kw,B,use_graph", [("deepsea", dict(size=10), 70, False), ("subleq", dict(word_size=16), 48, True)])
+def test_reanalyze_runner(ops, kind, kw, B, use_graph):
+    """reanalyze(): root forward + search + next-state forward + targets on device == the same pipeline on the oracle (EXACT network)."""
+    import torch
+
+    from e_alphazero_b200.reanalyze import ReanalyzeRunner
+
+    env = H.make_env(kind, seed=31, **kw)
+    net = H.make_net(env, seed=32, fill=0.5)
+    first = H.random_states(env, B, seed=33)
+    rng = np.random.default_rng(34)
+    second = O.env_step(env, O.copy_state(first), rng.integers(0, env.num_actions, B).astype(np.int32))
+    gum = rng.gumbel(size=(B, env.num_actions)).astype(np.float32)
+    n, gamma, rbeta, ebeta = 16, 0.97, -0.5, 0.6
+    # oracle pipeline
+    ev = O.mlp_forward_states(net, env, first)
+    root = dict(prior_logits=ev["exploit_logits"], value=ev["value"], value_epistemic_variance=ev["ube"], beta=np.full(B, rbeta, np.float32),
+                embedding=first, gumbel=gum)
+    so = O.search(_abi.default_search_config(num_simulations=n, discount=gamma, exploration=0), env, net, root, want_tree=False)
+    nv = O.mlp_forward_states(net, env, second)["value"]
+    exp = O.reanalyze_targets(gamma, ebeta, True, 1.0, so["action"], so["qvalues"], so["qvalues_epistemic_variance"], so["visit_counts"], so["value"],
+                              so["value_epistemic_std"], nv, second["rewards"][:, 0], second["terminated"], first["terminated"], None)
+    # device pipeline
+    denv, dnet = H.device_env(env), H.device_net(net)
+    r = ReanalyzeRunner(denv, dnet, B, n, gamma, reanalyze_beta=rbeta, exploration_beta=ebeta, exploration_ube_target=True, temperature=1.0,
+                        mlp_mode=_abi.MLP_EXACT, use_graph=use_graph)
+    df, dsec = ops.state_to_device(denv, first), ops.state_to_device(denv, second)
+    for _ in range(2):  # second call exercises the table-reuse path / graph replay
+        targets, out = r(df, dsec, gumbel=H.to_device(gum))
+        torch.cuda.synchronize()
+        for k in exp:
+            H.assert_same_bits(host(targets[k]), exp[k], k)
+        H.assert_same_bits(host(out["action_weights"]), so["action_weights"], "action_weights")
