@@ -406,12 +406,17 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mlp-mode", type=int, default=1, help="0 = fp32 FMA chains (bit-exact contract), 1 = tcgen05 3xTF32 (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the workload's batch (exploration, not a BASELINE config)")
+    ap.add_argument("--sims", type=int, default=0, help="override the workload's simulation count")
     ap.add_argument("--param-refresh", type=int, default=8,
                     help="rebuild the parameter-derived tables every N steps (the reference runs selfplay_steps=8 DeepSea steps per model, config.py:105)")
     ap.add_argument("--no-fused-root", action="store_true", help="evaluate the root network with a separate eaz_mlp_forward_states call")
     ap.add_argument("--no-graph", action="store_true", help="launch kernels eagerly instead of replaying a CUDA graph of the step")
     args = ap.parse_args()
     kind, kw, B, n, gamma, desc = WORKLOADS[args.workload]
+    if args.envs_per_gpu or args.sims:  # exploration knobs (not the BASELINE configs): the description says so
+        B, n = args.envs_per_gpu or B, args.sims or n
+        desc += f" [overridden: {B} envs/GPU, {n} simulations]"
     if args.impl == "reference":
         run_reference(args, kind, kw, B, n, gamma, desc)
     else:
