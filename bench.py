@@ -329,6 +329,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         l1 = 0 if kind == "deepsea" else 2 * D * H  # one-hot DeepSea layer 1 is a row gather
         flops_fwd = 3 * (l1 + 2 * H * H) + 2 * (2 * H) + 2 * H * A  # 3 heads evaluated per node (value, UBE, one policy head)
         mlp_ms = prof["network"][0]
+        tensor_kernel = "mlp_gather_kernel" if kind == "deepsea" else "mlp_tensor_kernel"  # one-hot rows: mlp_gather.cu
         total_ms = sum(v[0] for v in prof.values())
         dominant = "network" if mlp_ms >= tree_ms else "tree"
         tree_gbs = (tree_bytes + io_bytes) / (tree_ms * 1e-3) / 1e9
@@ -339,13 +340,13 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
                     "avg_launch_us": 1e3 * tree_ms / max(prof["select"][1] + prof["expand_backward"][1] + prof["env_step"][1], 1),
                     "edge_traversals": V, "peak_source": which}
         mlp_obj = {"bound": "tensor", "achieved": mlp_tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": mlp_tfs / tf_peak, "traffic": None,
-                   "kernels": "mlp_exact_kernel (fp32 FMA chains, bit-exact mode)" if args.mlp_mode == 0 else "mlp_tensor_kernel (tcgen05)",
+                   "kernels": "mlp_exact_kernel (fp32 FMA chains, bit-exact mode)" if args.mlp_mode == 0 else f"{tensor_kernel} (tcgen05)",
                    "flops_per_search": flops_fwd * B * n, "ms_per_search": mlp_ms, "avg_launch_us": 1e3 * mlp_ms / max(prof["network"][1], 1),
                    "peak_source": which}
         try:  # DRAM traffic per launch from the committed ncu --set full capture (profiles/r1_traffic.json)
             traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
             tree_obj["traffic"] = traffic.get("tree_step_kernel")
-            mlp_obj["traffic"] = traffic.get("mlp_tensor_kernel") if args.mlp_mode == 1 else None
+            mlp_obj["traffic"] = traffic.get(tensor_kernel) if args.mlp_mode == 1 else None
         except (OSError, ValueError):
             pass
         roofline = dict(mlp_obj if dominant == "network" else tree_obj)

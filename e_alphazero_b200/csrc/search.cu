@@ -167,6 +167,34 @@ __global__ void pack_states_kernel(EnvDesc env, StateSoA s, uint8_t* __restrict_
   for (int i = 0; i < S - EAZ_SQ_HDR; ++i) o[EAZ_SQ_HDR + i] = i < ws ? (uint8_t)s.memory[(size_t)b * ws + i] : 0;
 }
 
+// inverse of pack_states_kernel: compact records -> pgx.State leaves (replay-buffer decode)
+__global__ void unpack_states_kernel(EnvDesc env, const uint8_t* __restrict__ in, const float* __restrict__ rewards, StateSoA s, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  s.rewards[b] = rewards ? rewards[b] : 0.0f;
+  if (env.kind == EAZ_ENV_DEEPSEA) {
+    const uint32_t v = reinterpret_cast<const uint32_t*>(in)[b];
+    s.step_count[b] = EAZ_DS_STEP(v);
+    s.col[b] = EAZ_DS_COL(v);
+    s.terminated[b] = (uint8_t)EAZ_DS_TERM(v);
+    if (s.truncated) s.truncated[b] = (uint8_t)EAZ_DS_TRUNC(v);
+    return;
+  }
+  const int S = env.compact_bytes, ws = env.ws;
+  const uint8_t* o = in + (size_t)b * S;
+  const uint16_t* h = reinterpret_cast<const uint16_t*>(o);
+  for (int i = 0; i < 8; ++i) {
+    s.input_after[(size_t)b * 8 + i] = h[i];
+    s.output_after[(size_t)b * 8 + i] = h[8 + i];
+  }
+  s.step_count[b] = h[16];
+  s.task[b] = o[34];
+  s.terminated[b] = (o[35] & EAZ_SQ_FLAG_TERM) ? 1 : 0;
+  if (s.truncated) s.truncated[b] = (o[35] & EAZ_SQ_FLAG_TRUNC) ? 1 : 0;
+  s.solved[b] = (o[35] & EAZ_SQ_FLAG_SOLVED) ? 1 : 0;
+  for (int i = 0; i < ws; ++i) s.memory[(size_t)b * ws + i] = o[EAZ_SQ_HDR + i];
+}
+
 // ------------------------------------------------------------------ sequential halving table (mctx seq_halving.py)
 __global__ void seq_halving_table_kernel(int max_considered, int n, int32_t* __restrict__ table) {
   const int m = blockIdx.x * blockDim.x + threadIdx.x;
@@ -692,6 +720,20 @@ int eaz_env_compact(const eaz_env* env, const eaz_state* state, uint8_t* out, in
   if (B == 0) return 0;
   pack_states_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(d, soa_of(state), out, B);
   EAZ_CHECK_LAUNCH("pack_states_kernel");
+  return 0;
+}
+
+int eaz_env_uncompact(const eaz_env* env, const uint8_t* compact, const float* rewards, eaz_state* out, int32_t B, void* stream) {
+  EnvDesc d;
+  if (int rc = make_env_desc(env, &d)) return rc;
+  EAZ_CHECK_ARG(compact && out && B >= 0, "eaz_env_uncompact: bad arguments");
+  EAZ_CHECK_ARG(out->step_count && out->rewards && out->terminated, "eaz_env_uncompact: step_count / rewards / terminated must be non-NULL");
+  if (d.kind == EAZ_ENV_DEEPSEA) EAZ_CHECK_ARG(out->col != nullptr, "eaz_env_uncompact: col is NULL");
+  else EAZ_CHECK_ARG(out->memory && out->task && out->solved && out->input_after && out->output_after, "eaz_env_uncompact: NULL Subleq leaf");
+  if (B == 0) return 0;
+  unpack_states_kernel<<<ceil_div(B, 128), 128, 0, (cudaStream_t)stream>>>(d, compact, rewards, soa_of(out), B);
+  EAZ_CHECK_LAUNCH("unpack_states_kernel");
+  if (out->observation) return eaz_env_observe(env, out, out->observation, B, stream);
   return 0;
 }
 

@@ -1,7 +1,7 @@
 """Multi-GPU plumbing: self-play shards by environment, one process per GPU, no collective
 inside a search.  torch.distributed (NCCL over NVLink on GPUs; gloo in the CPU tests) is used only for
 (a) the parameter / hash-bitset broadcast after a learner update and (b) the all-gather of compact
-trajectories into the replay buffer."""
+trajectories into the replay buffer, plus (c) the OR-merge of the per-rank hash bitsets after a learner update."""
 from __future__ import annotations
 
 
@@ -55,3 +55,23 @@ def all_gather_trajectory(traj, out=None):
     buf = torch.empty((world * m, traj.shape[1]), dtype=traj.dtype, device=traj.device)
     dist.all_gather_into_tensor(buf.view(-1), padded.view(-1))
     return torch.cat([buf[r * m : r * m + s] for r, s in enumerate(sizes)], 0)
+
+
+def merge_hash_sets(binary_set):
+    """OR-merge of every rank's hash bitset, in place.  BaseHash.update (hashes.py:45-50) sets bits for
+    the observations a device trained on; under the reference's pmap each device's `binary_set` then diverges and only
+    device 0's copy is ever read back (train.py:90-96, main.py:467-469).  Here every rank ends with the union.  NCCL has no
+    bitwise-OR reduction, so the 2 MiB sets are all-gathered (world x 2 MiB over NVLink) and OR-ed locally."""
+    import torch
+    import torch.distributed as dist
+
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return binary_set
+    world = dist.get_world_size()
+    buf = torch.empty((world, binary_set.numel()), dtype=binary_set.dtype, device=binary_set.device)
+    dist.all_gather_into_tensor(buf.view(-1), binary_set.contiguous().view(-1))
+    merged = buf[0]
+    for r in range(1, world):
+        merged = torch.bitwise_or(merged, buf[r])
+    binary_set.view(-1).copy_(merged)
+    return binary_set

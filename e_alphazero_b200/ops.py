@@ -210,6 +210,18 @@ def env_compact(env: EnvSpec, st: dict):
     return out
 
 
+def env_uncompact(env: EnvSpec, compact, rewards=None, with_obs=False, out: dict | None = None) -> dict:
+    """eaz_env_uncompact: compact records [B,S] (+ rewards [B]) -> state dict (the decode step of the compact replay ring)."""
+    torch = require_cuda()
+    B = compact.shape[0]
+    st = out if out is not None else alloc_state(env, B, with_obs=with_obs, device=str(compact.device))
+    e, s = env.struct(), state_struct(env, st)
+    r = None if rewards is None else rewards.reshape(B).to(torch.float32).contiguous()
+    check(load().eaz_env_uncompact(C.byref(e), _ptr(compact.contiguous(), torch.uint8), _ptr(r, torch.float32), C.byref(s), B, _stream()),
+          "eaz_env_uncompact")
+    return st
+
+
 def subleq_test_cases(task: int, ws: int):
     import numpy as np
 

@@ -170,6 +170,12 @@ int eaz_mlp_forward_states(const eaz_fc_params* net, const eaz_env* env, const e
 /* Pack pgx.State leaves into the compact in-tree encoding, out: uint8 [B, eaz_env_compact_bytes]. */
 int eaz_env_compact(const eaz_env* env, const eaz_state* state, uint8_t* out, int32_t B, void* stream);
 
+/* Inverse of eaz_env_compact: compact records [B, eaz_env_compact_bytes] (+ the rewards leaf [B], NULL = zeros, which
+ * the compact encoding does not carry) -> pgx.State leaves; `out->observation`, if non-NULL, is materialised too.
+ * This is the decode step of a compact replay buffer (the reference's flashbax buffer, main.py:217-225,383-385, stores
+ * a full pgx.State per step: 25x..2500x larger). */
+int eaz_env_uncompact(const eaz_env* env, const uint8_t* compact, const float* rewards, eaz_state* out, int32_t B, void* stream);
+
 /* ------------------------------------------------------------------------ */
 /* emctx.epistemic_gumbel_muzero_policy (selfplay.py:107-117,                  */
 /* reanalyze.py:77-85, evaluate.py:36-45) with the recurrent_fn of            */

@@ -420,3 +420,39 @@ def test_reanalyze_runner(ops, kind, kw, B, use_graph):
         for k in exp:
             H.assert_same_bits(host(targets[k]), exp[k], k)
         H.assert_same_bits(host(out["action_weights"]), so["action_weights"], "action_weights")
+
+
+# ----------------------------------------------------------------------------- compact replay ring
+@pytest.mark.parametrize("kind,kw", [("deepsea", dict(size=30)), ("subleq", dict(word_size=16)), ("subleq", dict(word_size=256, binary=False))])
+def test_uncompact_round_trip_and_replay_ring(ops, kind, kw):
+    import torch
+
+    from e_alphazero_b200.replay import CompactReplayRing
+
+    env = H.make_env(kind, seed=41, **kw)
+    denv = H.device_env(env)
+    B = 40
+    st = H.random_states(env, B, seed=42)
+    dst = ops.state_to_device(denv, st)
+    # decode(encode(state)) == state, every leaf and the observation, bit for bit
+    back = ops.env_uncompact(denv, ops.env_compact(denv, dst), dst["rewards"], with_obs=True)
+    for k in O.state_fields(env):
+        H.assert_same_bits(host(back[k]), st[k], k)
+    H.assert_same_bits(host(back["observation"]), O.env_observe(env, st), "observation")
+    # ring: sampled pairs are consecutive states of one env, i.e. second == env.step(first, the action that was played)
+    ring = CompactReplayRing(denv, 6, B, seed=3)
+    rng = np.random.default_rng(43)
+    cur, traj = dst, []
+    for t in range(9):  # wraps around the 6-slot ring
+        ring.add(cur)
+        traj.append({k: host(v).copy() for k, v in cur.items()})
+        cur = ops.env_step(denv, cur, H.to_device(rng.integers(0, env.num_actions, B).astype(np.int32)), auto_reset=True,
+                           task_ids=np.ones(B, np.int32) if kind == "subleq" else None)
+    pair = ring.sample(256)
+    stored = traj[-6:]
+    f, s2 = {k: host(v) for k, v in pair.first.items()}, {k: host(v) for k, v in pair.second.items()}
+    keys = O.state_fields(env)
+    for i in range(256):
+        hits = [(t, b) for t in range(5) for b in range(B) if all((stored[t][k][b] == f[k][i]).all() for k in keys)
+                and all((stored[t + 1][k][b] == s2[k][i]).all() for k in keys)]
+        assert hits, f"sample {i} is not a stored consecutive pair"

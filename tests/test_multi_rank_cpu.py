@@ -52,6 +52,12 @@ def _worker(rank, world, port, total, out_dir):
     traj = D.pack_trajectory(torch.from_numpy(out["action"]), torch.from_numpy(nxt["rewards"]), torch.from_numpy(nxt["terminated"]),
                              torch.from_numpy(O.env_compact(env, nxt)))
     gathered = D.all_gather_trajectory(traj)
+    # learner side: each rank marks the observations of ITS shard as seen (hashes.py:45-50), then the sets are OR-merged
+    bset = np.zeros(1 << 21, np.uint8)
+    O.hash_update(O.env_observe(env, shard).astype(np.float32), bset, 24)
+    tb = torch.from_numpy(bset)
+    D.merge_hash_sets(tb)
+    np.save(os.path.join(out_dir, f"bset{rank}.npy"), np.flatnonzero(bset))
     if rank == 0:
         np.save(os.path.join(out_dir, "gathered.npy"), gathered.numpy())
     dist.barrier()
@@ -84,3 +90,8 @@ def test_sharded_selfplay_step_matches_single_process(tmp_path, total):
     assert (got[:, 1].view(np.float32) == nxt["rewards"][:, 0]).all()
     assert (got[:, 2] == nxt["terminated"]).all()
     assert (got[:, 3].view(np.uint32) == O.env_compact(env, nxt).view(np.uint32)[:, 0]).all()
+    # merged hash sets: both ranks hold the set a single process builds from the whole batch
+    full = np.zeros(1 << 21, np.uint8)
+    O.hash_update(O.env_observe(env, H.random_states(env, total, seed=3)).astype(np.float32), full, 24)
+    for r in range(2):
+        assert (np.load(tmp_path / f"bset{r}.npy") == np.flatnonzero(full)).all()
