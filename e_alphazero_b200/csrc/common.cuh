@@ -46,6 +46,31 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
 // everything before pdl_wait() must not touch data the predecessor produces.  pdl_trigger() lets the successor start.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Per-tile completion counters (search.cu "tile flags"): a finer-grained replacement for the grid-wide PDL wait between the
+// tree kernel and the network kernel of the fused DeepSea path.  Producers make their results visible (fence) and bump the
+// counter of their 128-tree tile; consumers poll it with acquire loads.  Counters only grow within a search (zeroed at its
+// start), so a launch waits for `>= epoch * producers_per_tile`.  The spin is bounded: a protocol bug traps instead of hanging.
+constexpr int kTileRows = 128;
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// ONE thread polls (relaxed loads straight from L2, with a back-off) and then issues the acquire fence; the caller
+// releases the rest of the CTA / warp with a barrier.  Hundreds of pollers or an acquire per poll would flood the memory pipe.
+__device__ __forceinline__ void wait_counter(const int* ctr, int target) {
+  unsigned spins = 0;
+  while (ld_relaxed_gpu(ctr) < target) {
+    __nanosleep(100);
+    if (++spins > (1u << 24)) __trap();
+  }
+  __threadfence();
+}
+__device__ __forceinline__ void signal_counter(int* ctr) {  // caller: results written, __syncwarp / __syncthreads done
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], 1;" ::"l"(ctr) : "memory");
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg{};

@@ -21,6 +21,11 @@ struct MlpSource {
   const int32_t* node_index;  // optional [B]: row b's state is compact[(node_index[b]*B + b)*S]; null: compact[b*S]
   const uint8_t* ds_seen;     // optional DeepSea per-cell "seen" table [D] (replaces hashing the one-hot row)
   const int32_t* cell_index;  // optional DeepSea observation cell of row b's leaf state (written by the tree kernel)
+  // tile flags (common.cuh): wait until the tree kernel has bumped tile_done[tile] to tree_epoch * rows_in_tile instead of a
+  // grid-wide PDL wait (tree_epoch == 0: PDL wait); bump mlp_done[tile] once per head when the outputs are visible
+  const int* tile_done;
+  int tree_epoch;
+  int* mlp_done;
 };
 
 struct MlpOutputs {

@@ -128,7 +128,12 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
 
   // Every thread waits for the previous kernel (tree step) and only then lets the next tree kernel launch (tree_step.cuh).
   if (tr && threadIdx.x == 0) trace[1] = clock64();
-  pdl_wait();
+  if (src.tile_done && src.tree_epoch > 0) {  // tile flags: this tile's trees are done (one polling lane per warp)
+    if (threadIdx.x == 0) wait_counter(src.tile_done + blockIdx.x, src.tree_epoch * nrows);
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
   pdl_trigger();
   if (tr && threadIdx.x == 0) trace[2] = clock64();
   const unsigned long long tl_wait = tl_on ? globaltimer_ns() : 0ull;
@@ -312,6 +317,7 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
   }
   tc_fence_before();
   __syncthreads();
+  if (src.mlp_done && threadIdx.x == 0) signal_counter(src.mlp_done + blockIdx.x);  // (after the barrier: one cumulative release fence)
   if (warp == 8) tmem_dealloc(tmem, kH);
   if (tr && threadIdx.x == 0) trace[10] = clock64();
   if (tl_on) {

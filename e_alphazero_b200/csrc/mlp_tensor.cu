@@ -567,7 +567,7 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
 int launch_mlp_tensor(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,
                       const MlpOutputs& out, cudaStream_t stream) {
   TensorHeads hl{0, {0, 0, 0, 0}};
-  for (int h = 0; h < 4; ++h)
+  for (int h = 3; h >= 0; --h)  // policy heads first: their CTAs are the longest (layer 3 on the tensor core), so a partial last wave holds short ones
     if (heads_mask & (1 << h)) hl.head[hl.n++] = h;
   if (hl.n == 0 || B == 0) return 0;
   const bool gather = env.kind == EAZ_ENV_DEEPSEA && src.compact != nullptr;

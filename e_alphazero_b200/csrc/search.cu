@@ -19,6 +19,7 @@
 // host synchronisation, so a whole search is CUDA-graph capturable.
 #include "mlp.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace eaz {
@@ -74,6 +75,7 @@ struct Tree {
   uint8_t* wimg;  // tensor-path weight images (mlp_mode TENSOR)
   int2* path;     // [max_depth][B] (node, action) per level of the current descent
   int32_t* path_len;
+  int32_t* tile_ctr;  // [2][tiles] completion counters of the tile-flag protocol (common.cuh)
 };
 
 struct Layout {
@@ -110,6 +112,7 @@ static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, 
   put(wimg_bytes);             // 24 tensor weight images
   put((size_t)max_depth * B * 8);  // 25 path
   put((size_t)B * 4);              // 26 path_len
+  put((size_t)2 * ceil_div(B, kTileRows) * 4);  // 27 tile counters: [tiles] tree done, [tiles] network done
   L->total = o;
 }
 
@@ -134,6 +137,7 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
   t.wimg = p + L.off[24];
   t.path = (int2*)(p + L.off[25]);
   t.path_len = (int32_t*)(p + L.off[26]);
+  t.tile_ctr = (int32_t*)(p + L.off[27]);
   return t;
 }
 
@@ -634,9 +638,26 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   MlpOutputs mo{{nullptr, nullptr}, t.net_value, t.net_ube, nullptr};
   mo.logits[lhead - EAZ_HEAD_EXPLOIT] = t.net_logits;
   const float *root_logits = in->prior_logits, *root_value = in->value, *root_var = in->value_epistemic_variance;
+  // Tile flags (common.cuh) between the tree kernel and the one-hot network kernel: each 128-tree tile hands over to its 3
+  // head CTAs (and back) as soon as IT is done, instead of every kernel waiting for the whole previous grid.  Measured on
+  // B200 at C2 (profiles/r1_summary.md section 9): 1.435 ms / step with flags both ways vs 1.453 ms with grid-wide PDL waits --
+  // inside the run-to-run noise, the fence + poll hand-over costs what the PDL release does.  OFF by default; EAZ_TILE_FLAGS=1
+  // (tree -> network only) or 2 (both ways) enables the protocol for experiments (tests/test_gpu_parity.py runs mode 2).
+  static const int flag_mode = getenv("EAZ_TILE_FLAGS") ? atoi(getenv("EAZ_TILE_FLAGS")) : 0;
+  const bool flags = flag_mode > 0 && mlp_mode == EAZ_MLP_TENSOR && env.kind == EAZ_ENV_DEEPSEA && t.A <= 4 && tl_prof == nullptr;
+  const int tiles = ceil_div(t.B, kTileRows), nheads = 3;
+  int* tile_done = flags ? t.tile_ctr : nullptr;
+  int* mlp_done = flags ? t.tile_ctr + tiles : nullptr;
+  int mlp_launches = 0;
+  if (flags) {
+    if (cudaError_t me = cudaMemsetAsync(t.tile_ctr, 0, (size_t)2 * tiles * sizeof(int), st); me != cudaSuccess) return cuda_fail(me, "tile counter memset");
+    src.tile_done = tile_done;
+    src.mlp_done = mlp_done;
+  }
   if (!root_logits) {  // fused root: forward.apply on the root states (node 0 = the first B compact states), selfplay.py:89
     ProfScope ps(CLS_MLP, st);
-    MlpSource rsrc{nullptr, t.states, nullptr, src.ds_seen, nullptr};
+    MlpSource rsrc{nullptr, t.states, nullptr, src.ds_seen, nullptr, nullptr, 0, mlp_done};
+    ++mlp_launches;
     if (int rc = launch_mlp(net, env, rsrc, t.B, mask, mo, mlp_mode, st, tw)) return rc;
     root_logits = t.net_logits;
     root_value = t.net_value;
@@ -655,7 +676,7 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
       cudaError_t le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), stage_bytes, st,  // one warp per tree
                                   t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions, g_timeline, g_tree_trace,
-                                  chase_cap);
+                                  chase_cap, tile_done, (const int*)mlp_done, (sim > 0 && flag_mode > 1) ? nheads * mlp_launches : 0);
       if (le != cudaSuccess) return cuda_fail(le, "tree_step_kernel launch");
     }
     EAZ_CHECK_LAUNCH("tree_step_kernel");
@@ -667,6 +688,8 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     }
     {
       ProfScope ps(CLS_MLP, st);
+      src.tree_epoch = flags ? sim + 1 : 0;  // tree launches so far
+      ++mlp_launches;
       if (int rc = launch_mlp(net, env, src, t.B, mask, mo, mlp_mode, st, tw)) return rc;
     }
   }

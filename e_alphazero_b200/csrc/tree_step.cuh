@@ -162,7 +162,8 @@ struct Stage {
 template <int G, int J>
 __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
                                                          const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid,
-                                                         unsigned long long* tl, long long* trace, int chase_cap) {
+                                                         unsigned long long* tl, long long* trace, int chase_cap, int* tile_done,
+                                                         const int* mlp_done, int mlp_target) {
   extern __shared__ __align__(16) uint32_t stage_smem[];
   unsigned long long t_entry = 0;
   if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_entry = globaltimer_ns();
@@ -260,7 +261,14 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
     __syncwarp();
   }
 
-  pdl_wait();     // the network kernel of this simulation has finished: its outputs are visible
+  // the network outputs of this simulation: per-tile counters (the 3 head CTAs of this tree's tile) or the grid-wide PDL wait
+  if (mlp_done && mlp_target > 0) {
+    // (the 4 trees of a CTA belong to one tile: one polling thread per CTA)
+    if (threadIdx.x == 0) wait_counter(mlp_done + (blockIdx.x * (blockDim.x >> 5)) / kTileRows, mlp_target);
+    __syncthreads();
+  } else {
+    pdl_wait();
+  }
   pdl_trigger();  // the next kernel (Subleq step / network) may begin its prologue now
   unsigned long long t_wait = 0;
   if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_wait = globaltimer_ns();
@@ -274,6 +282,16 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
     }
   } tl_exit{tl, t_entry, t_wait};
   if (!in_batch) return;
+  struct TileSignal {  // at every exit of the warp: results visible, then the tile's counter moves (consumed by the network kernel)
+    int* ctr;
+    int lane;
+    __device__ ~TileSignal() {
+      if (ctr) {
+        __syncwarp();  // every lane's stores are ordered before lane 0's release fence (cumulative)
+        if (lane == 0) signal_counter(ctr);
+      }
+    }
+  } tile_signal{tile_done ? tile_done + b / kTileRows : nullptr, lane};
   // optional per-tree section stamps (eaz_debug_set_tree_trace): [sim][b][8] = start, expand, backward, refresh, chase, depth, L, staged
   long long* trc = (trace && lane == 0) ? trace + ((size_t)sim * t.B + b) * 8 : nullptr;
   if (trc) { trc[0] = clock64(); trc[7] = staged; }

@@ -456,3 +456,19 @@ def test_uncompact_round_trip_and_replay_ring(ops, kind, kw):
         hits = [(t, b) for t in range(5) for b in range(B) if all((stored[t][k][b] == f[k][i]).all() for k in keys)
                 and all((stored[t + 1][k][b] == s2[k][i]).all() for k in keys)]
         assert hits, f"sample {i} is not a stored consecutive pair"
+
+
+def test_tile_flag_protocol_subprocess():
+    """EAZ_TILE_FLAGS=2 (per-tile release/acquire counters instead of grid-wide PDL waits between the tree kernel and the
+    DeepSea network kernel; read once per process, hence the subprocess): the tensor-mode search still replays bit-exactly."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, EAZ_TILE_FLAGS="2")
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_parity.py"), "-q", "-x", "-m", "gpu", "-k",
+                        "test_search_tensor_mode and deepsea or test_selfplay_runner_graph_equals_eager and deepsea"],
+                       cwd=root, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "passed" in r.stdout
