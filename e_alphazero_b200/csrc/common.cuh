@@ -228,48 +228,55 @@ __device__ __forceinline__ unsigned long long sq_pack_vec(const SubleqVec& v, in
 // (packed bytes, count), and the "output == expected" test as `no mismatch so far && count == expected length`
 // (a written word is < ws, so it can never equal the pad token ws: the arrays are equal iff exactly the expected
 // words were written and all matched).  Results are expanded into SubleqSim at the end.
+// The loop body is written branch-free (selects and predicated stores): the 32 lanes of a warp interpret 32 different
+// programs, so every data-dependent branch of a straightforward transcription (operand kind, IN / OUT handling, jump)
+// would split the warp and serialise its paths.  Loads go to clamped (always valid) addresses and are discarded by selects.
 template <typename MemT>
 __device__ __forceinline__ void subleq_simulate(int ws, MemT* mem, int trow, int k, SubleqSim& r) {
   const int AMAX = ws - 4, AIN = ws - 3, AOUT = ws - 2;
   const int in_len = c_sq_in[trow][k].len, out_len = c_sq_out[trow][k].len;
   const unsigned long long tin = sq_pack_vec(c_sq_in[trow][k], ws), tout = sq_pack_vec(c_sq_out[trow][k], ws);
   unsigned long long outp = 0ull;
-  int in_cur = 0, out_cur = 0, cur = 0, bytes = 0, cycles = 0, halt = 0, err = 0, bad = 0;
-  while (!err && !halt && cycles < EAZ_SUBLEQ_MAX_CYCLES) {  // :297-299
+  unsigned long long in_rest = tin, exp_rest = tout;  // unread input words / not yet matched expected words, next one in the low byte
+  int in_cur = 0, out_cur = 0, out_shift = 0, cur = 0, bytes = 0, cycles = 0, err = 0, bad = 0;
+  bool run = true;
+  while (run) {  // :297-299
     cycles += 1;
-    if (cur + 2 >= ws) {  // :364-370
-      err = 1;
-      break;
-    }
-    bytes = max(bytes, cur + 3);  // :311
-    const int a = mem[cur], b = mem[cur + 1], c = mem[cur + 2];
-    const int have_in = in_cur < in_len;  // input_state[0] < word_size (:197,218)
-    const int in0 = have_in ? (int)((tin >> (8 * in_cur)) & 0xffull) : 0;
-    int va = 0, vb = 0, acc = 0, e = 0;
-    if (a <= AMAX) va = mem[a];
-    else if (a == AIN) { if (!have_in) e = 1; else { va = in0; acc = 1; } }
-    if (b <= AMAX) vb = mem[b];
-    else if (b == AIN) { if (!have_in) e = 1; else { vb = in0; acc = 1; } }
+    const bool oob = cur + 2 >= ws;  // :364-370: costs a cycle, sets the error, changes nothing else
+    const bool live = !oob;
+    const int cc = oob ? 0 : cur;
+    const int a = mem[cc], b = mem[cc + 1], c = mem[cc + 2];
+    const bool have_in = in_cur < in_len;  // input_state[0] < word_size (:197,218)
+    const int in0 = (int)((unsigned)in_rest & 0xffu);
+    const bool a_mem = a <= AMAX, b_mem = b <= AMAX, a_in = a == AIN, b_in = b == AIN;
+    const int ma = mem[a_mem ? a : 0], mb = mem[b_mem ? b : 0];
+    const int va = a_mem ? ma : ((a_in && have_in) ? in0 : 0);  // reads of OUT / HALT give 0 (:225-228)
+    const int vb = b_mem ? mb : ((b_in && have_in) ? in0 : 0);
+    const bool uses_in = a_in || b_in;
     int value = va - vb;  // both in [0, ws): floor-mod is one conditional add (:322)
-    if (value < 0) value += ws;
-    int modified = 0, last_ok = 1;
-    if (a <= AMAX) mem[a] = (MemT)value;
-    else if (a == AOUT) {
-      if (out_cur >= 8) e = 1;
-      else {
-        last_ok = (out_cur < out_len) && (value == (int)((tout >> (8 * out_cur)) & 0xffull));
-        outp |= (unsigned long long)(unsigned)value << (8 * out_cur);
-        out_cur += 1;
-        modified = 1;
-        bad |= !last_ok;
-      }
+    value += value < 0 ? ws : 0;
+    if (live && a_mem) mem[a] = (MemT)value;  // writes to IN / HALT are ignored (:277-278,290-291)
+    const bool to_out = live && a == AOUT;
+    const bool out_ok = to_out && out_cur < 8;  // a write to a full output is an error (:282-283)
+    const bool last_ok = !out_ok || (out_cur < out_len && value == (int)((unsigned)exp_rest & 0xffu));
+    if (out_ok) {
+      outp |= (unsigned long long)(unsigned)value << out_shift;
+      out_shift += 8;
+      exp_rest >>= 8;
+      out_cur += 1;
     }
-    const int jump = (value == 0) || (2 * value >= ws);  // :329
-    cur = jump ? c : cur + 3;
-    in_cur += acc;  // :333-338 (at most one word per instruction)
-    const int all_eq = !bad && out_cur == out_len;
-    halt = ((((jump ? 1 : 0) & c) > AMAX) ? 1 : 0) | all_eq;  // :340-345, precedence as written
-    err = e | (modified && !last_ok);                         // :346-350
+    bad |= (out_ok && !last_ok) ? 1 : 0;
+    const bool jump = (value == 0) || (2 * value >= ws);  // :329
+    if (live && uses_in && have_in) {                     // :333-338 (at most one word per instruction)
+      in_cur += 1;
+      in_rest >>= 8;
+    }
+    const bool all_eq = !bad && out_cur == out_len;
+    const bool halt = live && (((((jump ? 1 : 0) & c) > AMAX)) || all_eq);  // :340-345, precedence as written
+    err = (oob || (live && uses_in && !have_in) || (to_out && !out_ok) || (out_ok && !last_ok)) ? 1 : 0;  // :346-350
+    bytes = live ? max(bytes, cur + 3) : bytes;  // :311
+    cur = live ? (jump ? c : cur + 3) : cur;
+    run = !err && !halt && cycles < EAZ_SUBLEQ_MAX_CYCLES;
   }
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
