@@ -209,7 +209,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
 
     # shard = this rank's envs (weak scaling: B per GPU fixed); directed exploration with beta = linspace(0,1,B) (UBE on)
     runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=100 + rank,
-                            use_graph=not args.no_graph, fused_root=not args.no_fused_root)
+                            use_graph=not args.no_graph, fused_root=not args.no_fused_root, streams=args.streams)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     states = ops.env_init(env, B, task_ids=torch.ones(B, dtype=torch.int32, device=dev) if kind == "subleq" else None, device=dev)
     A = env.num_actions
@@ -369,6 +369,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
             "data": "synthetic",
             "config": {"workload": desc, "envs_per_gpu": B, "num_simulations": n, "mlp_mode": "exact_fp32" if args.mlp_mode == 0 else "tensor",
                        "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": not args.no_graph, "fused_root": not args.no_fused_root, "directed_exploration": True, "beta": "linspace(0,1,B)",
+                       "streams": args.streams,
                        "param_refresh": f"weight images / novelty / seq-halving tables rebuilt every {args.param_refresh} steps (selfplay_steps of the reference, config.py:37,105), reused in between",
                        "multi_gpu": "envs sharded per rank, params broadcast once, compact trajectory all-gather per step" if world > 1 else "single GPU"},
             "simulations_per_s": value * n, "clocks": clocks,
@@ -407,6 +408,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mlp-mode", type=int, default=1, help="0 = fp32 FMA chains (bit-exact contract), 1 = tcgen05 3xTF32 (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--streams", type=int, default=0,
+                    help="EAZ_FLAG_STREAMS: search this many sub-batches concurrently on auxiliary streams (0 = 3 for DeepSea, 1 for Subleq: measured best)")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the workload's batch (exploration, not a BASELINE config)")
     ap.add_argument("--sims", type=int, default=0, help="override the workload's simulation count")
     ap.add_argument("--param-refresh", type=int, default=8,
@@ -418,6 +421,8 @@ def main():
     if args.envs_per_gpu or args.sims:  # exploration knobs (not the BASELINE configs): the description says so
         B, n = args.envs_per_gpu or B, args.sims or n
         desc += f" [overridden: {B} envs/GPU, {n} simulations]"
+    if args.streams <= 0:
+        args.streams = 3 if kind == "deepsea" else 1
     if args.impl == "reference":
         run_reference(args, kind, kw, B, n, gamma, desc)
     else:

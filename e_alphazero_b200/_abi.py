@@ -28,6 +28,14 @@ FLAG_BETA_RAW = 1 << 1
 FLAG_BETA_FINAL = 1 << 2
 FLAG_BACKUP_STD = 1 << 3
 FLAG_REUSE_PREPARED = 1 << 4
+FLAG_STREAMS_SHIFT = 8
+
+
+def flag_streams(k: int) -> int:
+    """EAZ_FLAG_STREAMS(k): search k sub-batches concurrently on auxiliary streams (results unchanged)."""
+    return (int(k) & 0xF) << FLAG_STREAMS_SHIFT
+
+
 SEARCH_DEFAULT_FLAGS = FLAG_BETA_INTERIOR | FLAG_BETA_RAW | FLAG_BETA_FINAL
 
 MLP_EXACT = 0

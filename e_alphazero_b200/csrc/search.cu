@@ -20,6 +20,7 @@
 #include "mlp.cuh"
 
 #include <cstdlib>
+#include <mutex>
 #include <vector>
 
 namespace eaz {
@@ -784,14 +785,37 @@ int eaz_mlp_forward_states(const eaz_fc_params* net, const eaz_env* env, const e
   return launch_mlp(nd, ed, src, B, mask, out, EAZ_MLP_EXACT, (cudaStream_t)stream);
 }
 
+static size_t layout_bytes(const eaz_search_config* cfg, const EnvDesc& d, int batch) {
+  Layout L;
+  make_layout(batch, cfg->num_simulations + 1, d.num_actions, d.compact_bytes, (cfg->max_num_considered_actions + 1) * cfg->num_simulations,
+              d.obs_dim, wimg_bytes_for(cfg->mlp_mode, d), cfg->max_depth > 0 ? cfg->max_depth : cfg->num_simulations, &L);
+  return L.total;
+}
+// EAZ_FLAG_STREAMS(k): the batch is cut into up to k sub-batches of whole 128-tree tiles; returns their sizes (count in *parts)
+static void sub_batches(const eaz_search_config* cfg, int* sizes, int* parts) {
+  int k = (cfg->flags >> EAZ_FLAG_STREAMS_SHIFT) & 0xF;
+  if (k > 8) k = 8;
+  const int tiles = ceil_div(cfg->batch, kTileRows);
+  if (k < 1) k = 1;
+  if (k > tiles) k = tiles;
+  const int per = ceil_div(tiles, k) * kTileRows;
+  int left = cfg->batch, p = 0;
+  while (left > 0) {
+    sizes[p] = left < per ? left : per;
+    left -= sizes[p++];
+  }
+  *parts = p;
+}
+
 size_t eaz_search_workspace_bytes(const eaz_search_config* cfg, const eaz_env* env) {
   EnvDesc d;
   if (!cfg || make_env_desc(env, &d) || cfg->batch < 1 || cfg->num_simulations < 1) return 0;
-  Layout L;
-  make_layout(cfg->batch, cfg->num_simulations + 1, d.num_actions, d.compact_bytes,
-              (cfg->max_num_considered_actions + 1) * cfg->num_simulations, d.obs_dim, wimg_bytes_for(cfg->mlp_mode, d),
-              cfg->max_depth > 0 ? cfg->max_depth : cfg->num_simulations, &L);
-  return L.total;
+  int sizes[8], parts;
+  sub_batches(cfg, sizes, &parts);
+  size_t total = 0;
+  for (int p = 0; p < parts; ++p) total += layout_bytes(cfg, d, sizes[p]);  // every sub-batch owns a complete layout
+  const size_t whole = layout_bytes(cfg, d, cfg->batch);                    // (the profiled variant runs unsplit)
+  return total > whole ? total : whole;
 }
 
 int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env) {
@@ -801,10 +825,13 @@ int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env
   const bool build_tables = (cfg->flags & EAZ_FLAG_REUSE_PREPARED) == 0;
   const int prep = (cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * 3 : 0) + 1 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0);  // weight images, seq-halving + seen tables
   // 1 memset + pack + root init + [tables] + per simulation + last tree step + finalize  (+1 network launch with a fused root)
-  return 1 + 2 + (build_tables ? prep : 0) + per_sim * cfg->num_simulations + 1 + 1;
+  int sizes[8], parts = 1;
+  if (cfg->batch >= 1) sub_batches(cfg, sizes, &parts);  // EAZ_FLAG_STREAMS: every sub-batch launches its own sequence
+  return parts * (1 + 2 + (build_tables ? prep : 0) + per_sim * cfg->num_simulations + 1 + 1);
 }
 
-int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
+// one search over the whole batch of `cfg` on one stream
+static int search_one(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
                       size_t workspace_bytes, void* stream) {
   EnvDesc env;
   NetDesc net;
@@ -870,6 +897,128 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
     EAZ_CHECK_LAUNCH("export_tree_kernel");
   }
   return 0;
+}
+
+// Auxiliary streams / events for EAZ_FLAG_STREAMS (created once per device, never destroyed).
+struct AuxStreams {
+  cudaStream_t s[8];
+  cudaEvent_t fork, join[8];
+  bool ready;
+};
+static AuxStreams* aux_streams() {
+  static AuxStreams table[32] = {};
+  static std::mutex mu;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  std::lock_guard<std::mutex> lock(mu);
+  AuxStreams* a = &table[dev];
+  if (!a->ready) {
+    for (int i = 0; i < 8; ++i) {
+      if (cudaStreamCreateWithFlags(&a->s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+      if (cudaEventCreateWithFlags(&a->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    }
+    if (cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+    a->ready = true;
+  }
+  return a;
+}
+
+int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  EAZ_CHECK_ARG(cfg && in && out, "search: NULL config / inputs / outputs");
+  int sizes[8], parts = 1;
+  if (cfg->batch >= 1) sub_batches(cfg, sizes, &parts);
+  if (parts <= 1 || tl_prof != nullptr) return search_one(cfg, in, out, workspace, workspace_bytes, stream);
+  // ---- EAZ_FLAG_STREAMS: independent sub-batches (trees never interact) searched concurrently on auxiliary streams, so that
+  // one sub-batch's tree kernel (issue-bound) overlaps another's network kernel (tensor / L2-bound) and env step (latency-bound)
+  EnvDesc env;
+  NetDesc net;
+  if (int rc = check_search(cfg, in, out, &env, &net)) return rc;
+  AuxStreams* aux = aux_streams();
+  if (!aux) {
+    set_error("could not create the auxiliary streams for EAZ_FLAG_STREAMS");
+    return EAZ_ERR_CUDA;
+  }
+  const size_t A = env.num_actions, N = cfg->num_simulations + 1, S = env.compact_bytes, D = env.obs_dim, W = env.ws;
+  size_t need = 0;
+  for (int p = 0; p < parts; ++p) need += layout_bytes(cfg, env, sizes[p]);
+  if (!workspace || workspace_bytes < need || ((uintptr_t)workspace & 255)) {
+    set_error("search workspace must be >= %zu bytes and 256-byte aligned (got %zu)", need, workspace_bytes);
+    return EAZ_ERR_WORKSPACE;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (cudaError_t e = cudaEventRecord(aux->fork, st); e != cudaSuccess) return cuda_fail(e, "fork event");
+  size_t b0 = 0, ws_off = 0;
+  int rc_all = 0;
+  for (int p = 0; p < parts; ++p) {
+    eaz_search_config c = *cfg;
+    c.batch = sizes[p];
+    c.flags &= ~(0xF << EAZ_FLAG_STREAMS_SHIFT);
+    auto offf = [&](const float* q, size_t per) { return q ? q + b0 * per : nullptr; };
+    auto offu = [&](const uint8_t* q, size_t per) { return q ? q + b0 * per : nullptr; };
+    auto offi = [&](const int32_t* q, size_t per) { return q ? q + b0 * per : nullptr; };
+    const eaz_state* e0 = in->embedding;
+    eaz_state es{};
+    if (e0) {
+      es.step_count = (int32_t*)offi(e0->step_count, 1);
+      es.rewards = (float*)offf(e0->rewards, 1);
+      es.terminated = (uint8_t*)offu(e0->terminated, 1);
+      es.truncated = (uint8_t*)offu(e0->truncated, 1);
+      es.observation = (uint8_t*)offu(e0->observation, D);
+      es.col = (int32_t*)offi(e0->col, 1);
+      es.memory = (int32_t*)offi(e0->memory, W);
+      es.task = (int32_t*)offi(e0->task, 1);
+      es.solved = (uint8_t*)offu(e0->solved, 1);
+      es.input_after = (int32_t*)offi(e0->input_after, 8);
+      es.output_after = (int32_t*)offi(e0->output_after, 8);
+    }
+    eaz_search_inputs si = *in;
+    si.prior_logits = offf(in->prior_logits, A);
+    si.value = offf(in->value, 1);
+    si.value_epistemic_variance = offf(in->value_epistemic_variance, 1);
+    si.beta = offf(in->beta, 1);
+    si.embedding = e0 ? &es : nullptr;
+    si.invalid_actions = offu(in->invalid_actions, A);
+    si.gumbel = offf(in->gumbel, A);
+    eaz_search_outputs so = *out;
+    so.action = (int32_t*)offi(out->action, 1);
+    so.action_weights = (float*)offf(out->action_weights, A);
+    so.value = (float*)offf(out->value, 1);
+    so.value_epistemic_std = (float*)offf(out->value_epistemic_std, 1);
+    so.visit_counts = (float*)offf(out->visit_counts, A);
+    so.visit_probs = (float*)offf(out->visit_probs, A);
+    so.qvalues = (float*)offf(out->qvalues, A);
+    so.qvalues_epistemic_variance = (float*)offf(out->qvalues_epistemic_variance, A);
+    so.node_visits = (int32_t*)offi(out->node_visits, N);
+    so.raw_values = (float*)offf(out->raw_values, N);
+    so.node_values = (float*)offf(out->node_values, N);
+    so.raw_values_epistemic_variance = (float*)offf(out->raw_values_epistemic_variance, N);
+    so.node_values_epistemic_variance = (float*)offf(out->node_values_epistemic_variance, N);
+    so.parents = (int32_t*)offi(out->parents, N);
+    so.action_from_parent = (int32_t*)offi(out->action_from_parent, N);
+    so.children_index = (int32_t*)offi(out->children_index, N * A);
+    so.children_prior_logits = (float*)offf(out->children_prior_logits, N * A);
+    so.children_visits = (int32_t*)offi(out->children_visits, N * A);
+    so.children_rewards = (float*)offf(out->children_rewards, N * A);
+    so.children_discounts = (float*)offf(out->children_discounts, N * A);
+    so.children_values = (float*)offf(out->children_values, N * A);
+    so.children_rewards_epistemic_variance = (float*)offf(out->children_rewards_epistemic_variance, N * A);
+    so.children_values_epistemic_variance = (float*)offf(out->children_values_epistemic_variance, N * A);
+    so.embeddings = (uint8_t*)offu(out->embeddings, N * S);
+    so.root_value = (float*)offf(out->root_value, 1);
+    so.root_ube = (float*)offf(out->root_ube, 1);
+    const size_t bytes = layout_bytes(cfg, env, sizes[p]);
+    cudaStream_t sp = aux->s[p];
+    if (cudaError_t e = cudaStreamWaitEvent(sp, aux->fork, 0); e != cudaSuccess) return cuda_fail(e, "fork wait");
+    const int rc = search_one(&c, &si, &so, (uint8_t*)workspace + ws_off, bytes, sp);
+    if (rc && !rc_all) rc_all = rc;
+    // always rejoin, also after an error: a forked stream must not be left dangling inside a stream capture
+    if (cudaError_t e = cudaEventRecord(aux->join[p], sp); e != cudaSuccess) return cuda_fail(e, "join event");
+    if (cudaError_t e = cudaStreamWaitEvent(st, aux->join[p], 0); e != cudaSuccess) return cuda_fail(e, "join wait");
+    b0 += sizes[p];
+    ws_off += bytes;
+  }
+  return rc_all;
 }
 
 int eaz_reanalyze_targets(const eaz_reanalyze_config* cfg, int32_t B, int32_t A, const int32_t* action, const float* qvalues,

@@ -40,13 +40,15 @@ class ReanalyzeRunner:
 
     def __init__(self, env_spec: ops.EnvSpec, net: ops.FcParams, batch: int, num_simulations: int, discount: float, reanalyze_beta: float = 0.0,
                  exploration_beta: float = 0.0, exploration_ube_target: bool = True, temperature: float = 1.0, rescale_values: bool = True,
-                 mlp_mode: int = _abi.MLP_EXACT, device="cuda", seed: int = 0, use_graph: bool = False):
+                 mlp_mode: int = _abi.MLP_EXACT, device="cuda", seed: int = 0, use_graph: bool = False, streams: int = 1):
         torch = require_cuda()
         self.env, self.net, self.B, self.device = env_spec, net, batch, device
         self.A = env_spec.num_actions
         # reanalyze_recurrent_fn: exploration=False (main.py:266-273); root = exploitation logits (reanalyze.py:70-71)
         self.cfg = _abi.default_search_config(batch=batch, num_simulations=num_simulations, discount=discount, exploration=0,
                                               rescale_values=int(rescale_values), mlp_mode=mlp_mode)
+        if streams > 1:
+            self.cfg.flags |= _abi.flag_streams(streams)
         self.plan = ops.SearchPlan(self.cfg, env_spec, net, want_tree=False, device=device)
         self.beta = torch.full((batch,), float(reanalyze_beta), device=device)  # reanalyze.py:75
         self.tcfg = (float(discount), float(exploration_beta), bool(exploration_ube_target), float(temperature))

@@ -26,12 +26,15 @@ class SelfplayRunner:
 
     def __init__(self, env_spec: ops.EnvSpec, net: ops.FcParams, batch: int, num_simulations: int, discount: float,
                  exploration_beta: float = 0.0, directed_exploration: bool = False, rescale_values: bool = True,
-                 mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0, use_graph: bool = False, fused_root: bool = False):
+                 mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0, use_graph: bool = False, fused_root: bool = False,
+                 streams: int = 1):
         torch = require_cuda()
         self.env, self.net, self.B, self.device = env_spec, net, batch, device
         self.directed = directed_exploration
         self.cfg = _abi.default_search_config(batch=batch, num_simulations=num_simulations, discount=discount,
                                               exploration=int(directed_exploration), rescale_values=int(rescale_values), mlp_mode=mlp_mode)
+        if streams > 1:  # EAZ_FLAG_STREAMS: sub-batches searched concurrently (tree kernel of one overlaps the network kernel of another)
+            self.cfg.flags |= _abi.flag_streams(streams)
         self.plan = ops.SearchPlan(self.cfg, env_spec, net, want_tree=False, device=device)
         beta = exploration_beta if directed_exploration else 0.0  # selfplay.py:92, config.py:172
         self.beta = (beta * torch.linspace(0, 1, batch, device=device)).contiguous()  # selfplay.py:105

@@ -194,8 +194,14 @@ enum {
    * net wrote into THIS workspace -- skip rebuilding them.  The model is constant across the steps of one selfplay()
    * scan (selfplay.py:148) and one reanalyze() call; the caller clears the flag after every learner update. */
   EAZ_FLAG_REUSE_PREPARED = 1 << 4,
+  /* Also not an emctx switch: bits 8..11 = k (2..8): cut the batch into k sub-batches of whole 128-tree tiles and search them
+   * concurrently on library-owned auxiliary streams, forked from and joined back into `stream` (CUDA-graph capturable).  Trees
+   * never interact, so the results are bit-identical to k = 0/1; the point is overlap -- one sub-batch's tree kernel runs while
+   * another's network kernel does.  eaz_search_workspace_bytes accounts for the k separate layouts. */
+  EAZ_FLAG_STREAMS_SHIFT = 8,
   EAZ_SEARCH_DEFAULT_FLAGS = (1 << 0) | (1 << 1) | (1 << 2)
 };
+#define EAZ_FLAG_STREAMS(k) ((k) << EAZ_FLAG_STREAMS_SHIFT)
 
 typedef struct eaz_search_config {
   int32_t batch;            /* B (per device) */

@@ -472,3 +472,21 @@ def test_tile_flag_protocol_subprocess():
                        cwd=root, env=env, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "passed" in r.stdout
+
+
+@pytest.mark.parametrize("kind,kw,B,k,mode", [("deepsea", dict(size=10), 300, 2, _abi.MLP_EXACT), ("deepsea", dict(size=10), 700, 4, _abi.MLP_TENSOR),
+                                              ("subleq", dict(word_size=16), 260, 3, _abi.MLP_EXACT)])
+def test_search_streams_identical(ops, kind, kw, B, k, mode):
+    """EAZ_FLAG_STREAMS(k): the batch searched as k concurrent sub-batches on auxiliary streams returns, array for array, what the
+    single-stream search returns (ragged last sub-batch included)."""
+    env = H.make_env(kind, seed=51, **kw)
+    net = H.make_net(env, seed=52, fill=0.5)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    root = H.device_root(env, denv, H.make_root(env, net, B, seed=53, invalid_frac=0.2))
+    kwc = dict(batch=B, num_simulations=16, discount=0.97, mlp_mode=mode)
+    one = {n: host(v).copy() for n, v in ops.search(_abi.default_search_config(**kwc), denv, dnet, root, want_tree=True).items()}
+    cfg = _abi.default_search_config(**kwc)
+    cfg.flags |= _abi.flag_streams(k)
+    many = {n: host(v).copy() for n, v in ops.search(cfg, denv, dnet, root, want_tree=True).items()}
+    for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
+        H.assert_same_bits(many[name], one[name], name)
