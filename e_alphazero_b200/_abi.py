@@ -8,7 +8,7 @@ from __future__ import annotations
 
 import ctypes as C
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 EAZ_OK = 0
 EAZ_ERR_INVALID_ARG = -1
@@ -29,6 +29,7 @@ FLAG_BETA_FINAL = 1 << 2
 FLAG_BACKUP_STD = 1 << 3
 FLAG_REUSE_PREPARED = 1 << 4
 FLAG_STREAMS_SHIFT = 8
+FLAG_PUCT = 1 << 5
 
 
 def flag_streams(k: int) -> int:
@@ -104,6 +105,10 @@ class EazSearchConfig(C.Structure):
         ("epsilon", C.c_float),
         ("flags", C.c_int32),
         ("mlp_mode", C.c_int32),
+        ("pb_c_init", C.c_float),
+        ("pb_c_base", C.c_float),
+        ("temperature", C.c_float),
+        ("noise_seed", C.c_uint32),
     ]
 
 
@@ -187,6 +192,10 @@ def default_search_config(**kw) -> EazSearchConfig:
         epsilon=1e-8,
         flags=SEARCH_DEFAULT_FLAGS,
         mlp_mode=MLP_EXACT,
+        pb_c_init=1.25,
+        pb_c_base=19652.0,
+        temperature=1.0,
+        noise_seed=0,
     )
     for k, v in kw.items():
         if not hasattr(cfg, k):

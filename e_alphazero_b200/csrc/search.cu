@@ -147,6 +147,8 @@ struct SearchParams {
   int n, max_depth, max_considered;
   float gumbel_scale, discount, value_scale, maxvisit_init, epsilon;
   int two_players, rescale, mixed, flags;
+  float pb_c_init, pb_c_base, temperature;  // EAZ_FLAG_PUCT (mctx muzero_policy)
+  uint32_t noise_seed;
 };
 
 // ------------------------------------------------------------------ state packing
@@ -360,6 +362,60 @@ __device__ __forceinline__ int root_argmax(const Edge<G, J>& e, const bool (&val
   return group_argmax<G>(best, besti);
 }
 
+// ---- emctx.epistemic_muzero_policy (EAZ_FLAG_PUCT): mctx muzero_action_selection + qtransform_by_parent_and_siblings
+// tie-break noise stream, identical to oracle/eaz_oracle.c:orc_tie_noise
+__device__ __forceinline__ float tie_noise(uint32_t seed, uint32_t b, uint32_t node, uint32_t visits, uint32_t a) {
+  uint32_t h = seed + EAZ_XX_P1;
+  h = xx_round(h, b);
+  h = xx_round(h, node);
+  h = xx_round(h, visits);
+  h = xx_round(h, a);
+  h ^= h >> 15; h *= EAZ_XX_P2; h ^= h >> 13; h *= EAZ_XX_P3; h ^= h >> 16;
+  return __fmul_rn((float)(h >> 8), 5.9604644775390625e-08f);
+}
+
+template <int G, int J>
+__device__ __forceinline__ int puct_select(const SearchParams& sp, const Edge<G, J>& e, const bool (&valid)[J], int node_visits, float node_value,
+                                           float node_var, float beta, bool use_beta, unsigned b, unsigned node, const bool (&inval)[J], int gl) {
+  if (use_beta && (sp.flags & EAZ_FLAG_BETA_RAW)) node_value = __fadd_rn(node_value, __fmul_rn(beta, __fsqrt_rn(node_var)));
+  float q[J];
+  float lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    q[j] = __fadd_rn(e.rew[j], __fmul_rn(e.dis[j], e.val[j]));
+    if (use_beta) {
+      const float qv = __fadd_rn(0.0f, __fmul_rn(__fmul_rn(e.dis[j], e.dis[j]), e.vvar[j]));
+      q[j] = __fadd_rn(q[j], __fmul_rn(beta, __fsqrt_rn(qv)));
+    }
+    const float safe = e.vis[j] > 0 ? q[j] : node_value;
+    if (valid[j]) { lo = fminf(lo, safe); hi = fmaxf(hi, safe); }
+  }
+  const float mn = eaz_min(node_value, group_min<G>(lo)), mx = eaz_max(node_value, group_max<G>(hi));
+  const float den = eaz_max(__fsub_rn(mx, mn), sp.epsilon);
+  const float nv = (float)node_visits;
+  const float pb_c = __fadd_rn(sp.pb_c_init, eaz_log(__fdiv_rn(__fadd_rn(__fadd_rn(nv, sp.pb_c_base), 1.0f), sp.pb_c_base)));
+  const float explore = __fmul_rn(__fsqrt_rn(nv), pb_c);
+  float p[J];
+  group_softmax<G, J>(e.pl, valid, p);
+  float best = -INFINITY;
+  int besti = 1 << 30;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int a = gl + G * j;
+    float s = -INFINITY;
+    if (valid[j]) {
+      const float value_score = __fdiv_rn(__fsub_rn(e.vis[j] > 0 ? q[j] : mn, mn), den);
+      const float policy_score = __fdiv_rn(__fmul_rn(explore, p[j]), __fadd_rn((float)e.vis[j], 1.0f));
+      const float noise = __fmul_rn(1e-7f, tie_noise(sp.noise_seed, b, node, (uint32_t)node_visits, (uint32_t)a));
+      s = __fadd_rn(__fadd_rn(value_score, policy_score), noise);
+      if (inval[j]) s = -INFINITY;
+    }
+    const int ia = valid[j] ? a : (1 << 30);
+    if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
+  }
+  return group_argmax<G>(best, besti);
+}
+
 #define EAZ_GROUP_PROLOGUE()                                               \
   const int lane = threadIdx.x & 31;                                       \
   const int gl = lane & (G - 1);                                           \
@@ -489,19 +545,42 @@ __global__ void __launch_bounds__(128) finalize_kernel(Tree t, SearchParams sp, 
   float cq[J];
   int sumN, maxN;
   qtransform<G, J>(sp, e, valid, raw, raw_var, beta, (sp.flags & EAZ_FLAG_BETA_FINAL) != 0, cq, sumN, maxN);
-  const int act = root_argmax<G, J>(e, valid, gum, inval, cq, maxN, gl);  // considered_visit = max visit count
-  // action_weights = softmax(mask_invalid(root_logits + completed_q))
+  int act;
   float x[J], p[J];
-  float m = -INFINITY;
+  if (sp.flags & EAZ_FLAG_PUCT) {
+    // mctx policies.muzero_policy: action_weights = visit_probs; action ~ categorical(log(visit_probs) / temperature) = Gumbel-max
+    float m = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    x[j] = __fadd_rn(e.pl[j], cq[j]);
-    if (valid[j]) m = fmaxf(m, x[j]);
+    for (int j = 0; j < J; ++j) {
+      p[j] = sumN > 0 ? __fdiv_rn((float)e.vis[j], eaz_max((float)sumN, 1.0f)) : __fdiv_rn(1.0f, (float)t.A);
+      x[j] = eaz_log(eaz_max(p[j], EAZ_F32_TINY));
+      if (valid[j]) m = fmaxf(m, x[j]);
+    }
+    m = group_max<G>(m);
+    const float tdiv = eaz_max(EAZ_F32_TINY, sp.temperature);
+    float best = -INFINITY;
+    int besti = 1 << 30;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const float s = valid[j] ? __fadd_rn(__fdiv_rn(__fsub_rn(x[j], m), tdiv), gum[j]) : -INFINITY;
+      const int ia = valid[j] ? gl + G * j : (1 << 30);
+      if (s > best || (s == best && ia < besti)) { best = s; besti = ia; }
+    }
+    act = group_argmax<G>(best, besti);
+  } else {
+    act = root_argmax<G, J>(e, valid, gum, inval, cq, maxN, gl);  // considered_visit = max visit count
+    // action_weights = softmax(mask_invalid(root_logits + completed_q))
+    float m = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      x[j] = __fadd_rn(e.pl[j], cq[j]);
+      if (valid[j]) m = fmaxf(m, x[j]);
+    }
+    m = group_max<G>(m);
+#pragma unroll
+    for (int j = 0; j < J; ++j) x[j] = inval[j] ? EAZ_F32_MIN : __fsub_rn(x[j], m);
+    group_softmax<G, J>(x, valid, p);
   }
-  m = group_max<G>(m);
-#pragma unroll
-  for (int j = 0; j < J; ++j) x[j] = inval[j] ? EAZ_F32_MIN : __fsub_rn(x[j], m);
-  group_softmax<G, J>(x, valid, p);
   if (!in_range) return;
   if (gl == 0) {
     out.action[b] = act;
@@ -848,7 +927,7 @@ static int search_one(const eaz_search_config* cfg, const eaz_search_inputs* in,
   Tree t = make_tree(workspace, L, B, N, A, S);
   SearchParams sp{n, cfg->max_depth > 0 ? cfg->max_depth : n, cfg->max_num_considered_actions, cfg->gumbel_scale, cfg->discount,
                   cfg->value_scale, cfg->maxvisit_init, cfg->epsilon, cfg->two_players_game, cfg->rescale_values, cfg->use_mixed_value,
-                  cfg->flags};
+                  cfg->flags, cfg->pb_c_init, cfg->pb_c_base, cfg->temperature, cfg->noise_seed};
   ProfScope* init_scope = new ProfScope(CLS_INIT, st);
   cudaError_t e = cudaMemsetAsync((uint8_t*)workspace + L.zero_begin, 0, L.zero_end - L.zero_begin, st);
   if (e != cudaSuccess) return cuda_fail(e, "search memset");

@@ -189,7 +189,7 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
   uint32_t* const s_next = s_misc + SG::kMiscWords;  // cached selection per node
   uint32_t* const s_state = s_next + chase_cap;      // DeepSea: compact state per node
   if constexpr (J == 1) {
-    if (in_batch && do_backward && chase_cap > sim + 1) {
+    if (in_batch && do_backward && chase_cap > sim + 1 && !(sp.flags & EAZ_FLAG_PUCT)) {  // (PUCT selection: DIRECT path)
       leaf = t.leaf[b];
       L = t.path_len[b];
       const unsigned lslot = (unsigned)leaf * uB + ub;
@@ -576,8 +576,24 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
       float raw, raw_var;
       load_edges<G, J>(t, slot, gl, act_on, e);
       load_node_raw(t, slot, act_on, raw, raw_var);
-      int child;
-      const int act = select_action<G, J>(t, sp, e, valid, raw, raw_var, beta, act_on && node == 0, ub, uA, invalid, lane, gl, &child);
+      int child, act;
+      if (sp.flags & EAZ_FLAG_PUCT) {  // muzero_action_selection at every depth (warp-uniform switch)
+        const bool is_root = act_on && node == 0;
+        uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
+        if (act_on) h0 = reinterpret_cast<const uint4*>(t.nodes + slot)[0];  // node_visits, node value, node variance
+        bool inval[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) inval[j] = (is_root && valid[j] && invalid) ? (invalid[ub * uA + gl + G * j] != 0) : false;
+        act = puct_select<G, J>(sp, e, valid, (int)h0.x, __uint_as_float(h0.y), __uint_as_float(h0.z), beta,
+                                is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0, ub, (unsigned)node, inval, gl);
+        int ci_sel = -1;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (j == act / G) ci_sel = e.ci[j];
+        child = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
+      } else {
+        act = select_action<G, J>(t, sp, e, valid, raw, raw_var, beta, act_on && node == 0, ub, uA, invalid, lane, gl, &child);
+      }
       if (act_on && gl == 0) t.nodes[slot].pad0 = pack_next(act, child);
     }
     __syncwarp();

@@ -126,10 +126,53 @@ def _draw_gumbel(rng_key, shape, device):
 _plans: dict = {}
 
 
+def qtransform_by_parent_and_siblings(tree=None, node_index=None, *, epsilon=1e-8):
+    """Marker for mctx's PUCT qtransform (evaluated inside the search kernels with EAZ_FLAG_PUCT)."""
+    raise EazError("the qtransform is evaluated inside the fused search; pass this function (or a partial of it) as qtransform=")
+
+
+def epistemic_muzero_policy(params, rng_key, root: EpistemicRootFnOutput, recurrent_fn, num_simulations: int, invalid_actions=None,
+                            max_depth=None, *, qtransform=qtransform_by_parent_and_siblings, dirichlet_fraction: float = 0.25,
+                            dirichlet_alpha: float = 0.3, pb_c_init: float = 1.25, pb_c_base: float = 19652.0, temperature: float = 1.0,
+                            return_tree: bool = False, flags: int = _abi.SEARCH_DEFAULT_FLAGS, mlp_mode: int | None = None,
+                            dirichlet_noise=None, noise_seed: int = 0) -> PolicyOutput:
+    """emctx.epistemic_muzero_policy (named by the task; the reference itself only calls the Gumbel policy): PUCT selection at the
+    root and inside the tree, action sampled in proportion to the visit counts, action_weights = visit_probs (mctx
+    policies.muzero_policy).  The Dirichlet root noise is drawn here (or passed as `dirichlet_noise` [B,A]) and mixed into the
+    prior logits exactly like mctx `_add_dirichlet_noise` / `_get_logits_from_probs`; the final categorical draw uses Gumbel-max
+    with noise from `rng_key` (an int seed, torch.Generator or PreDrawnGumbel)."""
+    torch = require_cuda()
+    kw = {}
+    fn = qtransform
+    while isinstance(fn, functools.partial):
+        kw = {**fn.keywords, **kw}
+        fn = fn.func
+    if fn is not qtransform_by_parent_and_siblings:
+        raise NotImplementedError("epistemic_muzero_policy supports qtransform_by_parent_and_siblings only")
+    probs = torch.softmax(root.prior_logits.to(torch.float32), dim=-1)
+    if dirichlet_noise is None:
+        gen = rng_key if isinstance(rng_key, torch.Generator) else None
+        conc = torch.full_like(probs, float(dirichlet_alpha))
+        g = torch._standard_gamma(conc, generator=gen) if gen is not None else torch._standard_gamma(conc)
+        dirichlet_noise = g / g.sum(-1, keepdim=True)
+    noisy = (1.0 - dirichlet_fraction) * probs + dirichlet_fraction * dirichlet_noise.to(probs)
+    noisy_logits = torch.log(torch.clamp_min(noisy, torch.finfo(torch.float32).tiny))
+    root = EpistemicRootFnOutput(noisy_logits, root.value, root.value_epistemic_variance, root.embedding, root.beta)
+    return _run_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions, max_depth,
+                       dict(epsilon=float(kw.get("epsilon", 1e-8))), 16, 1.0, return_tree, int(flags) | _abi.FLAG_PUCT, mlp_mode,
+                       dict(pb_c_init=float(pb_c_init), pb_c_base=float(pb_c_base), temperature=float(temperature), noise_seed=int(noise_seed)))
+
+
 def epistemic_gumbel_muzero_policy(params, rng_key, root: EpistemicRootFnOutput, recurrent_fn, num_simulations: int, invalid_actions=None,
                                    max_depth=None, *, qtransform=epistemic_qtransform_completed_by_mix_value,
                                    max_num_considered_actions: int = 16, gumbel_scale: float = 1.0, return_tree: bool = False,
                                    flags: int = _abi.SEARCH_DEFAULT_FLAGS, mlp_mode: int | None = None) -> PolicyOutput:
+    return _run_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions, max_depth, _qtransform_kwargs(qtransform),
+                       max_num_considered_actions, gumbel_scale, return_tree, flags, mlp_mode, {})
+
+
+def _run_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_actions, max_depth, q, max_num_considered_actions, gumbel_scale,
+                return_tree, flags, mlp_mode, extra_cfg) -> PolicyOutput:
     from .context import FusedRecurrentFn, as_fc_params
 
     if not isinstance(recurrent_fn, FusedRecurrentFn):
@@ -141,14 +184,13 @@ def epistemic_gumbel_muzero_policy(params, rng_key, root: EpistemicRootFnOutput,
     B, A = root.prior_logits.shape
     if A != rf.env.num_actions:
         raise EazError(f"prior_logits has {A} actions, env has {rf.env.num_actions}")
-    q = _qtransform_kwargs(qtransform)
     cfg = _abi.default_search_config(
         batch=B, num_simulations=int(num_simulations), max_depth=0 if max_depth is None else int(max_depth),
         max_num_considered_actions=int(max_num_considered_actions), gumbel_scale=float(gumbel_scale), discount=float(rf.discount),
         two_players_game=int(rf.two_players_game), exploration=int(rf.exploration), value_scale=float(q.get("value_scale", 0.1)),
         maxvisit_init=float(q.get("maxvisit_init", 50.0)), rescale_values=int(q.get("rescale_values", True)),
         use_mixed_value=int(q.get("use_mixed_value", True)), epsilon=float(q.get("epsilon", 1e-8)), flags=int(flags),
-        mlp_mode=int(rf.mlp_mode if mlp_mode is None else mlp_mode))
+        mlp_mode=int(rf.mlp_mode if mlp_mode is None else mlp_mode), **extra_cfg)
     dev = root.prior_logits.device
     key = (id(rf), id(net), B, bytes(cfg), bool(return_tree), str(dev))
     plan = _plans.get(key)

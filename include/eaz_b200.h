@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EAZ_ABI_VERSION 1
+#define EAZ_ABI_VERSION 2
 
 enum {
   EAZ_OK = 0,
@@ -199,6 +199,13 @@ enum {
    * never interact, so the results are bit-identical to k = 0/1; the point is overlap -- one sub-batch's tree kernel runs while
    * another's network kernel does.  eaz_search_workspace_bytes accounts for the k separate layouts. */
   EAZ_FLAG_STREAMS_SHIFT = 8,
+  /* emctx.epistemic_muzero_policy instead of the Gumbel policy (named by the task, never called by the reference): PUCT at the
+   * root and inside the tree (mctx action_selection.muzero_action_selection with qtransform_by_parent_and_siblings; the
+   * beta * sqrt(variance) bonus enters q exactly as in the Gumbel path), action ~ visit counts, action_weights = visit_probs
+   * (mctx policies.muzero_policy).  Randomness is supplied / derived, not drawn from a JAX key: the caller mixes the Dirichlet
+   * noise into `prior_logits`; `gumbel` is the noise of the final categorical draw; the 1e-7 tie-break noise of every
+   * selection is a counter-based stream keyed by (noise_seed, tree, node, visit count of the node, action). */
+  EAZ_FLAG_PUCT = 1 << 5,
   EAZ_SEARCH_DEFAULT_FLAGS = (1 << 0) | (1 << 1) | (1 << 2)
 };
 #define EAZ_FLAG_STREAMS(k) ((k) << EAZ_FLAG_STREAMS_SHIFT)
@@ -221,6 +228,11 @@ typedef struct eaz_search_config {
   float epsilon;            /* 1e-8 */
   int32_t flags;            /* EAZ_FLAG_* */
   int32_t mlp_mode;         /* EAZ_MLP_* */
+  /* ABI 2 (appended): mctx muzero_policy parameters, read only with EAZ_FLAG_PUCT */
+  float pb_c_init;          /* 1.25 */
+  float pb_c_base;          /* 19652 */
+  float temperature;        /* 1.0 */
+  uint32_t noise_seed;      /* tie-break noise stream */
 } eaz_search_config;
 
 enum {

@@ -157,4 +157,43 @@ EAZ_HD float eaz_tanh(float x) {
   return x < 0.0f ? -t : t;
 }
 
+/* ln(x) for finite x > 0 (normal or subnormal), <= 1 ulp-class accuracy: x = m * 2^e with m in [sqrt(1/2), sqrt(2)),
+ * Cephes-style degree-8 kernel in f = m - 1.  ln(0) = -inf, ln(x < 0) = NaN, ln(inf) = inf.  Used by the PUCT exploration
+ * constant (mctx action_selection.muzero_action_selection) and the visit-count logits of muzero_policy. */
+EAZ_HD float eaz_log(float x) {
+  if (x != x || x < 0.0f) return eaz_bits_to_f32(0x7fc00000u);
+  if (x == 0.0f) return eaz_bits_to_f32(0xff800000u);
+  uint32_t u = eaz_f32_to_bits(x);
+  if (u == 0x7f800000u) return x;
+  int e = 0;
+  if (u < 0x00800000u) { /* subnormal: scale by 2^23 (exact) */
+    x = eaz_mul(x, 8388608.0f);
+    u = eaz_f32_to_bits(x);
+    e = -23;
+  }
+  e += (int)(u >> 23) - 127;
+  float m = eaz_bits_to_f32((u & 0x007fffffu) | 0x3f800000u); /* [1, 2) */
+  if (m > 1.41421356237f) {
+    m = eaz_mul(m, 0.5f);
+    e += 1;
+  }
+  const float f = eaz_sub(m, 1.0f);
+  const float z = eaz_mul(f, f);
+  float p = 7.0376836292e-2f;
+  p = eaz_fma(p, f, -1.1514610310e-1f);
+  p = eaz_fma(p, f, 1.1676998740e-1f);
+  p = eaz_fma(p, f, -1.2420140846e-1f);
+  p = eaz_fma(p, f, 1.4249322787e-1f);
+  p = eaz_fma(p, f, -1.6668057665e-1f);
+  p = eaz_fma(p, f, 2.0000714765e-1f);
+  p = eaz_fma(p, f, -2.4999993993e-1f);
+  p = eaz_fma(p, f, 3.3333331174e-1f);
+  float y = eaz_mul(eaz_mul(f, z), p);
+  const float fe = (float)e;
+  y = eaz_fma(fe, -2.12194440e-4f, y);
+  y = eaz_fma(-0.5f, z, y);
+  y = eaz_add(f, y);
+  return eaz_fma(fe, 0.693359375f, y);
+}
+
 #endif /* EAZ_MATH_H_ */

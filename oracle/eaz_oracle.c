@@ -815,6 +815,55 @@ static int orc_root_argmax(const orc_tree* t, const float* gumbel, const float* 
   return orc_argmax(score, A);
 }
 
+/* ---- emctx.epistemic_muzero_policy (EAZ_FLAG_PUCT): mctx action_selection.muzero_action_selection with
+ * qtransforms.qtransform_by_parent_and_siblings; the beta bonus enters q as in the Gumbel path (assumption). */
+
+/* tie-break noise: mctx adds 1e-7 * uniform(rng_key, [A]); here a counter-based stream keyed by (seed, tree, node, visits of
+ * the node, action) -- "the k-th selection made at this node" -- so that lazily cached and eagerly recomputed selections agree */
+static uint32_t orc_xx_round(uint32_t acc, uint32_t w) { return rotl32(acc + w * 0x85EBCA77u, 13) * 0x9E3779B1u; }
+static float orc_tie_noise(uint32_t seed, uint32_t b, uint32_t node, uint32_t visits, uint32_t a) {
+  uint32_t h = seed + 0x9E3779B1u;
+  h = orc_xx_round(h, b);
+  h = orc_xx_round(h, node);
+  h = orc_xx_round(h, visits);
+  h = orc_xx_round(h, a);
+  h ^= h >> 15; h *= 0x85EBCA77u; h ^= h >> 13; h *= 0xC2B2AE3Du; h ^= h >> 16;
+  return eaz_mul((float)(h >> 8), 5.9604644775390625e-08f); /* 24 random bits * 2^-24: exact */
+}
+
+static int orc_puct_select(const eaz_search_config* cfg, const orc_tree* t, int node, int b, float beta, int use_beta,
+                           const uint8_t* invalid_at_root) {
+  const int A = t->A;
+  const size_t o = (size_t)node * A;
+  float q[ORC_MAX_A], safe[ORC_MAX_A] = {0}, p[ORC_MAX_A], score[ORC_MAX_A];
+  float node_value = t->node_values[node];
+  if (use_beta && (cfg->flags & EAZ_FLAG_BETA_RAW)) node_value = eaz_add(node_value, eaz_mul(beta, eaz_sqrt(t->node_var[node])));
+  for (int a = 0; a < A; ++a) { /* tree.qvalues(node) */
+    const float d = t->discounts[o + a];
+    q[a] = eaz_add(t->rewards[o + a], eaz_mul(d, t->values[o + a]));
+    if (use_beta) {
+      const float qv = eaz_add(t->rewards_var[o + a], eaz_mul(eaz_mul(d, d), t->values_var[o + a]));
+      q[a] = eaz_add(q[a], eaz_mul(beta, eaz_sqrt(qv)));
+    }
+    safe[a] = t->children_visits[o + a] > 0 ? q[a] : node_value;
+  }
+  const float mn = eaz_min(node_value, orc_minv(safe, A)), mx = eaz_max(node_value, orc_maxv(safe, A));
+  const float den = eaz_max(eaz_sub(mx, mn), cfg->epsilon);
+  const float nv = (float)t->node_visits[node];
+  const float pb_c = eaz_add(cfg->pb_c_init, eaz_log(eaz_div(eaz_add(eaz_add(nv, cfg->pb_c_base), 1.0f), cfg->pb_c_base)));
+  const float explore = eaz_mul(eaz_sqrt(nv), pb_c);
+  orc_softmax(t->prior_logits + o, A, p);
+  for (int a = 0; a < A; ++a) {
+    const int32_t vc = t->children_visits[o + a];
+    const float value_score = eaz_div(eaz_sub(vc > 0 ? q[a] : mn, mn), den);
+    const float policy_score = eaz_div(eaz_mul(explore, p[a]), eaz_add((float)vc, 1.0f));
+    const float noise = eaz_mul(1e-7f, orc_tie_noise(cfg->noise_seed, (uint32_t)b, (uint32_t)node, (uint32_t)t->node_visits[node], (uint32_t)a));
+    score[a] = eaz_add(eaz_add(value_score, policy_score), noise);
+    if (invalid_at_root && invalid_at_root[a]) score[a] = ORC_NEG_INF; /* masked_argmax(to_argmax, root_invalid_actions * (depth == 0)) */
+  }
+  return orc_argmax(score, A);
+}
+
 static void orc_update_node(orc_tree* t, int node, const float* logits, float value, float var,
                             const orc_env_state* emb) {
   memcpy(t->prior_logits + (size_t)node * t->A, logits, sizeof(float) * (size_t)t->A);
@@ -872,7 +921,9 @@ static void orc_search_one(orc_ctx* cx, const eaz_search_inputs* in, eaz_search_
     int node = 0, action = -1, depth = 0, next = 0, cont = 1;
     while (cont) {
       node = next;
-      if (depth == 0) { /* gumbel_muzero_root_action_selection */
+      if (cfg->flags & EAZ_FLAG_PUCT) { /* muzero_action_selection at every depth */
+        action = orc_puct_select(cfg, &t, node, b, beta, depth == 0 || (cfg->flags & EAZ_FLAG_BETA_INTERIOR) != 0, depth == 0 ? invalid : NULL);
+      } else if (depth == 0) { /* gumbel_muzero_root_action_selection */
         orc_qtransform(cfg, &t, 0, beta, 1, cq);
         int sim_index = 0;
         for (int a = 0; a < A; ++a) sim_index += t.children_visits[a];
@@ -937,6 +988,21 @@ static void orc_search_one(orc_ctx* cx, const eaz_search_inputs* in, eaz_search_
     }
   }
 
+  if (cfg->flags & EAZ_FLAG_PUCT) {
+    /* mctx policies.muzero_policy: action_weights = visit_probs; action ~ categorical(log(visit_probs) / temperature), drawn as
+     * argmax(logits + gumbel) with the supplied noise */
+    int32_t tot = 0;
+    for (int a = 0; a < A; ++a) tot += t.children_visits[a];
+    for (int a = 0; a < A; ++a) {
+      p[a] = tot > 0 ? eaz_div((float)t.children_visits[a], eaz_max((float)tot, 1.0f)) : eaz_div(1.0f, (float)A);
+      x[a] = eaz_log(eaz_max(p[a], EAZ_F32_TINY)); /* _get_logits_from_probs */
+    }
+    const float mxl = orc_maxv(x, A);
+    const float tdiv = eaz_max(EAZ_F32_TINY, cfg->temperature);
+    for (int a = 0; a < A; ++a) x[a] = eaz_add(eaz_div(eaz_sub(x[a], mxl), tdiv), gumbel[a]); /* _apply_temperature + Gumbel-max */
+    out->action[b] = orc_argmax(x, A);
+    if (out->action_weights) memcpy(out->action_weights + (size_t)b * A, p, sizeof(float) * (size_t)A);
+  } else {
   /* policy wrapper step 4 (A.1) */
   int considered_visit = 0;
   for (int a = 0; a < A; ++a) if (t.children_visits[a] > considered_visit) considered_visit = t.children_visits[a];
@@ -946,6 +1012,7 @@ static void orc_search_one(orc_ctx* cx, const eaz_search_inputs* in, eaz_search_
   orc_mask_invalid(x, invalid, A, logits);
   orc_softmax(logits, A, p);
   if (out->action_weights) memcpy(out->action_weights + (size_t)b * A, p, sizeof(float) * (size_t)A);
+  }
 
   /* epistemic_summary (A.7) */
   if (out->value) out->value[b] = t.node_values[0];

@@ -490,3 +490,51 @@ def test_search_streams_identical(ops, kind, kw, B, k, mode):
     many = {n: host(v).copy() for n, v in ops.search(cfg, denv, dnet, root, want_tree=True).items()}
     for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
         H.assert_same_bits(many[name], one[name], name)
+
+
+# ----------------------------------------------------------------------------- PUCT (emctx.epistemic_muzero_policy)
+PUCT_CASES = [
+    ("deepsea", dict(size=10), 64, dict(num_simulations=32, discount=0.997), dict(beta_max=1.0)),
+    ("deepsea", dict(size=6), 50, dict(num_simulations=24, discount=0.9, max_depth=4, temperature=0.5, noise_seed=7), dict(beta_max=0.5, invalid_frac=0.3)),
+    ("subleq", dict(word_size=16), 40, dict(num_simulations=32, discount=0.97, pb_c_init=2.0, gumbel_scale=0.0), dict(beta_max=1.0)),
+    ("subleq", dict(word_size=40), 12, dict(num_simulations=20, discount=0.97, flags=_abi.FLAG_PUCT), dict(beta_max=0.0)),
+]
+
+
+@pytest.mark.parametrize("kind,kw,B,cfg_kw,root_kw", PUCT_CASES)
+def test_search_puct_bit_exact(ops, kind, kw, B, cfg_kw, root_kw):
+    """EAZ_FLAG_PUCT: PUCT selection (mctx muzero_action_selection + qtransform_by_parent_and_siblings, beta bonus as in the Gumbel
+    path) and the muzero_policy output, CUDA vs oracle, every tree array bit for bit."""
+    env = H.make_env(kind, seed=61, **kw)
+    net = H.make_net(env, seed=62, fill=0.5)
+    root = H.make_root(env, net, B, seed=63, **root_kw)
+    cfg_kw = dict(cfg_kw)
+    cfg_kw["flags"] = cfg_kw.get("flags", _abi.SEARCH_DEFAULT_FLAGS) | _abi.FLAG_PUCT
+    exp, got = run_both(ops, env, net, root, cfg_kw)
+    assert_tree_equal(exp, got)
+    n = cfg_kw["num_simulations"]
+    assert (got["visit_counts"].sum(1) == n).all()
+    np.testing.assert_array_equal(got["action_weights"], got["visit_probs"])  # muzero_policy: action_weights = visit_probs
+    gum = cfg_kw.get("gumbel_scale", 1.0)
+    if gum == 0.0:  # greedy draw: the most visited action
+        assert (got["visit_counts"][np.arange(B), got["action"]] == got["visit_counts"].max(1)).all()
+
+
+def test_puct_policy_facade(ops):
+    import torch
+
+    from e_alphazero_b200 import context, emctx, pgx
+
+    amap = (np.random.default_rng(0).random((8, 8)) < 0.5).astype(np.uint8)
+    env = pgx.DeepSea(size_of_grid=8, action_map=amap)
+    onet = H.make_net(H.make_env("deepsea", seed=0, size=8), seed=2, fill=0.5)
+    net = H.device_net(onet)
+    B = 32
+    states = env.init(batch_size=B)
+    fwd = context.get_forward_fn(env)
+    (ex, _, v, u, _), _ = fwd.apply(net, None, states, is_training=False)
+    rf = context.get_epistemic_recurrent_fn(env, fwd, B, exploration=False, discount=0.997, two_players_game=False)
+    root = emctx.EpistemicRootFnOutput(prior_logits=ex, value=v, value_epistemic_variance=u, embedding=states, beta=torch.zeros(B, device="cuda"))
+    out = emctx.epistemic_muzero_policy(net, 3, root, rf, 16)
+    s = out.search_tree.epistemic_summary()
+    assert (s.visit_counts.sum(1) == 16).all() and torch.equal(out.action_weights, s.visit_probs)
