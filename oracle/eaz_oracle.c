@@ -1123,5 +1123,6 @@ int orc_reanalyze_targets(const eaz_reanalyze_config* cfg, int32_t B, int32_t A,
 
 float orc_expf(float x) { return eaz_exp(x); }
 float orc_tanhf(float x) { return eaz_tanh(x); }
+float orc_logf(float x) { return eaz_log(x); }
 void orc_softmax_probe(const float* x, int32_t A, float* p) { orc_softmax(x, A, p); }
 float orc_tree_sum_probe(const float* x, int32_t A) { return orc_tree_sum(x, A); }

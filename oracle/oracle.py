@@ -31,13 +31,14 @@ def build(force: bool = False) -> str:
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(_SO):
-            build()
+        build()  # (a no-op when libeaz_oracle.so is newer than its three sources)
         _lib = C.CDLL(_SO)
         _lib.orc_expf.restype = C.c_float
         _lib.orc_expf.argtypes = [C.c_float]
         _lib.orc_tanhf.restype = C.c_float
         _lib.orc_tanhf.argtypes = [C.c_float]
+        _lib.orc_logf.restype = C.c_float
+        _lib.orc_logf.argtypes = [C.c_float]
         _lib.orc_tree_sum_probe.restype = C.c_float
     return _lib
 
@@ -358,6 +359,10 @@ def reanalyze_targets(discount, exploration_beta, exploration_ube_target, temper
 
 def expf(x: float) -> float:
     return lib().orc_expf(float(x))
+
+
+def logf(x: float) -> float:
+    return float(lib().orc_logf(C.c_float(x)))
 
 
 def tanhf(x: float) -> float:

@@ -197,3 +197,42 @@ def test_reanalyze_targets(golden_dir):
         assert (got["ube_target"].view(np.uint32) == exp["ube_target"].view(np.uint32)).all(), i
         np.testing.assert_allclose(got["exploration_policy_target"], exp["exploration_policy_target"], rtol=1e-6, atol=1e-7)
         assert (got["exploration_policy_target"][args["invalid_actions"].astype(bool)] == 0).all()
+
+
+def test_eaz_log_accuracy():
+    """include/eaz_math.h eaz_log (used by the PUCT exploration constant and the muzero_policy visit-count logits)."""
+    rng = np.random.default_rng(3)
+    xs = np.concatenate([np.exp(rng.uniform(-87, 88, 4000)), 1.0 + rng.uniform(-1e-3, 1e-3, 500), [1.0, 2.0, 0.5, 1e-40, 3.4e38, 1.17549435e-38]]).astype(np.float32)
+    got = np.array([O.logf(float(x)) for x in xs], np.float32)
+    ref = np.log(xs.astype(np.float64))
+    ulp = np.abs(got - ref) / np.maximum(np.spacing(np.abs(ref).astype(np.float32)), 1e-45)
+    assert ulp.max() <= 1.0, ulp.max()
+    assert O.logf(0.0) == -np.inf and np.isnan(O.logf(-1.0)) and O.logf(float("inf")) == np.inf
+
+
+@pytest.mark.parametrize("kind,kw", [("deepsea", dict(size=8)), ("subleq", dict(word_size=16))])
+def test_puct_oracle_tree_invariants(kind, kw):
+    """Oracle PUCT search (EAZ_FLAG_PUCT): mctx tree invariants and the muzero_policy outputs."""
+    from e_alphazero_b200 import _abi
+    from tests import helpers as H
+
+    env = H.make_env(kind, seed=1, **kw)
+    net = H.make_net(env, seed=2, fill=0.5)
+    B, n = 24, 20
+    root = H.make_root(env, net, B, seed=3, beta_max=1.0, invalid_frac=0.2)
+    cfg = _abi.default_search_config(num_simulations=n, discount=0.97, gumbel_scale=0.0)
+    cfg.flags |= _abi.FLAG_PUCT
+    out = O.search(cfg, env, net, root, want_tree=True)
+    assert (out["visit_counts"].sum(1) == n).all() and (out["node_visits"][:, 0] == n + 1).all()
+    cv, ci = out["children_visits"], out["children_index"]
+    assert (out["node_visits"] == np.where(out["node_visits"] > 0, 1 + cv.sum(2), 0)).all()  # node_visits[parent] = 1 + sum(children_visits)
+    for b in range(B):
+        for node in range(n + 1):
+            for a in np.flatnonzero(ci[b, node] >= 0):
+                c = ci[b, node, a]
+                assert out["parents"][b, c] == node and out["action_from_parent"][b, c] == a
+    np.testing.assert_array_equal(out["action_weights"], out["visit_probs"])
+    assert (out["visit_counts"][np.arange(B), out["action"]] == out["visit_counts"].max(1)).all()  # gumbel_scale 0: greedy in the visit counts
+    inv = root["invalid_actions"].astype(bool)
+    some_valid = ~inv.all(1)  # (all actions invalid: masked_argmax falls back to action 0, like mctx)
+    assert (out["visit_counts"][some_valid][inv[some_valid]] == 0).all()  # invalid root actions are never selected
