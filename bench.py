@@ -350,6 +350,9 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         except (OSError, ValueError):
             pass
         roofline = dict(mlp_obj if dominant == "network" else tree_obj)
+        roofline["timing"] = ("per-launch CUDA events in a separate profiled pass of the same search on the same stream (eaz_search_gumbel_profiled): the "
+                              "events serialise the PDL chain and the sub-batch streams, so these durations are upper bounds -- in the timed region the tree "
+                              "kernel stages its data under the network kernel and sub-batches overlap (value / ms_per_step is the overlapped time)")
         roofline["dominant"] = dominant
         roofline["share_of_search_time"] = (mlp_ms if dominant == "network" else tree_ms) / total_ms
         roofline["other"] = tree_obj if dominant == "network" else mlp_obj

@@ -749,7 +749,8 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   }
   EAZ_CHECK_LAUNCH("root_init_kernel");
   // staging area of tree_step_kernel (tree_step.cuh): per warp, sized for the cached selections + states of all N nodes
-  const int chase_cap = (J == 1 && t.N <= 512) ? ((t.N + 2 + 7) & ~7) : 0;
+  static const bool no_staging = getenv("EAZ_NO_STAGING") != nullptr;  // measurement knob: force the DIRECT path
+  const int chase_cap = (J == 1 && t.N <= 512 && !no_staging) ? ((t.N + 2 + 7) & ~7) : 0;
   const size_t stage_bytes = chase_cap ? (size_t)4 * Stage<G>::words(chase_cap) * sizeof(uint32_t) : 0;
   for (int sim = 0; sim <= sp.n; ++sim) {
     {  // backward of simulation sim-1 fused with the descent of simulation sim
