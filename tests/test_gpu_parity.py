@@ -538,3 +538,44 @@ def test_puct_policy_facade(ops):
     out = emctx.epistemic_muzero_policy(net, 3, root, rf, 16)
     s = out.search_tree.epistemic_summary()
     assert (s.visit_counts.sum(1) == 16).all() and torch.equal(out.action_weights, s.visit_probs)
+
+
+# ----------------------------------------------------------------------------- edge shapes
+@pytest.mark.parametrize("kind,kw,B,n,mode", [
+    ("deepsea", dict(size=4), 1, 1, _abi.MLP_EXACT),       # one tree, one simulation
+    ("deepsea", dict(size=4), 1, 5, _abi.MLP_TENSOR),      # one row in a 128-row network tile
+    ("deepsea", dict(size=10), 129, 8, _abi.MLP_TENSOR),   # one row past a tile boundary
+    ("deepsea", dict(size=4), 37, 70, _abi.MLP_EXACT),     # far more simulations than reachable states: deep absorbing chains (DIRECT path, L > 32)
+    ("subleq", dict(word_size=16), 1, 3, _abi.MLP_TENSOR),
+    ("subleq", dict(word_size=16), 131, 4, _abi.MLP_TENSOR),
+])
+def test_search_edge_shapes(ops, kind, kw, B, n, mode):
+    env = H.make_env(kind, seed=71, **kw)
+    net = H.make_net(env, seed=72, fill=0.5)
+    root = H.make_root(env, net, B, seed=73, beta_max=1.0)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(batch=B, num_simulations=n, discount=0.97, mlp_mode=mode)
+    cfg.flags |= _abi.flag_streams(2)  # fewer tiles than streams must degrade gracefully
+    got = {k: host(v) for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
+    ocfg = _abi.default_search_config(num_simulations=n, discount=0.97)
+    if mode == _abi.MLP_EXACT:
+        exp = O.search(ocfg, env, net, root, want_tree=True)
+    else:
+        replay = dict(states=got["embeddings"], logits=got["children_prior_logits"], value=got["raw_values"], var=got["raw_values_epistemic_variance"])
+        exp = O.search(ocfg, env, None, root, want_tree=True, replay=replay)
+        assert exp["replay_misses"] == 0
+    assert_tree_equal(exp, got)
+    assert (got["node_visits"][:, 0] == n + 1).all()
+
+
+def test_search_rejects_bad_arguments(ops):
+    env = H.make_env("deepsea", seed=1, size=4)
+    net = H.make_net(env, seed=2, fill=0.5)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    root = H.device_root(env, denv, H.make_root(env, net, 8, seed=3))
+    from e_alphazero_b200._lib import EazError
+
+    with pytest.raises(EazError):
+        ops.search(_abi.default_search_config(batch=8, num_simulations=0), denv, dnet, root)
+    with pytest.raises(EazError):
+        ops.search(_abi.default_search_config(batch=8, num_simulations=8, max_num_considered_actions=0), denv, dnet, root)
