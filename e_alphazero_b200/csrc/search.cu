@@ -142,6 +142,9 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
   return t;
 }
 
+constexpr int kFlagManyTrees = 1 << 30;  // internal (set by eaz_search_gumbel): the whole batch is >= kManyTrees trees
+constexpr int kManyTrees = 6144;
+
 // Search scalars, by value into the kernels.
 struct SearchParams {
   int n, max_depth, max_considered;
@@ -752,10 +755,26 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   static const bool no_staging = getenv("EAZ_NO_STAGING") != nullptr;  // measurement knob: force the DIRECT path
   const int chase_cap = (J == 1 && t.N <= 512 && !no_staging) ? ((t.N + 2 + 7) & ~7) : 0;
   const size_t stage_bytes = chase_cap ? (size_t)4 * Stage<G>::words(chase_cap) * sizeof(uint32_t) : 0;
+  static const bool one_per_warp = getenv("EAZ_ONE_TREE_PER_WARP") != nullptr;  // measurement knob
+  bool two_per_warp = false;
+  size_t stage2_bytes = 0;
+  if constexpr (G <= 4 && J == 1) {
+    stage2_bytes = (size_t)8 * Stage2<G>::words(chase_cap) * sizeof(uint32_t);
+    // issue-bound regime only (measured: C2 = 4096 trees is 3 % faster with one tree per warp, 8192 trees 4 % and 65536 trees 12 %
+    // faster with two): the caller-visible batch decides, not the sub-batch of one stream
+    two_per_warp = !one_per_warp && (sp.flags & kFlagManyTrees) && chase_cap > 0 && stage2_bytes <= 48 * 1024 && !flags;
+  }
   for (int sim = 0; sim <= sp.n; ++sim) {
     {  // backward of simulation sim-1 fused with the descent of simulation sim
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
-      cudaError_t le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), stage_bytes, st,  // one warp per tree
+      cudaError_t le;
+      if constexpr (G <= 4 && J == 1) {
+        if (two_per_warp)  // 16 lanes per tree (tree_step.cuh: tree_step2_kernel)
+          le = launch_pdl(tree_step2_kernel<G>, dim3(ceil_div(t.B, 8)), dim3(128), stage2_bytes, st, t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n),
+                          in->beta, in->invalid_actions, g_timeline, g_tree_trace, chase_cap);
+      }
+      if (!two_per_warp)
+      le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), stage_bytes, st,  // one warp per tree
                                   t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions, g_timeline, g_tree_trace,
                                   chase_cap, tile_done, (const int*)mlp_done, (sim > 0 && flag_mode > 1) ? nheads * mlp_launches : 0);
       if (le != cudaSuccess) return cuda_fail(le, "tree_step_kernel launch");
@@ -1008,7 +1027,11 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   EAZ_CHECK_ARG(cfg && in && out, "search: NULL config / inputs / outputs");
   int sizes[8], parts = 1;
   if (cfg->batch >= 1) sub_batches(cfg, sizes, &parts);
-  if (parts <= 1 || tl_prof != nullptr) return search_one(cfg, in, out, workspace, workspace_bytes, stream);
+  if (parts <= 1 || tl_prof != nullptr) {
+    eaz_search_config c = *cfg;
+    c.flags = (c.flags & ~kFlagManyTrees) | (cfg->batch >= kManyTrees ? kFlagManyTrees : 0);
+    return search_one(&c, in, out, workspace, workspace_bytes, stream);
+  }
   // ---- EAZ_FLAG_STREAMS: independent sub-batches (trees never interact) searched concurrently on auxiliary streams, so that
   // one sub-batch's tree kernel (issue-bound) overlaps another's network kernel (tensor / L2-bound) and env step (latency-bound)
   EnvDesc env;
@@ -1034,6 +1057,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
     eaz_search_config c = *cfg;
     c.batch = sizes[p];
     c.flags &= ~(0xF << EAZ_FLAG_STREAMS_SHIFT);
+    c.flags = (c.flags & ~kFlagManyTrees) | (cfg->batch >= kManyTrees ? kFlagManyTrees : 0);
     auto offf = [&](const float* q, size_t per) { return q ? q + b0 * per : nullptr; };
     auto offu = [&](const uint8_t* q, size_t per) { return q ? q + b0 * per : nullptr; };
     auto offi = [&](const int32_t* q, size_t per) { return q ? q + b0 * per : nullptr; };

@@ -146,6 +146,205 @@ __device__ __forceinline__ int select_action_staged(const SearchParams& sp, cons
   return act;
 }
 
+// DIRECT path: one warp, one tree, everything loaded as it is needed (also the reference implementation of the arithmetic that
+// the STAGED paths reproduce from staged copies).
+template <int G, int J>
+__device__ __forceinline__ void tree_step_direct(const Tree& t, const SearchParams& sp, const EnvDesc& env, int sim, int do_backward, int do_select,
+                                                 float beta, const uint8_t* __restrict__ invalid, int b, int lane, long long* trc) {
+  const unsigned uB = (unsigned)t.B, uA = (unsigned)t.A, ub = (unsigned)b;
+  constexpr int kLevelsPerRound = 32 / G;
+  const int gl = lane & (G - 1), glev = lane / G;
+  bool valid[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) valid[j] = (gl + G * j) < t.A;
+  int L = 0, leaf = 0;
+  if (do_backward) {
+    // ------------------------------------------------------------------ 1. expand
+    leaf = t.leaf[b];
+    L = t.path_len[b];
+    const unsigned lslot = (unsigned)leaf * uB + ub;
+    float m = -INFINITY;
+    for (int a = lane; a < t.A; a += 32) m = fmaxf(m, t.net_logits[ub * uA + a]);
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));  // context.py:135
+    for (int a = lane; a < t.A; a += 32)
+      t.edges[(size_t)(lslot * uA + a)].pl = __fsub_rn(t.net_logits[ub * uA + a], m);  // legal_action_mask is all True (:137)
+    int term;
+    if (env.kind == EAZ_ENV_DEEPSEA) term = EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot]);
+    else term = t.states[(size_t)lslot * t.S + 35] & EAZ_SQ_FLAG_TERM;
+    const float value = term ? 0.0f : t.net_value[b];  // :140
+    const float var = term ? 0.0f : t.net_ube[b];      // :141
+    float disc = sp.discount;
+    if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
+    if (term) disc = 0.0f;                              // :144
+    const int2 last = t.path[(unsigned)(L - 1) * uB + ub];
+    EdgeRec* pe0 = t.edges + (size_t)(((unsigned)last.x * uB + ub) * uA + (unsigned)last.y);
+    if (lane == 0) {
+      // update_tree_node: the leaf's record (visits + 1: a leaf can be re-expanded under a max_depth cut-off)
+      uint4* ln = reinterpret_cast<uint4*>(t.nodes + lslot);
+      const int old_visits = (int)ln[0].x;
+      ln[0] = make_uint4((unsigned)(old_visits + 1), __float_as_uint(value), __float_as_uint(var), 0u);
+      ln[1] = make_uint4(__float_as_uint(value), __float_as_uint(var), (unsigned)(last.x + 1), (unsigned)(last.y + 1));
+      pe0->ci1 = leaf + 1;
+      pe0->rew = t.reward[b];  // :139
+      pe0->dis = disc;
+    }
+    __syncwarp();
+    if (trc) trc[1] = clock64();
+
+    // ------------------------------------------------------------------ 2. backward (levels L-1 .. 0)
+    const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
+    float lv = value, lvar = std_backup ? __fsqrt_rn(var) : var;  // running leaf_value / leaf variance (or std)
+    float below_val = value, below_var = var;                     // updated mean / variance of the node one level deeper
+    for (int hi = L; hi > 0; hi -= 32) {                          // rounds of 32 levels, deepest first
+      const int lo = max(hi - 32, 0), cnt = hi - lo;
+      const int lev = lo + lane;                                  // this lane's level
+      const bool have = lane < cnt;
+      int2 pa = make_int2(0, 0);
+      uint4 nrec = make_uint4(0u, 0u, 0u, 0u);
+      float rr = 0.0f, dd = 0.0f;
+      int cvis = 0;
+      unsigned pslot = 0;
+      EdgeRec* pe = nullptr;
+      if (have) {
+        pa = t.path[(unsigned)lev * uB + ub];
+        pslot = (unsigned)pa.x * uB + ub;
+        pe = t.edges + (size_t)(pslot * uA + (unsigned)pa.y);
+        nrec = reinterpret_cast<const uint4*>(t.nodes + pslot)[0];
+        cvis = pe->vis;
+        rr = pe->rew;
+        dd = pe->dis;
+      }
+      // the recurrences: a uniform loop over this round's levels, deepest first, in the reference's op order
+      float my_lv = 0.0f, my_lvar = 0.0f;
+      for (int i = cnt - 1; i >= 0; --i) {
+        const float r = __shfl_sync(0xffffffffu, rr, i), d = __shfl_sync(0xffffffffu, dd, i);
+        lv = __fadd_rn(r, __fmul_rn(d, lv));
+        lvar = std_backup ? __fadd_rn(0.0f, __fmul_rn(fabsf(d), lvar)) : __fadd_rn(0.0f, __fmul_rn(__fmul_rn(d, d), lvar));
+        if (lane == i) { my_lv = lv; my_lvar = lvar; }
+      }
+      // running means, all levels in parallel
+      const int nvis = (int)nrec.x;
+      const float nval = __uint_as_float(nrec.y), nvar = __uint_as_float(nrec.z);
+      const float count = (float)nvis;
+      const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(nval, count), my_lv), __fadd_rn(count, 1.0f));
+      float pvar;
+      if (std_backup) {
+        const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(nvar), count), my_lvar), __fadd_rn(count, 1.0f));
+        pvar = __fmul_rn(ps, ps);
+      } else {
+        pvar = __fdiv_rn(__fadd_rn(__fmul_rn(nvar, count), my_lvar), __fadd_rn(count, 1.0f));
+      }
+      // children_values[parent, a] = the child's CURRENT (already updated) mean: one level deeper
+      float cval = __shfl_down_sync(0xffffffffu, pv, 1), cvarr = __shfl_down_sync(0xffffffffu, pvar, 1);
+      if (lane == cnt - 1) { cval = below_val; cvarr = below_var; }
+      if (have) {
+        reinterpret_cast<uint4*>(t.nodes + pslot)[0] = make_uint4((unsigned)(nvis + 1), __float_as_uint(pv), __float_as_uint(pvar), 0u);
+        pe->vis = cvis + 1;
+        *reinterpret_cast<float2*>(&pe->val) = make_float2(cval, cvarr);
+      }
+      below_val = __shfl_sync(0xffffffffu, pv, 0);
+      below_var = __shfl_sync(0xffffffffu, pvar, 0);
+    }
+    __syncwarp();
+    if (trc) { trc[2] = clock64(); trc[6] = L; }
+  }
+  if (!do_select) return;
+
+  // -------------------------------------------------------------------- 3. refresh the cached selections
+  // nodes: path levels 0..L-1 and the new leaf (index L); before the first simulation only the root.
+  {
+    const int nrefresh = do_backward ? L + 1 : 1;
+    for (int base = 0; base < nrefresh; base += kLevelsPerRound) {
+      const int lev = base + glev;
+      const bool act_on = lev < nrefresh;
+      int node = 0;
+      if (act_on && do_backward) node = lev < L ? t.path[(unsigned)lev * uB + ub].x : leaf;
+      const unsigned slot = (unsigned)node * uB + ub;
+      Edge<G, J> e;
+      float raw, raw_var;
+      load_edges<G, J>(t, slot, gl, act_on, e);
+      load_node_raw(t, slot, act_on, raw, raw_var);
+      int child, act;
+      if (sp.flags & EAZ_FLAG_PUCT) {  // muzero_action_selection at every depth (warp-uniform switch)
+        const bool is_root = act_on && node == 0;
+        uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
+        if (act_on) h0 = reinterpret_cast<const uint4*>(t.nodes + slot)[0];  // node_visits, node value, node variance
+        bool inval[J];
+#pragma unroll
+        for (int j = 0; j < J; ++j) inval[j] = (is_root && valid[j] && invalid) ? (invalid[ub * uA + gl + G * j] != 0) : false;
+        act = puct_select<G, J>(sp, e, valid, (int)h0.x, __uint_as_float(h0.y), __uint_as_float(h0.z), beta,
+                                is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0, ub, (unsigned)node, inval, gl);
+        int ci_sel = -1;
+#pragma unroll
+        for (int j = 0; j < J; ++j)
+          if (j == act / G) ci_sel = e.ci[j];
+        child = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
+      } else {
+        act = select_action<G, J>(t, sp, e, valid, raw, raw_var, beta, act_on && node == 0, ub, uA, invalid, lane, gl, &child);
+      }
+      if (act_on && gl == 0) t.nodes[slot].pad0 = pack_next(act, child);
+    }
+    __syncwarp();
+    if (trc) trc[3] = clock64();
+  }
+
+  // -------------------------------------------------------------------- 4. simulate: follow the cached selections
+  // Nodes 0..sim exist.  For trees of up to 32*kChaseSlots nodes every cached (action, child) word is fetched once
+  // (independent loads, lane i holds nodes i, i+32, ...) and the chase itself runs over registers with warp
+  // shuffles; larger trees chase through memory, one dependent 16-byte load per level.
+  constexpr int kChaseSlots = 9;
+  int node = 0, depth = 0, action = 0, child = -1;
+  if (sim < 32 * kChaseSlots) {
+    int nxw[kChaseSlots];
+#pragma unroll
+    for (int s = 0; s < kChaseSlots; ++s) {
+      const int nd = lane + 32 * s;
+      nxw[s] = (32 * s <= sim && nd <= sim) ? t.nodes[(unsigned)nd * uB + ub].pad0 : 0;
+    }
+    while (true) {
+      const int slot = node >> 5;
+      int v = 0;
+#pragma unroll
+      for (int s = 0; s < kChaseSlots; ++s)
+        if (s == slot) v = nxw[s];
+      const int nx = __shfl_sync(0xffffffffu, v, node & 31);
+      action = nx & 0xff;
+      child = (nx >> 8) - 1;
+      if (lane == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
+      depth += 1;
+      if (child < 0 || depth >= sp.max_depth) break;
+      node = child;
+    }
+  } else {
+    while (true) {
+      const int nx = t.nodes[(unsigned)node * uB + ub].pad0;
+      action = nx & 0xff;
+      child = (nx >> 8) - 1;
+      if (lane == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
+      depth += 1;
+      if (child < 0 || depth >= sp.max_depth) break;
+      node = child;
+    }
+  }
+  if (trc) { trc[4] = clock64(); trc[5] = depth; }
+  if (lane == 0) {
+    const int new_leaf = child < 0 ? sim + 1 : child;  // search.py: node first expanded on simulation i gets index i+1
+    t.path_len[b] = depth;
+    t.parent[b] = node;
+    t.action[b] = action;
+    t.leaf[b] = new_leaf;
+    if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
+      uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
+      float reward;
+      const uint32_t ns = deepsea_step(st[(unsigned)node * uB + ub], action, env.size, env.action_map, &reward);
+      st[(unsigned)new_leaf * uB + ub] = ns;
+      t.reward[b] = reward;
+      t.cell[b] = deepsea_obs_index(ns, env.size);
+    }
+  }
+}
+
 // Staging area of one warp (uint32 words); kRounds refresh rounds = kNodes nodes (path + leaf) fit.
 template <int G>
 struct Stage {
@@ -469,177 +668,345 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
   }
 
   // ==================================================================== DIRECT path
-  if (do_backward) {
-    // ------------------------------------------------------------------ 1. expand
-    leaf = t.leaf[b];
-    L = t.path_len[b];
-    const unsigned lslot = (unsigned)leaf * uB + ub;
-    float m = -INFINITY;
-    for (int a = lane; a < t.A; a += 32) m = fmaxf(m, t.net_logits[ub * uA + a]);
-#pragma unroll
-    for (int s = 16; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));  // context.py:135
-    for (int a = lane; a < t.A; a += 32)
-      t.edges[(size_t)(lslot * uA + a)].pl = __fsub_rn(t.net_logits[ub * uA + a], m);  // legal_action_mask is all True (:137)
-    int term;
-    if (env.kind == EAZ_ENV_DEEPSEA) term = EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot]);
-    else term = t.states[(size_t)lslot * t.S + 35] & EAZ_SQ_FLAG_TERM;
-    const float value = term ? 0.0f : t.net_value[b];  // :140
-    const float var = term ? 0.0f : t.net_ube[b];      // :141
-    float disc = sp.discount;
-    if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
-    if (term) disc = 0.0f;                              // :144
-    const int2 last = t.path[(unsigned)(L - 1) * uB + ub];
-    EdgeRec* pe0 = t.edges + (size_t)(((unsigned)last.x * uB + ub) * uA + (unsigned)last.y);
-    if (lane == 0) {
-      // update_tree_node: the leaf's record (visits + 1: a leaf can be re-expanded under a max_depth cut-off)
-      uint4* ln = reinterpret_cast<uint4*>(t.nodes + lslot);
-      const int old_visits = (int)ln[0].x;
-      ln[0] = make_uint4((unsigned)(old_visits + 1), __float_as_uint(value), __float_as_uint(var), 0u);
-      ln[1] = make_uint4(__float_as_uint(value), __float_as_uint(var), (unsigned)(last.x + 1), (unsigned)(last.y + 1));
-      pe0->ci1 = leaf + 1;
-      pe0->rew = t.reward[b];  // :139
-      pe0->dis = disc;
-    }
-    __syncwarp();
-    if (trc) trc[1] = clock64();
+  tree_step_direct<G, J>(t, sp, env, sim, do_backward, do_select, beta, invalid, b, lane, trc);
+}
 
-    // ------------------------------------------------------------------ 2. backward (levels L-1 .. 0)
-    const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
-    float lv = value, lvar = std_backup ? __fsqrt_rn(var) : var;  // running leaf_value / leaf variance (or std)
-    float below_val = value, below_var = var;                     // updated mean / variance of the node one level deeper
-    for (int hi = L; hi > 0; hi -= 32) {                          // rounds of 32 levels, deepest first
-      const int lo = max(hi - 32, 0), cnt = hi - lo;
-      const int lev = lo + lane;                                  // this lane's level
-      const bool have = lane < cnt;
-      int2 pa = make_int2(0, 0);
-      uint4 nrec = make_uint4(0u, 0u, 0u, 0u);
-      float rr = 0.0f, dd = 0.0f;
-      int cvis = 0;
-      unsigned pslot = 0;
-      EdgeRec* pe = nullptr;
-      if (have) {
-        pa = t.path[(unsigned)lev * uB + ub];
-        pslot = (unsigned)pa.x * uB + ub;
-        pe = t.edges + (size_t)(pslot * uA + (unsigned)pa.y);
-        nrec = reinterpret_cast<const uint4*>(t.nodes + pslot)[0];
-        cvis = pe->vis;
-        rr = pe->rew;
-        dd = pe->dis;
+// ======================================================================================================================
+// Two trees per warp (16 lanes each) for small action counts (G lanes per node, G <= 4): the one-tree kernel keeps a handful
+// of its 32 lanes busy -- the path is a few levels deep and a node has G actions -- and is bound by warp-instruction issue
+// (1 421 warp instructions per tree at C2), so halving the warps nearly halves its cost.  Same STAGED scheme and the same
+// arithmetic as tree_step_kernel; per tree the staging area holds 32 nodes (path + leaf) in rounds of 16 / G.  If either
+// tree of a pair cannot be staged (first launch, path longer than 31, re-expanded leaf, PUCT) both take the DIRECT path,
+// one after the other, with the whole warp.
+template <int G>
+struct Stage2 {
+  static constexpr int kW = 16;                      // lanes per tree
+  static constexpr int kPerRound = kW / G;           // nodes refreshed per round
+  static constexpr int kRounds = 32 / kPerRound;     // 32 nodes (path + leaf) fit
+  static constexpr int kLaneWords = 10;              // ci1, vis, pl, rew, val, vvar, dis, raw, rawvar, prior probability
+  static constexpr int kEdgeWords = kRounds * kLaneWords * kW;  // [round][word][lane of the tree]
+  static constexpr int kBackWords = 4 * 32;          // [node | action << 16, visits -> child value, value -> child variance, variance][level]
+  static constexpr int kRootWords = 2 * kW;          // lanes 0..G-1: gumbel + (logit - max logit), invalid flag
+  static constexpr int kMiscWords = 16;              // [2] leaf terminal, [4] reward, [5] considered visit, [8..8+G) leaf priors
+  static __host__ __device__ constexpr int words(int chase_cap) { return kEdgeWords + kBackWords + kRootWords + kMiscWords + 2 * chase_cap; }
+};
+
+template <int G>
+__global__ void __launch_bounds__(128) tree_step2_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
+                                                          const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid,
+                                                          unsigned long long* tl, long long* trace, int chase_cap) {
+  extern __shared__ __align__(16) uint32_t stage_smem[];
+  unsigned long long t_entry = 0;
+  if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_entry = globaltimer_ns();
+  using SG = Stage2<G>;
+  constexpr int kW = SG::kW, kPR = SG::kPerRound;
+  const int lane = threadIdx.x & 31, hl = lane & (kW - 1), hbase = lane & kW, sub = lane >> 4;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int b = 2 * warp_global + sub;  // 16 lanes per tree
+  const bool in_batch = b < t.B;
+  const unsigned uB = (unsigned)t.B, uA = (unsigned)t.A, ub = (unsigned)(in_batch ? b : 0);
+  const int gl = hl & (G - 1), glev = hl / G;
+  const bool valid1[1] = {gl < t.A};
+  uint32_t* const sw = stage_smem + ((threadIdx.x >> 5) * 2 + sub) * SG::words(chase_cap);
+  uint32_t* const s_edge = sw;
+  uint32_t* const s_back = sw + SG::kEdgeWords;
+  uint32_t* const s_root = s_back + SG::kBackWords;
+  uint32_t* const s_misc = s_root + SG::kRootWords;
+  uint32_t* const s_next = s_misc + SG::kMiscWords;
+  uint32_t* const s_state = s_next + chase_cap;
+
+  // ==================================================================== staging (before the grid-dependency wait)
+  bool staged = false;
+  int L = 0, leaf = 0;
+  if (do_backward && chase_cap > sim + 1 && !(sp.flags & EAZ_FLAG_PUCT)) {  // warp-uniform
+    bool ok = true;
+    if (in_batch) {
+      leaf = t.leaf[b];
+      L = t.path_len[b];
+      ok = L + 1 <= 32 && reinterpret_cast<const uint4*>(t.nodes + ((unsigned)leaf * uB + ub))[0].x == 0u;  // fits, and the leaf is fresh
+    }
+    if (__all_sync(0xffffffffu, ok)) {
+      staged = true;
+      const unsigned lslot = (unsigned)leaf * uB + ub;
+      if (in_batch) {  // backward operands: this lane owns levels hl and hl + 16
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int lev = hl + kW * k;
+          if (lev < L) {
+            const int2 pa = t.path[(unsigned)lev * uB + ub];
+            const uint4 nrec = reinterpret_cast<const uint4*>(t.nodes + ((unsigned)pa.x * uB + ub))[0];
+            s_back[0 * 32 + lev] = (uint32_t)pa.x | ((uint32_t)pa.y << 16);
+            s_back[1 * 32 + lev] = nrec.x;
+            s_back[2 * 32 + lev] = nrec.y;
+            s_back[3 * 32 + lev] = nrec.z;
+          }
+        }
       }
-      // the recurrences: a uniform loop over this round's levels, deepest first, in the reference's op order
-      float my_lv = 0.0f, my_lvar = 0.0f;
-      for (int i = cnt - 1; i >= 0; --i) {
-        const float r = __shfl_sync(0xffffffffu, rr, i), d = __shfl_sync(0xffffffffu, dd, i);
+      __syncwarp();
+      const int Lw = max(L, __shfl_xor_sync(0xffffffffu, L, kW));
+#pragma unroll
+      for (int r = 0; r < SG::kRounds; ++r) {
+        if (r * kPR <= Lw) {  // warp-uniform
+          const int lev = r * kPR + glev;
+          const bool on = in_batch && lev <= L && gl < t.A;
+          uint4 h0 = make_uint4(0u, 0u, 0u, 0u), h1 = h0, n1 = h0;
+          if (on) {
+            const int node = lev < L ? (int)(s_back[lev] & 0xffffu) : leaf;
+            const unsigned slot = (unsigned)node * uB + ub;
+            const uint4* p = reinterpret_cast<const uint4*>(t.edges + (size_t)(slot * uA + (unsigned)gl));
+            h0 = p[0];
+            h1 = p[1];
+            n1 = reinterpret_cast<const uint4*>(t.nodes + slot)[1];
+          }
+          const float xl[1] = {__uint_as_float(h0.z)};
+          float pr[1];
+          group_softmax<G, 1>(xl, valid1, pr);  // p = max(tiny, softmax(prior logits)) of _compute_mixed_value
+          if (on) {
+            uint32_t* se = s_edge + r * SG::kLaneWords * kW + hl;
+            se[0 * kW] = h0.x; se[1 * kW] = h0.y; se[2 * kW] = h0.z; se[3 * kW] = h0.w;
+            se[4 * kW] = h1.x; se[5 * kW] = h1.y; se[6 * kW] = h1.z;
+            se[7 * kW] = n1.x; se[8 * kW] = n1.y;
+            se[9 * kW] = __float_as_uint(eaz_max(EAZ_F32_TINY, pr[0]));
+          }
+          if (r == 0) {  // the root is level 0 of every path: its seq-halving score terms
+            const bool rt = in_batch && glev == 0 && gl < t.A;
+            const float gum = rt ? t.gumbel[ub * uA + gl] : 0.0f;
+            const bool inval = rt && invalid && invalid[ub * uA + gl] != 0;
+            const float m = group_max<G>(gl < t.A ? xl[0] : -INFINITY);
+            const int num_valid = group_sum_i<G>((gl < t.A && !inval) ? 1 : 0);
+            if (rt) {
+              s_root[hl] = __float_as_uint(__fadd_rn(gum, __fsub_rn(xl[0], m)));
+              s_root[kW + hl] = inval ? 1u : 0u;
+            }
+            if (in_batch && hl == 0) s_misc[5] = (uint32_t)t.table[min(sp.max_considered, num_valid) * sp.n + min(sim, sp.n - 1)];
+          }
+        }
+      }
+      if (in_batch && hl == 0) {
+        s_misc[2] = env.kind == EAZ_ENV_DEEPSEA ? (uint32_t)EAZ_DS_TERM(reinterpret_cast<const uint32_t*>(t.states)[lslot])
+                                                 : (uint32_t)(t.states[(size_t)lslot * t.S + 35] & EAZ_SQ_FLAG_TERM);
+        s_misc[4] = __float_as_uint(t.reward[b]);
+      }
+      if (do_select && in_batch) {
+        for (int nd = hl; nd <= sim; nd += kW) {
+          s_next[nd] = (uint32_t)t.nodes[(unsigned)nd * uB + ub].pad0;
+          if (env.kind == EAZ_ENV_DEEPSEA) s_state[nd] = reinterpret_cast<const uint32_t*>(t.states)[(unsigned)nd * uB + ub];
+        }
+      }
+    }
+  }
+  __syncwarp();
+
+  pdl_wait();     // the network kernel of this simulation has finished: its outputs are visible
+  pdl_trigger();  // the next kernel may begin its prologue now
+  unsigned long long t_wait = 0;
+  if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_wait = globaltimer_ns();
+  struct TlExit {
+    unsigned long long *tl, a, b;
+    __device__ ~TlExit() {
+      if (tl && blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long i = atomicAdd(tl, 1ull);
+        if (i < 2000) { tl[8 + 4 * i] = a; tl[9 + 4 * i] = b; tl[10 + 4 * i] = globaltimer_ns(); tl[11 + 4 * i] = 0; }
+      }
+    }
+  } tl_exit{tl, t_entry, t_wait};
+
+  if (!staged) {  // both trees through the DIRECT path, one after the other, with the whole warp
+#pragma unroll 1
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const int bb = 2 * warp_global + s2;
+      if (bb < t.B)
+        tree_step_direct<G, 1>(t, sp, env, sim, do_backward, do_select, beta_in ? beta_in[bb] : 0.0f, invalid, bb, lane,
+                               (trace && lane == 0) ? trace + ((size_t)sim * t.B + bb) * 8 : nullptr);
+      __syncwarp();
+    }
+    return;
+  }
+
+  // ==================================================================== STAGED path, 16 lanes per tree
+  long long* trc = (trace && hl == 0 && in_batch) ? trace + ((size_t)sim * t.B + b) * 8 : nullptr;
+  if (trc) { trc[0] = clock64(); trc[7] = 2; }
+  const float beta = (in_batch && beta_in) ? beta_in[b] : 0.0f;
+  const unsigned lslot = (unsigned)leaf * uB + ub;
+  // ---- 1. expand (lane a of the tree holds action a's logit)
+  const float lg = (in_batch && hl < t.A) ? t.net_logits[ub * uA + hl] : -INFINITY;
+  const float nv = in_batch ? t.net_value[b] : 0.0f, nu = in_batch ? t.net_ube[b] : 0.0f;
+  float m = lg;
+#pragma unroll
+  for (int s = kW / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));  // context.py:135 (within the tree's 16 lanes)
+  const float pl_leaf = __fsub_rn(lg, m);                                                  // legal_action_mask is all True (:137)
+  if (in_batch && hl < t.A) {
+    t.edges[(size_t)(lslot * uA + hl)].pl = pl_leaf;
+    s_misc[8 + hl] = __float_as_uint(pl_leaf);
+  }
+  const int term = in_batch ? (int)s_misc[2] : 0;
+  const float value = term ? 0.0f : nv;  // :140
+  const float var = term ? 0.0f : nu;    // :141
+  float disc = sp.discount;
+  if (sp.two_players) disc = __fmul_rn(disc, -1.0f);  // :142-143
+  if (term) disc = 0.0f;                              // :144
+  const float reward = in_batch ? __uint_as_float(s_misc[4]) : 0.0f;
+  if (in_batch && hl == 0) {
+    const uint32_t last = s_back[L - 1];
+    const int last_node = (int)(last & 0xffffu), last_act = (int)(last >> 16);
+    uint4* ln = reinterpret_cast<uint4*>(t.nodes + lslot);  // update_tree_node: a fresh leaf (staging condition)
+    ln[0] = make_uint4(1u, __float_as_uint(value), __float_as_uint(var), 0u);
+    ln[1] = make_uint4(__float_as_uint(value), __float_as_uint(var), (unsigned)(last_node + 1), (unsigned)(last_act + 1));
+    EdgeRec* pe0 = t.edges + (size_t)(((unsigned)last_node * uB + ub) * uA + (unsigned)last_act);
+    pe0->ci1 = leaf + 1;
+    pe0->rew = reward;  // :139
+    pe0->dis = disc;
+  }
+  if (trc) trc[1] = clock64();
+
+  // ---- 2. backward: rounds of 16 levels, deepest first; lane = level within the round
+  const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
+  float lv = value, lvar = std_backup ? __fsqrt_rn(var) : var;
+  float below_val = value, below_var = var;
+  const int Lw = max(L, __shfl_xor_sync(0xffffffffu, L, kW));
+#pragma unroll 1
+  for (int k = Lw > kW ? 1 : 0; k >= 0; --k) {
+    const int lo = kW * k, cnt = min(max(L - lo, 0), kW);
+    const int lev = lo + hl;
+    const bool have = in_batch && hl < cnt;
+    int my_node = 0, my_act = 0, nvis = 0, cvis = 0;
+    float nval = 0.0f, nvar = 0.0f, rr = 0.0f, dd = 0.0f;
+    if (have) {
+      const uint32_t pa = s_back[lev];
+      my_node = (int)(pa & 0xffffu);
+      my_act = (int)(pa >> 16);
+      nvis = (int)s_back[32 + lev];
+      nval = __uint_as_float(s_back[64 + lev]);
+      nvar = __uint_as_float(s_back[96 + lev]);
+      const uint32_t* se = s_edge + (lev / kPR) * SG::kLaneWords * kW + (lev % kPR) * G + my_act;  // the traversed edge in the refresh staging
+      cvis = (int)se[1 * kW];
+      rr = __uint_as_float(se[3 * kW]);
+      dd = __uint_as_float(se[6 * kW]);
+      if (lev == L - 1) { rr = reward; dd = disc; }  // written by the expand step above
+    }
+    const int cmax = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, kW));
+    float my_lv = 0.0f, my_lvar = 0.0f;
+    for (int i = cmax - 1; i >= 0; --i) {  // the recurrences, in the reference's op order
+      const float r = __shfl_sync(0xffffffffu, rr, hbase + i), d = __shfl_sync(0xffffffffu, dd, hbase + i);
+      if (i < cnt) {
         lv = __fadd_rn(r, __fmul_rn(d, lv));
         lvar = std_backup ? __fadd_rn(0.0f, __fmul_rn(fabsf(d), lvar)) : __fadd_rn(0.0f, __fmul_rn(__fmul_rn(d, d), lvar));
-        if (lane == i) { my_lv = lv; my_lvar = lvar; }
+        if (hl == i) { my_lv = lv; my_lvar = lvar; }
       }
-      // running means, all levels in parallel
-      const int nvis = (int)nrec.x;
-      const float nval = __uint_as_float(nrec.y), nvar = __uint_as_float(nrec.z);
-      const float count = (float)nvis;
-      const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(nval, count), my_lv), __fadd_rn(count, 1.0f));
-      float pvar;
-      if (std_backup) {
-        const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(nvar), count), my_lvar), __fadd_rn(count, 1.0f));
-        pvar = __fmul_rn(ps, ps);
-      } else {
-        pvar = __fdiv_rn(__fadd_rn(__fmul_rn(nvar, count), my_lvar), __fadd_rn(count, 1.0f));
-      }
-      // children_values[parent, a] = the child's CURRENT (already updated) mean: one level deeper
-      float cval = __shfl_down_sync(0xffffffffu, pv, 1), cvarr = __shfl_down_sync(0xffffffffu, pvar, 1);
-      if (lane == cnt - 1) { cval = below_val; cvarr = below_var; }
-      if (have) {
-        reinterpret_cast<uint4*>(t.nodes + pslot)[0] = make_uint4((unsigned)(nvis + 1), __float_as_uint(pv), __float_as_uint(pvar), 0u);
-        pe->vis = cvis + 1;
-        *reinterpret_cast<float2*>(&pe->val) = make_float2(cval, cvarr);
-      }
-      below_val = __shfl_sync(0xffffffffu, pv, 0);
-      below_var = __shfl_sync(0xffffffffu, pvar, 0);
     }
-    __syncwarp();
-    if (trc) { trc[2] = clock64(); trc[6] = L; }
+    const float count = (float)nvis;
+    const float pv = __fdiv_rn(__fadd_rn(__fmul_rn(nval, count), my_lv), __fadd_rn(count, 1.0f));
+    float pvar;
+    if (std_backup) {
+      const float ps = __fdiv_rn(__fadd_rn(__fmul_rn(__fsqrt_rn(nvar), count), my_lvar), __fadd_rn(count, 1.0f));
+      pvar = __fmul_rn(ps, ps);
+    } else {
+      pvar = __fdiv_rn(__fadd_rn(__fmul_rn(nvar, count), my_lvar), __fadd_rn(count, 1.0f));
+    }
+    // children_values[parent, a] = the child's CURRENT (already updated) mean: one level deeper
+    float cval = __shfl_down_sync(0xffffffffu, pv, 1, kW), cvarr = __shfl_down_sync(0xffffffffu, pvar, 1, kW);
+    if (hl == cnt - 1) { cval = below_val; cvarr = below_var; }
+    if (have) {
+      const unsigned pslot = (unsigned)my_node * uB + ub;
+      EdgeRec* pe = t.edges + (size_t)(pslot * uA + (unsigned)my_act);
+      reinterpret_cast<uint4*>(t.nodes + pslot)[0] = make_uint4((unsigned)(nvis + 1), __float_as_uint(pv), __float_as_uint(pvar), 0u);
+      pe->vis = cvis + 1;
+      *reinterpret_cast<float2*>(&pe->val) = make_float2(cval, cvarr);
+      s_back[32 + lev] = __float_as_uint(cval);  // for the refresh below: the traversed edge's new child value / variance
+      s_back[64 + lev] = __float_as_uint(cvarr);
+    }
+    const float b0v = __shfl_sync(0xffffffffu, pv, hbase), b0r = __shfl_sync(0xffffffffu, pvar, hbase);
+    if (cnt > 0) { below_val = b0v; below_var = b0r; }
   }
+  __syncwarp();
+  if (trc) { trc[2] = clock64(); trc[6] = L; }
   if (!do_select) return;
 
-  // -------------------------------------------------------------------- 3. refresh the cached selections
-  // nodes: path levels 0..L-1 and the new leaf (index L); before the first simulation only the root.
+  // ---- 3. refresh the cached selections of the path nodes and the leaf: staged records + this backward's updates
   {
-    const int nrefresh = do_backward ? L + 1 : 1;
-    for (int base = 0; base < nrefresh; base += kLevelsPerRound) {
-      const int lev = base + glev;
-      const bool act_on = lev < nrefresh;
-      int node = 0;
-      if (act_on && do_backward) node = lev < L ? t.path[(unsigned)lev * uB + ub].x : leaf;
-      const unsigned slot = (unsigned)node * uB + ub;
-      Edge<G, J> e;
-      float raw, raw_var;
-      load_edges<G, J>(t, slot, gl, act_on, e);
-      load_node_raw(t, slot, act_on, raw, raw_var);
-      int child, act;
-      if (sp.flags & EAZ_FLAG_PUCT) {  // muzero_action_selection at every depth (warp-uniform switch)
-        const bool is_root = act_on && node == 0;
-        uint4 h0 = make_uint4(0u, 0u, 0u, 0u);
-        if (act_on) h0 = reinterpret_cast<const uint4*>(t.nodes + slot)[0];  // node_visits, node value, node variance
-        bool inval[J];
-#pragma unroll
-        for (int j = 0; j < J; ++j) inval[j] = (is_root && valid[j] && invalid) ? (invalid[ub * uA + gl + G * j] != 0) : false;
-        act = puct_select<G, J>(sp, e, valid, (int)h0.x, __uint_as_float(h0.y), __uint_as_float(h0.z), beta,
-                                is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0, ub, (unsigned)node, inval, gl);
-        int ci_sel = -1;
-#pragma unroll
-        for (int j = 0; j < J; ++j)
-          if (j == act / G) ci_sel = e.ci[j];
-        child = __shfl_sync(0xffffffffu, ci_sel, (lane & ~(G - 1)) + (act & (G - 1)));
-      } else {
-        act = select_action<G, J>(t, sp, e, valid, raw, raw_var, beta, act_on && node == 0, ub, uA, invalid, lane, gl, &child);
+    const int rounds = in_batch ? (L + kPR) / kPR : 0;  // ceil((L + 1) / kPR)
+    const int rmax = max(rounds, __shfl_xor_sync(0xffffffffu, rounds, kW));
+#pragma unroll 1
+    for (int r = 0; r < rmax; ++r) {
+      const int lev = r * kPR + glev;
+      const bool act_on = in_batch && lev <= L;
+      int node = 0, act_l = 0;
+      float cval_l = 0.0f, cvar_l = 0.0f;
+      if (act_on && lev < L) {
+        const uint32_t pa = s_back[lev];
+        node = (int)(pa & 0xffffu);
+        act_l = (int)(pa >> 16);
+        cval_l = __uint_as_float(s_back[32 + lev]);
+        cvar_l = __uint_as_float(s_back[64 + lev]);
+      } else if (act_on) {
+        node = leaf;
       }
-      if (act_on && gl == 0) t.nodes[slot].pad0 = pack_next(act, child);
+      Edge<G, 1> e;
+      e.ci[0] = -1; e.vis[0] = 0;
+      e.pl[0] = 0.0f; e.rew[0] = 0.0f; e.dis[0] = 0.0f; e.val[0] = 0.0f; e.vvar[0] = 0.0f;
+      float raw = 0.0f, raw_var = 0.0f, prior_p = 0.0f;
+      if (act_on) {
+        const uint32_t* sg0 = s_edge + r * SG::kLaneWords * kW + (hl & ~(G - 1));  // the group's action-0 lane always holds raw / raw variance
+        raw = __uint_as_float(sg0[7 * kW]);
+        raw_var = __uint_as_float(sg0[8 * kW]);
+        if (lev == L) { raw = value; raw_var = var; }  // the leaf: fresh raw values
+        if (gl < t.A) {
+          const uint32_t* se = s_edge + r * SG::kLaneWords * kW + hl;
+          e.ci[0] = (int)se[0] - 1;
+          e.vis[0] = (int)se[1 * kW];
+          e.pl[0] = __uint_as_float(se[2 * kW]);
+          e.rew[0] = __uint_as_float(se[3 * kW]);
+          e.val[0] = __uint_as_float(se[4 * kW]);
+          e.vvar[0] = __uint_as_float(se[5 * kW]);
+          e.dis[0] = __uint_as_float(se[6 * kW]);
+          prior_p = __uint_as_float(se[9 * kW]);  // (unused for the fresh leaf: none of its children has visits)
+          if (lev == L) {
+            e.pl[0] = __uint_as_float(s_misc[8 + gl]);  // fresh priors
+          } else if (gl == act_l) {  // the edge this simulation went through
+            e.vis[0] += 1;
+            e.val[0] = cval_l;
+            e.vvar[0] = cvar_l;
+            if (lev == L - 1) { e.ci[0] = leaf; e.rew[0] = reward; e.dis[0] = disc; }
+          }
+        }
+      }
+      const bool is_root = act_on && node == 0;
+      float g2 = 0.0f;
+      bool inval = false;
+      int considered_visit = 0;
+      if (r == 0 && is_root && gl < t.A) {
+        g2 = __uint_as_float(s_root[hl]);
+        inval = s_root[kW + hl] != 0u;
+        considered_visit = (int)s_misc[5];
+      }
+      int child;
+      const int act = select_action_staged<G>(sp, e, valid1[0], raw, raw_var, prior_p, beta, is_root, g2, inval, considered_visit, lane, gl, &child);
+      if (act_on && gl == 0) {
+        const int packed = pack_next(act, child);
+        t.nodes[(unsigned)node * uB + ub].pad0 = packed;
+        s_next[node] = (uint32_t)packed;
+      }
     }
-    __syncwarp();
-    if (trc) trc[3] = clock64();
   }
+  __syncwarp();
+  if (trc) trc[3] = clock64();
 
-  // -------------------------------------------------------------------- 4. simulate: follow the cached selections
-  // Nodes 0..sim exist.  For trees of up to 32*kChaseSlots nodes every cached (action, child) word is fetched once
-  // (independent loads, lane i holds nodes i, i+32, ...) and the chase itself runs over registers with warp
-  // shuffles; larger trees chase through memory, one dependent 16-byte load per level.
-  constexpr int kChaseSlots = 9;
+  // ---- 4. simulate: follow the cached selections through the staged copy (each tree until its own descent ends)
   int node = 0, depth = 0, action = 0, child = -1;
-  if (sim < 32 * kChaseSlots) {
-    int nxw[kChaseSlots];
-#pragma unroll
-    for (int s = 0; s < kChaseSlots; ++s) {
-      const int nd = lane + 32 * s;
-      nxw[s] = (32 * s <= sim && nd <= sim) ? t.nodes[(unsigned)nd * uB + ub].pad0 : 0;
-    }
-    while (true) {
-      const int slot = node >> 5;
-      int v = 0;
-#pragma unroll
-      for (int s = 0; s < kChaseSlots; ++s)
-        if (s == slot) v = nxw[s];
-      const int nx = __shfl_sync(0xffffffffu, v, node & 31);
+  bool active = in_batch;
+  while (__any_sync(0xffffffffu, active)) {
+    if (active) {
+      const int nx = (int)s_next[node];
       action = nx & 0xff;
       child = (nx >> 8) - 1;
-      if (lane == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
+      if (hl == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
       depth += 1;
-      if (child < 0 || depth >= sp.max_depth) break;
-      node = child;
-    }
-  } else {
-    while (true) {
-      const int nx = t.nodes[(unsigned)node * uB + ub].pad0;
-      action = nx & 0xff;
-      child = (nx >> 8) - 1;
-      if (lane == 0) t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
-      depth += 1;
-      if (child < 0 || depth >= sp.max_depth) break;
-      node = child;
+      if (child < 0 || depth >= sp.max_depth) active = false;
+      else node = child;
     }
   }
   if (trc) { trc[4] = clock64(); trc[5] = depth; }
-  if (lane == 0) {
+  if (in_batch && hl == 0) {
     const int new_leaf = child < 0 ? sim + 1 : child;  // search.py: node first expanded on simulation i gets index i+1
     t.path_len[b] = depth;
     t.parent[b] = node;
@@ -647,10 +1014,10 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
     t.leaf[b] = new_leaf;
     if (env.kind == EAZ_ENV_DEEPSEA) {  // context.py:127 env.step fused here
       uint32_t* st = reinterpret_cast<uint32_t*>(t.states);
-      float reward;
-      const uint32_t ns = deepsea_step(st[(unsigned)node * uB + ub], action, env.size, env.action_map, &reward);
+      float rw;
+      const uint32_t ns = deepsea_step(s_state[node], action, env.size, env.action_map, &rw);
       st[(unsigned)new_leaf * uB + ub] = ns;
-      t.reward[b] = reward;
+      t.reward[b] = rw;
       t.cell[b] = deepsea_obs_index(ns, env.size);
     }
   }

@@ -579,3 +579,26 @@ def test_search_rejects_bad_arguments(ops):
         ops.search(_abi.default_search_config(batch=8, num_simulations=0), denv, dnet, root)
     with pytest.raises(EazError):
         ops.search(_abi.default_search_config(batch=8, num_simulations=8, max_num_considered_actions=0), denv, dnet, root)
+
+
+@pytest.mark.parametrize("B,mode,streams", [(6201, _abi.MLP_EXACT, 1), (6400, _abi.MLP_TENSOR, 3)])
+def test_search_many_trees_two_per_warp(ops, B, mode, streams):
+    """Batches of >= 6144 trees switch the DeepSea tree kernel to two trees per warp (tree_step2_kernel): same trees, bit for bit
+    (odd batch: the last warp holds one tree)."""
+    env = H.make_env("deepsea", seed=81, size=10)
+    net = H.make_net(env, seed=82, fill=0.5)
+    n = 24
+    root = H.make_root(env, net, B, seed=83, beta_max=1.0, invalid_frac=0.1)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(batch=B, num_simulations=n, discount=0.997, mlp_mode=mode)
+    if streams > 1:
+        cfg.flags |= _abi.flag_streams(streams)
+    got = {k: host(v) for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
+    ocfg = _abi.default_search_config(num_simulations=n, discount=0.997)
+    if mode == _abi.MLP_EXACT:
+        exp = O.search(ocfg, env, net, root, want_tree=True)
+    else:
+        replay = dict(states=got["embeddings"], logits=got["children_prior_logits"], value=got["raw_values"], var=got["raw_values_epistemic_variance"])
+        exp = O.search(ocfg, env, None, root, want_tree=True, replay=replay)
+        assert exp["replay_misses"] == 0
+    assert_tree_equal(exp, got)
