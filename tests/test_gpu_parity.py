@@ -581,8 +581,8 @@ def test_search_rejects_bad_arguments(ops):
         ops.search(_abi.default_search_config(batch=8, num_simulations=8, max_num_considered_actions=0), denv, dnet, root)
 
 
-@pytest.mark.parametrize("B,mode,streams", [(6201, _abi.MLP_EXACT, 1), (6400, _abi.MLP_TENSOR, 3)])
-def test_search_many_trees_two_per_warp(ops, B, mode, streams):
+@pytest.mark.parametrize("B,mode,streams,puct", [(6201, _abi.MLP_EXACT, 1, False), (6400, _abi.MLP_TENSOR, 3, False), (6150, _abi.MLP_EXACT, 1, True)])
+def test_search_many_trees_two_per_warp(ops, B, mode, streams, puct):
     """Batches of >= 6144 trees switch the DeepSea tree kernel to two trees per warp (tree_step2_kernel): same trees, bit for bit
     (odd batch: the last warp holds one tree)."""
     env = H.make_env("deepsea", seed=81, size=10)
@@ -593,8 +593,11 @@ def test_search_many_trees_two_per_warp(ops, B, mode, streams):
     cfg = _abi.default_search_config(batch=B, num_simulations=n, discount=0.997, mlp_mode=mode)
     if streams > 1:
         cfg.flags |= _abi.flag_streams(streams)
-    got = {k: host(v) for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
     ocfg = _abi.default_search_config(num_simulations=n, discount=0.997)
+    if puct:  # PUCT selection is not staged: both trees of a warp take the DIRECT path
+        cfg.flags |= _abi.FLAG_PUCT
+        ocfg.flags |= _abi.FLAG_PUCT
+    got = {k: host(v) for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
     if mode == _abi.MLP_EXACT:
         exp = O.search(ocfg, env, net, root, want_tree=True)
     else:
