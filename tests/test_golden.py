@@ -236,3 +236,78 @@ def test_puct_oracle_tree_invariants(kind, kw):
     inv = root["invalid_actions"].astype(bool)
     some_valid = ~inv.all(1)  # (all actions invalid: masked_argmax falls back to action 0, like mctx)
     assert (out["visit_counts"][some_valid][inv[some_valid]] == 0).all()  # invalid root actions are never selected
+
+
+def test_seq_halving_schedules_known_answers():
+    """considered-visit schedules of mctx seq_halving.get_sequence_of_considered_visits."""
+    t = O.seq_halving_table(16, 32)
+    assert t[16].tolist() == [0] * 16 + [1] * 8 + [2] * 4 + [3] * 4
+    assert t[2].tolist() == [v for v in range(16) for _ in range(2)] and t[2].sum() == 240
+    assert t[1].tolist() == list(range(32)) and t[0].tolist() == list(range(32))
+    t = O.seq_halving_table(16, 64)
+    assert t[16].tolist()[:48] == [0] * 16 + [1] * 8 + [2] * 8 + [3] * 4 + [4] * 4 + [5] * 4 + [6] * 4 and t[16].sum() == 264 and t[2].sum() == 992
+    t = O.seq_halving_table(16, 128)
+    assert t[16].sum() == 1120 and t[16].max() == 29 and t[2].sum() == 4032
+    t = O.seq_halving_table(16, 256)
+    assert t[16].sum() == 4608 and t[16].max() == 59
+
+
+def test_subleq_known_answers():
+    """Subleq ws=16 NEGATION_POSITIVE: empty program spins 200 cycles, [14] errors after one cycle, [14, 13]
+    (`subleq OUT IN 0`) solves the task; reward on the solving step, termination (with zero reward) one step later."""
+    env = O.Env.subleq(16, True)
+    st = O.env_init(env, 1, np.array([1], np.int32))
+    assert not st["solved"][0] and st["step_count"][0] == 0
+    st = O.env_step(env, st, np.array([14], np.int32))
+    assert st["rewards"][0, 0] == 0 and not st["solved"][0] and st["output_after"][0].tolist()[:2] == [2, 16]
+    st = O.env_step(env, st, np.array([13], np.int32))
+    assert st["rewards"][0, 0] == 1 and st["solved"][0] and not st["terminated"][0]
+    assert st["output_after"][0].tolist() == [15, 14, 13, 12, 11, 10, 9, 16] and st["input_after"][0].tolist() == [16] * 8
+    st = O.env_step(env, st, np.array([0], np.int32))
+    assert st["terminated"][0] and st["rewards"][0, 0] == 0
+    st2 = O.env_step(env, O.copy_state(st), np.array([5], np.int32))  # absorbing: same state, zero reward
+    assert st2["terminated"][0] and st2["rewards"][0, 0] == 0 and (st2["memory"] == st["memory"]).all()
+
+
+try:
+    from hypothesis import given, settings, strategies as hst
+
+    @settings(max_examples=12, deadline=None)
+    @given(kind=hst.sampled_from(["deepsea", "subleq"]), n=hst.integers(1, 40), seed=hst.integers(0, 1000), max_depth=hst.sampled_from([0, 0, 3, 7]),
+           rescale=hst.booleans(), gscale=hst.sampled_from([0.0, 1.0]), considered=hst.sampled_from([1, 2, 4, 16]))
+    def test_gumbel_oracle_tree_invariants(kind, n, seed, max_depth, rescale, gscale, considered):
+        """Property test: mctx tree invariants hold for the oracle search under random configurations."""
+        from e_alphazero_b200 import _abi
+        from tests import helpers as H
+
+        env = H.make_env(kind, seed=seed, **(dict(size=6) if kind == "deepsea" else dict(word_size=16)))
+        net = H.make_net(env, seed=seed + 1, fill=0.5)
+        B = 6
+        root = H.make_root(env, net, B, seed=seed + 2, beta_max=1.0, invalid_frac=0.25)
+        cfg = _abi.default_search_config(num_simulations=n, discount=0.97, max_depth=max_depth, rescale_values=int(rescale), gumbel_scale=gscale,
+                                         max_num_considered_actions=considered)
+        out = O.search(cfg, env, net, root, want_tree=True)
+        nv, cv, ci, par, afp = out["node_visits"], out["children_visits"], out["children_index"], out["parents"], out["action_from_parent"]
+        assert (out["visit_counts"].sum(1) == n).all() and (nv[:, 0] == n + 1).all()
+        assert (par[:, 0] == -1).all() and (afp[:, 0] == -1).all()
+        for b in range(B):
+            live = np.flatnonzero(nv[b] > 0)
+            if max_depth == 0:
+                assert live.tolist() == list(range(len(live)))                   # node i is first expanded by simulation i - 1
+            # (under a max_depth cut-off a simulation re-expands an existing node and its slot sim + 1 stays empty, as in mctx)
+            for i in live[1:]:
+                assert 0 <= par[b, i] < i and ci[b, par[b, i], afp[b, i]] == i   # node i was expanded from an older node
+            for i in live:
+                kids = ci[b, i][ci[b, i] >= 0]
+                assert len(set(kids.tolist())) == len(kids)
+                if max_depth == 0:
+                    assert nv[b, i] == 1 + cv[b, i].sum()                        # node_visits[parent] = 1 + sum(children_visits)
+        inv = root["invalid_actions"].astype(bool)
+        some_valid = ~inv.all(1)
+        assert (out["visit_counts"][some_valid][inv[some_valid]] == 0).all()
+        assert not inv[some_valid][np.arange(some_valid.sum()), out["action"][some_valid]].any()
+        np.testing.assert_allclose(out["action_weights"].sum(1), 1.0, rtol=1e-5)
+        again = O.search(cfg, env, net, root, want_tree=True)                     # deterministic
+        assert all((again[k] == out[k]).all() for k in ("action", "children_index", "node_visits"))
+except ImportError:  # pragma: no cover
+    pass
