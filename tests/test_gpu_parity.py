@@ -605,3 +605,48 @@ def test_search_many_trees_two_per_warp(ops, B, mode, streams, puct):
         exp = O.search(ocfg, env, None, root, want_tree=True, replay=replay)
         assert exp["replay_misses"] == 0
     assert_tree_equal(exp, got)
+
+
+# ----------------------------------------------------------------------------- BASELINE full sizes: size-independent properties
+@pytest.mark.parametrize("wl", ["c2", "c3"])
+def test_full_size_properties(ops, wl):
+    """BASELINE configs C2 (DeepSea-30, 4096 envs, 64 simulations) and C3 (Subleq-16, 8192 envs, 64 simulations) at full size, tensor-core
+    network, concurrent sub-batches: mctx tree invariants over every tree, and bit-exact oracle replay of a sample of the trees."""
+    import torch
+
+    import bench
+
+    kind, kw, B, n, gamma, _ = bench.WORKLOADS[wl]
+    envp, netp = bench.synth_params(kind, kw, 0)
+    if kind == "deepsea":
+        env = O.Env.deepsea(envp["size"], envp["action_map"])
+    else:
+        env = O.Env.subleq(envp["word_size"], True)
+    net = O.FcNet(netp["in_dim"], 256, netp["num_actions"], netp["w"], netp["b"], netp["binary_set"], 24, netp["hash_io"], netp["word_size"])
+    st = H.random_states(env, B, seed=5)
+    root = H.make_root(env, net, B, seed=6, beta_max=1.0, states=st)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(batch=B, num_simulations=n, discount=gamma, exploration=1, mlp_mode=_abi.MLP_TENSOR)
+    cfg.flags |= _abi.flag_streams(3)
+    got = {k: host(v) for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
+    nv, cv, ci, par, afp = got["node_visits"], got["children_visits"], got["children_index"], got["parents"], got["action_from_parent"]
+    A = env.num_actions
+    assert (got["visit_counts"].sum(1) == n).all() and (nv[:, 0] == n + 1).all() and (nv[:, 1:] >= 1).all()
+    assert (nv == 1 + cv.sum(2)).all()                                             # node_visits[parent] = 1 + sum(children_visits)
+    idx = np.arange(1, n + 1)
+    assert (par[:, 1:] < idx).all() and (par[:, 1:] >= 0).all()                      # node i hangs under an older node
+    bb = np.repeat(np.arange(B), n)
+    assert (ci[bb, par[:, 1:].reshape(-1), afp[:, 1:].reshape(-1)] == np.tile(idx, B)).all()  # children_index[parent, action] = child
+    assert ((ci >= 0).sum((1, 2)) == n).all()                                        # exactly n edges are expanded
+    assert (got["action"] >= 0).all() and (got["action"] < A).all()
+    np.testing.assert_allclose(got["action_weights"].sum(1), 1.0, rtol=1e-5)
+    assert np.isfinite(got["qvalues"]).all() and (got["qvalues_epistemic_variance"] >= 0).all()
+    # oracle replay (the GPU's own per-node network outputs) on a sample of the trees: bit for bit
+    pick = np.random.default_rng(7).choice(B, 48, replace=False)
+    sub_root = {k: (v[pick] if k != "embedding" else {kk: vv[pick] for kk, vv in v.items()}) for k, v in root.items()}
+    replay = dict(states=got["embeddings"][pick], logits=got["children_prior_logits"][pick], value=got["raw_values"][pick],
+                  var=got["raw_values_epistemic_variance"][pick])
+    exp = O.search(_abi.default_search_config(num_simulations=n, discount=gamma, exploration=1), env, None, sub_root, want_tree=True, replay=replay)
+    assert exp["replay_misses"] == 0
+    for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
+        H.assert_same_bits(got[name][pick], exp[name], name)
