@@ -650,3 +650,28 @@ def test_full_size_properties(ops, wl):
     assert exp["replay_misses"] == 0
     for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
         H.assert_same_bits(got[name][pick], exp[name], name)
+
+
+@pytest.mark.parametrize("kind,kw,steps", [("deepsea", dict(size=6), 10), ("subleq", dict(word_size=16), 6)])
+def test_evaluate_mirror(ops, kind, kw, steps):
+    """evaluate.py:13-57: greedy episodes with gumbel_scale = 0 -- device loop == the same loop on the oracle (EXACT network)."""
+    from e_alphazero_b200.evaluate import evaluate
+
+    env = H.make_env(kind, seed=91, **kw)
+    net = H.make_net(env, seed=92, fill=0.5)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    B, n, gamma = 24, 12, 0.97
+    mean, total = evaluate(dnet, denv, B, n, gamma, max_episode_length=steps, exploitation_beta=0.3)
+    st = O.env_init(env, B, np.ones(B, np.int32))
+    tot = np.zeros(B, np.float32)
+    counter = 0
+    while not st["terminated"].all() and counter <= steps:
+        ev = O.mlp_forward_states(net, env, st)
+        root = dict(prior_logits=ev["exploit_logits"], value=ev["value"], value_epistemic_variance=ev["ube"], beta=np.full(B, 0.3, np.float32),
+                    embedding=st, gumbel=np.zeros((B, env.num_actions), np.float32))
+        out = O.search(_abi.default_search_config(num_simulations=n, discount=gamma, gumbel_scale=0.0), env, net, root, want_tree=False)
+        st = O.env_step(env, st, out["action"])
+        tot += st["rewards"][:, 0]
+        counter += 1
+    H.assert_same_bits(host(total), tot, "sum_of_rewards")
+    assert abs(float(mean) - tot.mean()) < 1e-6
