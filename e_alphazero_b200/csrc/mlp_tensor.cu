@@ -50,6 +50,7 @@ struct TensorSmem {
   alignas(16) float bias_s[2][kH];  // b1, b2 pre-multiplied by kActScale: relu(acc*un + b) * S == relu(fma(acc, un*S, b*S)) exactly (S = 2^k)
   alignas(16) float w3[kH][kSimtOutMax];    // layer-3 weights of narrow heads
   alignas(16) float part[kTM][kSimtOutMax];  // partial dot products of producer group 1
+  alignas(16) int16_t example[6][16];        // Subleq: example input [0..8) / example output [8..16) words per task row (test case 0)
 };
 constexpr size_t kTensorSmemFixed = (size_t)kStages * (kAStage + kBStageMax) + sizeof(TensorSmem) + 128;
 
@@ -60,6 +61,16 @@ __device__ __forceinline__ int sq_word_g(const uint8_t* st, int row, int ws, int
   if (part == 0) return sq_test_in(trow, 0, i, ws);
   if (part == 1) return h[i];
   if (part == 2) return sq_test_out(trow, 0, i, ws);
+  return h[8 + i];
+}
+// same, with the example input / output rows taken from the per-CTA table (they cost a runtime modulo each otherwise)
+__device__ __forceinline__ int sq_word_t(const uint8_t* st, int row, int ws, const int16_t* example) {
+  if (row < ws) return st[EAZ_SQ_HDR + row];
+  const int r = row - ws, part = r >> 3, i = r & 7;
+  const uint16_t* h = reinterpret_cast<const uint16_t*>(st);
+  if (part == 0) return example[i];
+  if (part == 1) return h[i];
+  if (part == 2) return example[8 + i];
   return h[8 + i];
 }
 __device__ __forceinline__ int sq_bit_g(int v, int c, int w, int ws, int binary) {
@@ -161,6 +172,10 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
     sh->bias[2][j] = b2;
     if (simt3) *reinterpret_cast<float4*>(sh->w3[j]) = make_float4(w[0], w[1], w[2], w[3]);
   }
+  if (env.kind == EAZ_ENV_SUBLEQ && threadIdx.x < 96) {  // example rows of Subleq._observe (subleq.py:698-704) for the 6 task rows
+    const int tr6 = threadIdx.x >> 4, idx = threadIdx.x & 15;
+    sh->example[tr6][idx] = (int16_t)(idx < 8 ? sq_test_in(tr6, 0, idx, env.ws) : sq_test_out(tr6, 0, idx - 8, env.ws));
+  }
   if (warp == 8) {
     tmem_alloc(&sh->tmem_base, 512);
     tmem_relinquish();
@@ -253,13 +268,56 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
     __syncwarp();
   } else {
     // ================= worker warps: A producer (thread == row) + epilogue =================
+    // Stage this thread's compact state record in shared memory first (the A stages are still unused): the observation
+    // builders below read it byte by byte, and from global memory every one of those ~50 dependent byte loads cost an L2
+    // round trip (16.7k of the kernel's 47.7k cycles at C3, profiles/trace_mlp_tensor.py).  Vector loads, issued together.
+    bool state_staged = false;
+    if (cached_bits && st && env.kind == EAZ_ENV_SUBLEQ && env.compact_bytes <= 64) {
+      uint2 piece[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) piece[i] = 8 * i < env.compact_bytes ? __ldg(reinterpret_cast<const uint2*>(st) + i) : make_uint2(0u, 0u);
+      uint8_t* slot = sA + (size_t)threadIdx.x * 64;  // 256 worker threads x 64 B inside A stage 0
+#pragma unroll
+      for (int i = 0; i < 8; ++i) reinterpret_cast<uint2*>(slot)[i] = piece[i];
+      st = slot;
+      trow = sq_task_row(st[34]);
+      state_staged = true;
+    }
+    if (tr && threadIdx.x == 0) trace[6] = clock64();
     if (cached_bits) {  // this row's whole observation as a bit-string in shared memory (Subleq._observe, subleq.py:679-707)
       const int w = env.obs_cols, ws = env.ws;
-      if (st && env.binary) {  // words are in [0, ws] for any reachable state: v % ws == (v == ws ? 0 : v), no division
+      if (state_staged && env.binary && ws == 16 && w == 5) {
+        // subleq-16 (the reference's own experiment size): 48 rows x 5 bits, and for v in [0, 16] the 5-bit pattern of
+        // subleq.py:88-97 IS v (low 4 bits, or bit 4 for the pad value 16) -- a straight-line pack of 48 fields, no branches
+        unsigned long long acc[4] = {0ull, 0ull, 0ull, 0ull};
+        const uint4 h0 = *reinterpret_cast<const uint4*>(st), h1 = *reinterpret_cast<const uint4*>(st + 16);   // in_after, out_after (u16 x 8 each)
+        const uint2 m0 = *reinterpret_cast<const uint2*>(st + EAZ_SQ_HDR), m1 = *reinterpret_cast<const uint2*>(st + EAZ_SQ_HDR + 8);  // memory bytes 0..15
+        const uint4 mw = make_uint4(m0.x, m0.y, m1.x, m1.y);
+        const uint4 e0 = *reinterpret_cast<const uint4*>(sh->example[trow]), e1 = *reinterpret_cast<const uint4*>(sh->example[trow] + 8);
+        const uint32_t mem4[4] = {mw.x, mw.y, mw.z, mw.w}, in4[4] = {h0.x, h0.y, h0.z, h0.w}, out4[4] = {h1.x, h1.y, h1.z, h1.w};
+        const uint32_t ei4[4] = {e0.x, e0.y, e0.z, e0.w}, eo4[4] = {e1.x, e1.y, e1.z, e1.w};
+#pragma unroll
+        for (int r = 0; r < 48; ++r) {
+          uint32_t v;
+          if (r < 16) v = (mem4[r >> 2] >> (8 * (r & 3))) & 0xffu;
+          else {
+            const int i = (r - 16) & 7, part = (r - 16) >> 3;
+            const uint32_t word = part == 0 ? ei4[i >> 1] : part == 1 ? in4[i >> 1] : part == 2 ? eo4[i >> 1] : out4[i >> 1];
+            v = (word >> (16 * (i & 1))) & 0xffffu;
+          }
+          const int bit = 5 * r, q = bit >> 6, lo = bit & 63;
+          acc[q] |= (unsigned long long)(v & 0x1fu) << lo;
+          if (lo > 59) acc[q + 1] |= (unsigned long long)(v & 0x1fu) >> (64 - lo);
+        }
+#pragma unroll
+        for (int wd = 0; wd < 8; ++wd)
+          if (wd < bits_words) sbits[wd * kTM + row] = live ? (uint32_t)(acc[wd >> 1] >> (32 * (wd & 1))) : 0u;
+        for (int wd = 8; wd < bits_words; ++wd) sbits[wd * kTM + row] = 0u;
+      } else if (st && env.binary) {  // words are in [0, ws] for any reachable state: v % ws == (v == ws ? 0 : v), no division
         unsigned long long acc = 0ull;
         int fill = 0, wd = 0;
         for (int orow = 0; orow < ws + 32; ++orow) {
-          const int v = sq_word_g(st, orow, ws, trow);
+          const int v = sq_word_t(st, orow, ws, sh->example[trow]);
           const unsigned pat = (v == ws) ? (1u << (w - 1)) : ((unsigned)v & 0xffu);  // subleq.py:88-97
           if (live) acc |= (unsigned long long)pat << fill;
           fill += w;
@@ -278,7 +336,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         for (int wd = 0; wd < bits_words; ++wd) sbits[wd * kTM + row] = 0u;
         if (live && st) {  // one-hot rows (subleq.py:51-55)
           for (int orow = 0, pos = 0; orow < ws + 32; ++orow, pos += w) {
-            const int v = sq_word_g(st, orow, ws, trow);
+            const int v = sq_word_t(st, orow, ws, sh->example[trow]);
             const int k = pos + (v == ws ? ws : floormod(v, ws));
             sbits[(k >> 5) * kTM + row] |= 1u << (k & 31);
           }
@@ -289,6 +347,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         }
       }
     }
+    if (tr && threadIdx.x == 0) trace[7] = clock64();
+    if (state_staged) asm volatile("bar.sync 1, 256;" ::: "memory");  // every worker is done with its staged record: A stage 0 may be overwritten
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int grp = warp >> 2;  // two producer groups: group g produces chunks t with t % 2 == g
     bool waited[2] = {false, false};
