@@ -349,6 +349,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
     }
     if (tr && threadIdx.x == 0) trace[7] = clock64();
     if (state_staged) asm volatile("bar.sync 1, 256;" ::: "memory");  // every worker is done with its staged record: A stage 0 may be overwritten
+    if (tr && threadIdx.x == 0) trace[776] = clock64();
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int grp = warp >> 2;  // two producer groups: group g produces chunks t with t % 2 == g
     bool waited[2] = {false, false};
@@ -425,6 +426,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         }
       }
       warp_wait(&sh->empty[s], ph ^ 1);
+      if (tr && threadIdx.x == 0 && t < 2) trace[778 + t] = clock64();
       store_a_chunk(sA + s * kAStage, row, v, layer != 0);
       fence_proxy_async();
       __syncwarp();
@@ -438,11 +440,40 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       if (layer == 0 || (layer == 1 && gather)) return true;
       return waited[layer - 1];
     };
+    // Layer-1 chunks of cached observation bit-strings go straight from the 32-bit word to fp16 operand pieces (1.0 = 0x3C00, two
+    // bits per 32-bit word: 0x3C00 * bit0 + 0x3C000000 * bit1); no lo tile (0 / 1 are exact in fp16, the MMA warp skips that product)
+    auto bits_chunk = [&](int t) { return cached_bits && t < n1; };
+    auto store_bits = [&](int t) {
+      const int s = t % kStages, ph = (t / kStages) & 1;
+      const uint32_t wd = live ? sbits[((t * kCK) >> 5) * kTM + row] : 0u;
+      warp_wait(&sh->empty[s], ph ^ 1);
+      uint8_t* stage = sA + s * kAStage;
+#pragma unroll
+      for (int q = 0; q < kCK / 8; ++q) {
+        uint32_t h[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t two = (wd >> (8 * q + 2 * i)) & 3u;
+          h[i] = (two & 1u) * 0x3C00u + (two >> 1) * 0x3C000000u;
+        }
+        *reinterpret_cast<uint4*>(stage + tile_offset_h32(row, q * 8)) = make_uint4(h[0], h[1], h[2], h[3]);
+      }
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->full_a[s]);
+      if (tr && (threadIdx.x & 127) == 0) trace[264 + t] = clock64();
+    };
     uint32_t cur[kCK], nxt[kCK];
     int t = grp;
-    if (t < total) load_raw(t, cur);
+    if (t < total && !bits_chunk(t)) load_raw(t, cur);
+    if (tr && threadIdx.x == 0) trace[777] = clock64();
     for (; t < total; t += 2) {
       const int tn = t + 2;
+      if (bits_chunk(t)) {
+        store_bits(t);
+        if (tn < total && !bits_chunk(tn)) load_raw(tn, cur);
+        continue;
+      }
       const bool pre = tn < total && can_prefetch(tn);
       if (pre) load_raw(tn, nxt);
       finish_store(t, cur);

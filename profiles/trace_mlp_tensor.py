@@ -29,7 +29,7 @@ torch.cuda.synchronize()
 lib.eaz_debug_set_mlp_trace(None)
 t = buf.cpu().numpy()
 t0 = t[0]
-print(f"state staged at {t[6] - t0}, observation bits built at {t[7] - t0}")
+print(f"state staged at {t[6] - t0}, observation bits built at {t[7] - t0}, after barrier {t[776] - t0}, first load_raw {t[777] - t0}, before first store {t[778] - t0}")
 print(f"workload {wl}: kernel span {t[1] - t0} cycles; after PDL wait {t[2] - t0}; layer-3 start {t[3] - t0}, layer-3 fma done {t[4] - t0}, after barrier {t[5] - t0}")
 ready = [int(x - t0) for x in t[8:8 + 256] if x]
 arrive = [int(x - t0) for x in t[264:264 + 256] if x]
