@@ -246,19 +246,6 @@ __device__ __forceinline__ void subleq_simulate(int ws, MemT* mem, int trow, int
     const bool live = !oob;
     const int cc = oob ? 0 : cur;
     const int a = mem[cc], b = mem[cc + 1], c = mem[cc + 2];
-    if (live && a <= AMAX && b <= AMAX) {
-      // Plain memory-to-memory instruction: nothing of the IN / OUT / error bookkeeping below can change (no input is consumed, the
-      // output and `bad` stay as they are -- so `all_eq` stays false, or the loop would have halted already -- and (jump & c) <= 1
-      // can never exceed ADDRESS_MAX).  Programs that survive more than a few cycles are almost always loops of such
-      // instructions, and a warp whose remaining lanes are all here skips the ~4x longer general body.
-      int value = (int)mem[a] - (int)mem[b];
-      value += value < 0 ? ws : 0;
-      mem[a] = (MemT)value;
-      bytes = max(bytes, cur + 3);
-      cur = ((value == 0) || (2 * value >= ws)) ? c : cur + 3;
-      run = cycles < EAZ_SUBLEQ_MAX_CYCLES;
-      continue;
-    }
     const bool have_in = in_cur < in_len;  // input_state[0] < word_size (:197,218)
     const int in0 = (int)((unsigned)in_rest & 0xffu);
     const bool a_mem = a <= AMAX, b_mem = b <= AMAX, a_in = a == AIN, b_in = b == AIN;
