@@ -675,3 +675,14 @@ def test_evaluate_mirror(ops, kind, kw, steps):
         counter += 1
     H.assert_same_bits(host(total), tot, "sum_of_rewards")
     assert abs(float(mean) - tot.mean()) < 1e-6
+
+
+@pytest.mark.parametrize("kind,kw,B,n", [("deepsea", dict(size=6), 9, 600), ("subleq", dict(word_size=16), 5, 330)])
+def test_search_many_simulations(ops, kind, kw, B, n):
+    """Trees of more than 512 nodes (no staging area) and descents past node 288 (pointer chase through memory instead of registers)."""
+    env = H.make_env(kind, seed=101, **kw)
+    net = H.make_net(env, seed=102, fill=0.5)
+    root = H.make_root(env, net, B, seed=103, beta_max=1.0)
+    exp, got = run_both(ops, env, net, root, dict(num_simulations=n, discount=0.97))
+    assert_tree_equal(exp, got)
+    assert (got["node_visits"][:, 0] == n + 1).all()
