@@ -44,3 +44,6 @@ print(f"kernel span first-start -> last-chase-end: mean {span.mean():.0f} cycles
 for s in (1, 8, 32, n - 1):
     m = t[s]
     print(f"sim {s:3d}: mean sections {[int((m[:, k + 1] - m[:, k]).mean()) for k in range(4)]} max total {int((m[:, 4] - m[:, 0]).max())} mean L {m[:, 6].mean():.1f}")
+mx = (t[1:n, :, 4] - t[1:n, :, 0]).max(1)
+print(f"slowest tree per launch: mean {mx.mean():.0f} cycles, median {np.median(mx):.0f}, p90 {np.percentile(mx, 90):.0f}, max {mx.max():.0f}; "
+      f"share of trees on the DIRECT path {1.0 - (t[1:n, :, 7] > 0).mean():.4f}; max L {int(t[1:n, :, 6].max())}")
