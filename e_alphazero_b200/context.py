@@ -49,25 +49,76 @@ def get_epistemic_recurrent_fn(env: Env, forward, batch_size: int, exploration: 
     return FusedRecurrentFn(env, int(batch_size), bool(exploration), float(discount), bool(two_players_game), int(mlp_mode))
 
 
+class _ParamEntry:
+    """Device copy of one haiku (params, state) pair.  Holds STRONG references to the two pytrees, so their id()s cannot be
+    reused by other objects while the entry is alive (a key on bare id()s returned stale weights once the learner freed the old
+    pytrees: CPython hands the addresses out again)."""
+
+    def __init__(self, model, fc, sources):
+        self.model = (model[0], model[1])
+        self.fc = fc
+        self.sources = sources  # [(device tensor, source leaf, version token or None)]
+
+
 _param_cache: dict = {}
 
 
+def _leaf_token(leaf):
+    """Change token of a source leaf: torch tensors count their in-place updates (`_version`); numpy / other leaves have no such
+    counter and are re-copied on every call."""
+    import torch
+
+    if torch.is_tensor(leaf):
+        return (leaf.data_ptr(), leaf._version)
+    return None
+
+
+def _haiku_sources(params, state, prefix="fc_az_net"):
+    names = [f"{prefix}/linear" + ("" if i == 0 else f"_{i}") for i in range(12)]
+    w = [[params[names[h * 3 + l]]["w"] for l in range(3)] for h in range(4)]
+    b = [[params[names[h * 3 + l]]["b"] for l in range(3)] for h in range(4)]
+    return w, b, state[f"{prefix}/xxhash32"]["binary_set"]
+
+
 def as_fc_params(model, rf: FusedRecurrentFn | None = None, env: Env | None = None) -> ops.FcParams:
-    """Accepts an ops.FcParams, or the reference's `model = (params, state)` haiku pytrees (numpy / torch leaves)."""
+    """Accepts an ops.FcParams, or the reference's `model = (params, state)` haiku pytrees (numpy / torch leaves).
+
+    The device copy is cached per pytree PAIR (strong references, identity-checked) and REFRESHED on every call: a leaf whose
+    change token moved -- or that has none (numpy) -- is copied again into the existing device tensor, and `FcParams.version`
+    is bumped so that plans rebuild their parameter-derived tables.  New pytrees (a learner update) get a new entry."""
+    import torch
+
     if isinstance(model, ops.FcParams):
         return model
     env = env or (rf.env if rf is not None else None)
-    if isinstance(model, (tuple, list)) and len(model) == 2 and env is not None:
-        key = (id(model[0]), id(model[1]))
-        hit = _param_cache.get(key)
-        if hit is None:
-            if len(_param_cache) > 8:
-                _param_cache.clear()
-            subleq = env.spec.kind == _abi.ENV_SUBLEQ
-            hit = _param_cache[key] = ops.FcParams.from_haiku(model[0], model[1], env.num_actions, hash_io=int(subleq),
-                                                             word_size=env.spec.word_size if subleq else 0)
-        return hit
-    raise EazError("params must be an ops.FcParams or a (haiku params, haiku state) pair")
+    if not (isinstance(model, (tuple, list)) and len(model) == 2 and env is not None):
+        raise EazError("params must be an ops.FcParams or a (haiku params, haiku state) pair")
+    key = (id(model[0]), id(model[1]), id(env))
+    hit = _param_cache.get(key)
+    if hit is not None and hit.model[0] is model[0] and hit.model[1] is model[1]:
+        w, b, bset = _haiku_sources(model[0], model[1])
+        fresh = [w[h][l] for h in range(4) for l in range(3)] + [b[h][l] for h in range(4) for l in range(3)] + [bset]
+        changed = False
+        for i, (dst, src, tok) in enumerate(hit.sources):
+            cur = fresh[i]
+            ntok = _leaf_token(cur)
+            if cur is src and tok is not None and ntok == tok:
+                continue
+            dst.copy_(torch.as_tensor(cur).to(dtype=dst.dtype).reshape(dst.shape), non_blocking=False)
+            hit.sources[i] = (dst, cur, ntok)
+            changed = True
+        if changed:
+            hit.fc.version += 1
+        return hit.fc
+    while len(_param_cache) >= 8:  # bounded: drop the oldest entry (dicts keep insertion order)
+        _param_cache.pop(next(iter(_param_cache)))
+    subleq = env.spec.kind == _abi.ENV_SUBLEQ
+    fc = ops.FcParams.from_haiku(model[0], model[1], env.num_actions, hash_io=int(subleq), word_size=env.spec.word_size if subleq else 0)
+    w, b, bset = _haiku_sources(model[0], model[1])
+    srcs = [w[h][l] for h in range(4) for l in range(3)] + [b[h][l] for h in range(4) for l in range(3)] + [bset]
+    dsts = [fc.w[h][l] for h in range(4) for l in range(3)] + [fc.b[h][l] for h in range(4) for l in range(3)] + [fc.binary_set]
+    _param_cache[key] = _ParamEntry(model, fc, [(d, s_, _leaf_token(s_)) for d, s_ in zip(dsts, srcs)])
+    return fc
 
 
 class ForwardFn:

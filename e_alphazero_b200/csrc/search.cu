@@ -948,7 +948,9 @@ static int search_one(const eaz_search_config* cfg, const eaz_search_inputs* in,
   SearchParams sp{n, cfg->max_depth > 0 ? cfg->max_depth : n, cfg->max_num_considered_actions, cfg->gumbel_scale, cfg->discount,
                   cfg->value_scale, cfg->maxvisit_init, cfg->epsilon, cfg->two_players_game, cfg->rescale_values, cfg->use_mixed_value,
                   cfg->flags, cfg->pb_c_init, cfg->pb_c_base, cfg->temperature, cfg->noise_seed};
-  ProfScope* init_scope = new ProfScope(CLS_INIT, st);
+  TensorWeights tw{};
+  {
+  ProfScope init_scope(CLS_INIT, st);  // (a stack object: closed on every return path)
   cudaError_t e = cudaMemsetAsync((uint8_t*)workspace + L.zero_begin, 0, L.zero_end - L.zero_begin, st);
   if (e != cudaSuccess) return cuda_fail(e, "search memset");
   const bool build_tables = (cfg->flags & EAZ_FLAG_REUSE_PREPARED) == 0;  // parameter-derived tables: once per model, not per search
@@ -959,12 +961,11 @@ static int search_one(const eaz_search_config* cfg, const eaz_search_inputs* in,
   if (int rc = eaz_env_compact(in->env, in->embedding, t.states, B, stream)) return rc;  // node 0 = roots
   if (env.kind == EAZ_ENV_DEEPSEA && build_tables)
     if (int rc = launch_deepsea_seen_table(net, env, t.ds_seen, st)) return rc;
-  TensorWeights tw{};
   if (cfg->mlp_mode == EAZ_MLP_TENSOR) {
     const int lhead = cfg->exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;
     if (int rc = prepare_tensor_weights(net, env, (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead), t.wimg, &tw, st, build_tables)) return rc;
   }
-  delete init_scope;
+  }
 
   SummaryOut so{out->action, out->action_weights, out->value, out->value_epistemic_std, out->visit_counts, out->visit_probs,
                 out->qvalues, out->qvalues_epistemic_variance};
@@ -998,28 +999,51 @@ static int search_one(const eaz_search_config* cfg, const eaz_search_inputs* in,
   return 0;
 }
 
-// Auxiliary streams / events for EAZ_FLAG_STREAMS (created once per device, never destroyed).
+// Auxiliary streams / events for EAZ_FLAG_STREAMS: one set PER WORKSPACE (the workspace already identifies one search at a
+// time -- two searches must not share one), so concurrent callers -- host threads, plans on different user streams -- never
+// re-record each other's fork / join events or interleave on each other's streams.  Sets are created on first use, kept in a
+// small per-process table (never destroyed: they may be baked into captured graphs) and, should a process ever cycle
+// through more than kAuxSets workspaces, shared by hashing -- which only costs false serialisation, because a set is locked
+// for the whole enqueue.
 struct AuxStreams {
   cudaStream_t s[8];
   cudaEvent_t fork, join[8];
-  bool ready;
+  std::mutex enqueue;  // held from the fork record to the last join wait
+  const void* owner = nullptr;
+  int device = -1;
+  bool ready = false;
 };
-static AuxStreams* aux_streams() {
-  static AuxStreams table[32] = {};
+constexpr int kAuxSets = 64;
+static AuxStreams* aux_streams(const void* workspace) {
+  static AuxStreams table[kAuxSets];
   static std::mutex mu;
   int dev = 0;
-  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 32) return nullptr;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
   std::lock_guard<std::mutex> lock(mu);
-  AuxStreams* a = &table[dev];
-  if (!a->ready) {
-    for (int i = 0; i < 8; ++i) {
-      if (cudaStreamCreateWithFlags(&a->s[i], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
-      if (cudaEventCreateWithFlags(&a->join[i], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+  AuxStreams* pick = nullptr;
+  for (int i = 0; i < kAuxSets && !pick; ++i)
+    if (table[i].ready && table[i].owner == workspace && table[i].device == dev) pick = &table[i];
+  for (int i = 0; i < kAuxSets && !pick; ++i)
+    if (!table[i].ready) {
+      AuxStreams* a = &table[i];
+      for (int k = 0; k < 8; ++k) {
+        if (cudaStreamCreateWithFlags(&a->s[k], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (cudaEventCreateWithFlags(&a->join[k], cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      }
+      if (cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      a->owner = workspace;
+      a->device = dev;
+      a->ready = true;
+      pick = a;
     }
-    if (cudaEventCreateWithFlags(&a->fork, cudaEventDisableTiming) != cudaSuccess) return nullptr;
-    a->ready = true;
+  if (!pick) {  // table full: share a set of the same device (serialised by its enqueue mutex)
+    const size_t h = ((uintptr_t)workspace >> 8) * 0x9E3779B97F4A7C15ull >> 32;
+    for (int k = 0; k < kAuxSets && !pick; ++k) {
+      AuxStreams* a = &table[(h + k) % kAuxSets];
+      if (a->device == dev) pick = a;
+    }
   }
-  return a;
+  return pick;
 }
 
 int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
@@ -1037,11 +1061,12 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   EnvDesc env;
   NetDesc net;
   if (int rc = check_search(cfg, in, out, &env, &net)) return rc;
-  AuxStreams* aux = aux_streams();
+  AuxStreams* aux = aux_streams(workspace);
   if (!aux) {
     set_error("could not create the auxiliary streams for EAZ_FLAG_STREAMS");
     return EAZ_ERR_CUDA;
   }
+  std::lock_guard<std::mutex> enqueue_lock(aux->enqueue);
   const size_t A = env.num_actions, N = cfg->num_simulations + 1, S = env.compact_bytes, D = env.obs_dim, W = env.ws;
   size_t need = 0;
   for (int p = 0; p < parts; ++p) need += layout_bytes(cfg, env, sizes[p]);

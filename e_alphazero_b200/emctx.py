@@ -192,12 +192,14 @@ def _run_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_ac
         use_mixed_value=int(q.get("use_mixed_value", True)), epsilon=float(q.get("epsilon", 1e-8)), flags=int(flags),
         mlp_mode=int(rf.mlp_mode if mlp_mode is None else mlp_mode), **extra_cfg)
     dev = root.prior_logits.device
+    # the entry keeps rf and net alive, so their id()s stay unique for as long as the key exists (and are re-checked with `is`)
     key = (id(rf), id(net), B, bytes(cfg), bool(return_tree), str(dev))
-    plan = _plans.get(key)
-    if plan is None:
-        if len(_plans) > 16:
-            _plans.clear()
-        plan = _plans[key] = ops.SearchPlan(cfg, rf.env.spec, net, want_tree=bool(return_tree), device=str(dev))
+    hit = _plans.get(key)
+    if hit is None or hit[0] is not rf or hit[1] is not net:
+        while len(_plans) >= 16:
+            _plans.pop(next(iter(_plans)))
+        hit = _plans[key] = (rf, net, ops.SearchPlan(cfg, rf.env.spec, net, want_tree=bool(return_tree), device=str(dev)))
+    plan = hit[2]
     f32 = lambda t: t.to(dtype=torch.float32).contiguous()
     emb = root.embedding.leaves if hasattr(root.embedding, "leaves") else root.embedding
     beta = root.beta
@@ -207,7 +209,7 @@ def _run_policy(params, rng_key, root, recurrent_fn, num_simulations, invalid_ac
               beta=f32(beta.reshape(B)), embedding=emb, gumbel=_draw_gumbel(rng_key, (B, A), dev))
     if invalid_actions is not None:
         rd["invalid_actions"] = invalid_actions.to(torch.uint8).contiguous()
-    out = plan.run(rd)  # (tables are rebuilt on every call: the facade cannot know whether `params` changed in place)
+    out = plan.run(rd, reuse_prepared=None)  # parameter-derived tables are rebuilt only when net.content_token() moved
     out = {k: v.clone() for k, v in out.items()}  # the plan's buffers are reused by the next call
     tree = EpistemicTree(out, A, int(num_simulations))
     return PolicyOutput(action=out["action"], action_weights=out["action_weights"], search_tree=tree)

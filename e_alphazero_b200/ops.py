@@ -281,6 +281,14 @@ class FcParams:
     word_size: int = 0
     max_u: float = 1.0
     novelty_scale: float = 1.0
+    version: int = 0  # bumped by whoever rewrites the device tensors through a path torch does not see (context.as_fc_params)
+
+    def content_token(self):
+        """Changes whenever the parameters may have changed: `version` plus torch's in-place update counters of every device
+        tensor (optimizer steps, copy_, collectives).  Plans compare it to decide whether their parameter-derived tables
+        (weight images, novelty table) are still valid."""
+        return (self.version, self.hash_bits, self.hash_io, self.max_u, self.novelty_scale,
+                tuple((t.data_ptr(), t._version) for row in self.w + self.b for t in row) + ((self.binary_set.data_ptr(), self.binary_set._version),))
 
     @staticmethod
     def from_numpy(w, b, binary_set, num_actions, hash_bits=24, hash_io=0, word_size=0, max_u=1.0, novelty_scale=1.0, device="cuda"):
@@ -386,9 +394,13 @@ class SearchPlan:
 
     PROFILE_CLASSES = ("init", "select", "env_step", "network", "expand_backward", "finalize", "export")
 
-    def run(self, root: dict, profile: bool = False, reuse_prepared: bool = False):
+    def run(self, root: dict, profile: bool = False, reuse_prepared: bool | None = False):
         """root: prior_logits [B,A], value [B], value_epistemic_variance [B], beta [B], embedding (state dict),
-        gumbel [B,A] pre-drawn standard Gumbel noise, optional invalid_actions [B,A] (bool/uint8)."""
+        gumbel [B,A] pre-drawn standard Gumbel noise, optional invalid_actions [B,A] (bool/uint8).
+
+        The returned tensors are THIS PLAN'S buffers: the next run() overwrites them (clone what must survive).
+        reuse_prepared: False = rebuild the parameter-derived tables, True = the caller promises env / net are unchanged,
+        None = decide from `net.content_token()` (rebuild only when the parameters changed since the last run)."""
         import torch
 
         f32, u8 = torch.float32, torch.uint8
@@ -404,6 +416,12 @@ class SearchPlan:
         # parameter-derived tables (seq-halving table, seen table, weight images) live in the workspace across runs
         # (reuse_prepared=True is the caller's promise that env / net are unchanged since an earlier run on this plan)
         cfg = _abi.EazSearchConfig.from_buffer_copy(self.cfg)
+        if reuse_prepared is None:
+            tok = (self.net.content_token(), None if self.env.action_map is None else (self.env.action_map.data_ptr(), self.env.action_map._version))
+            reuse_prepared = getattr(self, "_prepared", False) and getattr(self, "_prepared_token", None) == tok
+            self._prepared_token = tok
+        else:
+            self._prepared_token = None
         if reuse_prepared:
             if not getattr(self, "_prepared", False):
                 raise EazError("reuse_prepared=True before any search built the tables in this plan's workspace")

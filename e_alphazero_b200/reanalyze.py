@@ -144,17 +144,23 @@ def reanalyze(model, config, context, experience_pair, rng_key=None) -> Reanalyz
     B = first["terminated"].shape[0]
     key = (id(env), id(net), B, int(config.reanalyze_simulations_per_step), float(config.discount), float(config.reanalyze_beta),
            float(config.exploration_beta), bool(config.exploration_ube_target), float(config.exploration_policy_target_temperature))
-    r = _runners.get(key)
-    if r is None:
-        if len(_runners) > 8:
-            _runners.clear()
-        r = _runners[key] = ReanalyzeRunner(env.spec, net, B, int(config.reanalyze_simulations_per_step), float(config.discount),
+    hit = _runners.get(key)  # (env, net, runner): the strong references keep the id()s in the key unique
+    if hit is None or hit[0] is not env or hit[1] is not net:
+        while len(_runners) >= 8:
+            _runners.pop(next(iter(_runners)))
+        hit = _runners[key] = (env, net, ReanalyzeRunner(env.spec, net, B, int(config.reanalyze_simulations_per_step), float(config.discount),
                                             reanalyze_beta=float(config.reanalyze_beta), exploration_beta=float(config.exploration_beta),
                                             exploration_ube_target=bool(config.exploration_ube_target),
                                             temperature=float(config.exploration_policy_target_temperature),
-                                            rescale_values=bool(getattr(config, "rescale_q_values_in_search", True)),
-                                            mlp_mode=int(getattr(config, "mlp_mode", _abi.MLP_EXACT)), device=str(first["terminated"].device))
-    r.params_updated()  # the facade cannot know whether the model changed in place
+                                            # reanalyze.py:84 passes the bare qtransform: rescale_values stays at its default (True);
+                                            # config.rescale_q_values_in_search only reaches the self-play search (selfplay.py:115)
+                                            rescale_values=True,
+                                            mlp_mode=int(getattr(config, "mlp_mode", _abi.MLP_EXACT)), device=str(first["terminated"].device)))
+    r = hit[2]
+    tok = net.content_token()
+    if getattr(r, "_net_token", None) != tok:  # rebuild the parameter-derived tables only when the parameters moved
+        r.params_updated()
+        r._net_token = tok
     gumbel = rng_key.gumbel if isinstance(rng_key, PreDrawnGumbel) else None
     targets, out = r(first, second, gumbel=gumbel)  # legal_action_mask is all True for DeepSea / Subleq: no invalid actions
     obs = ops.env_observe(env.spec, first)

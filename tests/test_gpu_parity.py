@@ -147,7 +147,7 @@ def test_xxhash_golden(ops, golden_dir):
 
 
 # ----------------------------------------------------------------------------- network
-@pytest.mark.parametrize("kind,kw,B", [("deepsea", dict(size=10), 70), ("deepsea", dict(size=30), 33),
+@pytest.mark.parametrize("kind,kw,B", [("deepsea", dict(size=10), 70), ("deepsea", dict(size=30), 33), ("deepsea", dict(size=100), 40),
                                        ("subleq", dict(word_size=16), 100), ("subleq", dict(word_size=16, binary=False), 40),
                                        ("subleq", dict(word_size=40), 37), ("subleq", dict(word_size=256), 33)])
 def test_network_exact(ops, kind, kw, B):
@@ -223,6 +223,27 @@ def test_search_bit_exact(ops, kind, kw, B, cfg_kw, root_kw):
     n = cfg_kw["num_simulations"]
     assert (got["visit_counts"].sum(1) == n).all()
     assert (got["node_visits"][:, 0] == n + 1).all()
+
+
+@pytest.mark.parametrize("kind,kw,B,n", [("deepsea", dict(size=8), 96, 24), ("subleq", dict(word_size=16), 40, 20)])
+def test_search_assumption_switches_all_combinations(ops, kind, kw, B, n):
+    """the four emctx assumptions are switches (EAZ_FLAG_BETA_INTERIOR / BETA_RAW / BETA_FINAL / BACKUP_STD).
+    All 16 combinations, x {mixed value on / off}, must agree with the oracle bit for bit, and the switches must not be dead:
+    different combinations produce different trees."""
+    env = H.make_env(kind, seed=31, **kw)
+    net = H.make_net(env, seed=32, fill=0.5)
+    root = H.make_root(env, net, B, seed=33, beta_max=2.0, invalid_frac=0.15)
+    seen = set()
+    for combo in range(16):
+        flags = ((_abi.FLAG_BETA_INTERIOR if combo & 1 else 0) | (_abi.FLAG_BETA_RAW if combo & 2 else 0) |
+                 (_abi.FLAG_BETA_FINAL if combo & 4 else 0) | (_abi.FLAG_BACKUP_STD if combo & 8 else 0))
+        for mixed in (1, 0):
+            cfg_kw = dict(num_simulations=n, discount=0.97, flags=flags, use_mixed_value=mixed, rescale_values=combo & 1)
+            exp, got = run_both(ops, env, net, root, cfg_kw)
+            assert_tree_equal(exp, got)
+            if mixed:
+                seen.add((got["node_visits"].tobytes(), got["node_values_epistemic_variance"].tobytes(), got["action_weights"].tobytes()))
+    assert len(seen) >= 12, f"only {len(seen)} distinct results over 16 switch combinations"
 
 
 def test_search_summary_only_and_plan_reuse(ops):
@@ -607,16 +628,76 @@ def test_search_many_trees_two_per_warp(ops, B, mode, streams, puct):
     assert_tree_equal(exp, got)
 
 
+def test_facade_param_cache_never_stale(ops):
+    """context.as_fc_params: the device copy of a haiku (params, state) pair follows in-place leaf updates, and freshly built
+    pytrees never hit an old entry (a cache keyed on bare id()s returned stale weights once CPython reused the addresses)."""
+    import gc
+
+    import torch
+
+    from e_alphazero_b200 import context, pgx
+
+    env = pgx.DeepSea(size_of_grid=6)
+    oenv = H.make_env("deepsea", seed=1, size=6)
+
+    def pytrees(seed):
+        net = H.make_net(oenv, seed=seed, fill=0.3)
+        names = ["fc_az_net/linear" + ("" if i == 0 else f"_{i}") for i in range(12)]
+        params = {names[h * 3 + l]: {"w": net.w[h][l].copy(), "b": net.b[h][l].copy()} for h in range(4) for l in range(3)}
+        state = {"fc_az_net/xxhash32": {"binary_set": net.binary_set.copy()}}
+        return net, params, state
+
+    for seed in range(12):  # fresh pytrees every "learner update"; the old ones are freed, so their addresses get reused
+        net, params, state = pytrees(seed)
+        fc = context.as_fc_params((params, state), env=env)
+        assert (fc.w[2][1].cpu().numpy() == net.w[2][1]).all() and (fc.binary_set.cpu().numpy() == net.binary_set).all(), seed
+        # in-place update of a numpy leaf: picked up by the next call, version bumped
+        v0 = fc.version
+        params["fc_az_net/linear_4"]["w"][:] = 0.5
+        fc2 = context.as_fc_params((params, state), env=env)
+        assert fc2 is fc and fc.version > v0 and bool((fc.w[1][1] == 0.5).all())
+        del net, params, state, fc, fc2
+        gc.collect()
+    # torch leaves: unchanged leaves are not re-copied (version stays), an in-place update is
+    net, params, state = pytrees(99)
+    tparams = {k: {kk: torch.as_tensor(vv).cuda() for kk, vv in v.items()} for k, v in params.items()}
+    tstate = {"fc_az_net/xxhash32": {"binary_set": torch.as_tensor(state["fc_az_net/xxhash32"]["binary_set"]).cuda()}}
+    fc = context.as_fc_params((tparams, tstate), env=env)
+    v0 = fc.version
+    assert context.as_fc_params((tparams, tstate), env=env) is fc and fc.version == v0
+    tok = fc.content_token()
+    tparams["fc_az_net/linear"]["b"].add_(1.0)
+    assert context.as_fc_params((tparams, tstate), env=env).version == v0 + 1 and fc.content_token() != tok
+    assert torch.allclose(fc.b[0][0], tparams["fc_az_net/linear"]["b"])
+
+
 # ----------------------------------------------------------------------------- BASELINE full sizes: size-independent properties
-@pytest.mark.parametrize("wl", ["c2", "c3"])
+# name: (env kind, env kwargs, envs, simulations, discount, sub-batch streams, sampled trees for the oracle replay)
+FULL_SIZE = {
+    "c2": ("deepsea", dict(size=30), 4096, 64, 0.997, 3, 48),
+    "c3": ("subleq", dict(word_size=16), 8192, 64, 0.97, 1, 48),
+    # C4: the per-GPU shard of BASELINE config 4 (DeepSea-100, 65 536 envs over 8 GPUs = 8192 per GPU, 128 simulations):
+    # 30 MB layer-1 row table per head, two-trees-per-warp tree kernel, 129-node trees
+    "c4": ("deepsea", dict(size=100), 8192, 128, 0.997, 3, 48),
+    # C5 corner points of the Subleq sweep (16k-256k envs x 32-256 simulations): the deepest trees and the widest batch
+    "c5_64k_n256": ("subleq", dict(word_size=16), 65536, 256, 0.97, 1, 32),
+    "c5_256k_n32": ("subleq", dict(word_size=16), 262144, 32, 0.97, 1, 48),
+    # the reference's code default word size (main.py:159) at scale: A = 256 actions (32 lanes x 8 slots), 296-byte states
+    "ws256": ("subleq", dict(word_size=256), 2048, 64, 0.97, 1, 24),
+}
+
+
+@pytest.mark.parametrize("wl", list(FULL_SIZE))
 def test_full_size_properties(ops, wl):
-    """BASELINE configs C2 (DeepSea-30, 4096 envs, 64 simulations) and C3 (Subleq-16, 8192 envs, 64 simulations) at full size, tensor-core
-    network, concurrent sub-batches: mctx tree invariants over every tree, and bit-exact oracle replay of a sample of the trees."""
+    """BASELINE configs at full size (C2, C3, the C4 per-GPU shard, the corner points of the C5 sweep, ws=256), tensor-core network:
+    mctx tree invariants over EVERY tree, network accuracy (1e-5) on the sampled trees' nodes, and bit-exact oracle replay of a
+    sample of the trees.  Root network outputs are inputs of the search; for the large batches they come from the (bit-exact,
+    test_network_exact) CUDA fp32 network instead of the slower CPU oracle."""
     import torch
 
     import bench
 
-    kind, kw, B, n, gamma, _ = bench.WORKLOADS[wl]
+    kind, kw, B, n, gamma, streams, nsample = FULL_SIZE[wl]
     envp, netp = bench.synth_params(kind, kw, 0)
     if kind == "deepsea":
         env = O.Env.deepsea(envp["size"], envp["action_map"])
@@ -624,32 +705,54 @@ def test_full_size_properties(ops, wl):
         env = O.Env.subleq(envp["word_size"], True)
     net = O.FcNet(netp["in_dim"], 256, netp["num_actions"], netp["w"], netp["b"], netp["binary_set"], 24, netp["hash_io"], netp["word_size"])
     st = H.random_states(env, B, seed=5)
-    root = H.make_root(env, net, B, seed=6, beta_max=1.0, states=st)
     denv, dnet = H.device_env(env), H.device_net(net)
-    cfg = _abi.default_search_config(batch=B, num_simulations=n, discount=gamma, exploration=1, mlp_mode=_abi.MLP_TENSOR)
-    cfg.flags |= _abi.flag_streams(3)
-    got = {k: host(v) for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
-    nv, cv, ci, par, afp = got["node_visits"], got["children_visits"], got["children_index"], got["parents"], got["action_from_parent"]
     A = env.num_actions
-    assert (got["visit_counts"].sum(1) == n).all() and (nv[:, 0] == n + 1).all() and (nv[:, 1:] >= 1).all()
-    assert (nv == 1 + cv.sum(2)).all()                                             # node_visits[parent] = 1 + sum(children_visits)
-    idx = np.arange(1, n + 1)
-    assert (par[:, 1:] < idx).all() and (par[:, 1:] >= 0).all()                      # node i hangs under an older node
-    bb = np.repeat(np.arange(B), n)
-    assert (ci[bb, par[:, 1:].reshape(-1), afp[:, 1:].reshape(-1)] == np.tile(idx, B)).all()  # children_index[parent, action] = child
-    assert ((ci >= 0).sum((1, 2)) == n).all()                                        # exactly n edges are expanded
-    assert (got["action"] >= 0).all() and (got["action"] < A).all()
-    np.testing.assert_allclose(got["action_weights"].sum(1), 1.0, rtol=1e-5)
-    assert np.isfinite(got["qvalues"]).all() and (got["qvalues_epistemic_variance"] >= 0).all()
-    # oracle replay (the GPU's own per-node network outputs) on a sample of the trees: bit for bit
-    pick = np.random.default_rng(7).choice(B, 48, replace=False)
+    if B <= 8192 and wl != "c4":
+        root = H.make_root(env, net, B, seed=6, beta_max=1.0, states=st)
+    else:
+        ev = {k: host(v) for k, v in ops.mlp_forward_states(dnet, denv, ops.state_to_device(denv, st)).items()}
+        root = dict(prior_logits=ev["exploit_logits"], value=ev["value"], value_epistemic_variance=ev["ube"],
+                    beta=np.linspace(0, 1, B).astype(np.float32), embedding=st,
+                    gumbel=np.random.default_rng(13).gumbel(size=(B, A)).astype(np.float32))
+    cfg = _abi.default_search_config(batch=B, num_simulations=n, discount=gamma, exploration=1, mlp_mode=_abi.MLP_TENSOR)
+    if streams > 1:
+        cfg.flags |= _abi.flag_streams(streams)
+    dgot = ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True)
+    torch.cuda.synchronize()
+    pick = np.sort(np.random.default_rng(7).choice(B, nsample, replace=False))
+    # ---- invariants over every tree, evaluated on the device (the big shapes hold > 10^8 edges), then cross-checked on the host sample
+    nv, cv, ci = dgot["node_visits"], dgot["children_visits"], dgot["children_index"]
+    par, afp = dgot["parents"].long(), dgot["action_from_parent"].long()
+    assert bool((dgot["visit_counts"].sum(1) == n).all()) and bool((nv[:, 0] == n + 1).all()) and bool((nv[:, 1:] >= 1).all())
+    assert bool((nv == 1 + cv.sum(2)).all())                                             # node_visits[parent] = 1 + sum(children_visits)
+    idx = torch.arange(1, n + 1, device=nv.device)
+    assert bool((par[:, 1:] < idx).all()) and bool((par[:, 1:] >= 0).all())             # node i hangs under an older node
+    flat = ci.reshape(B, -1).gather(1, par[:, 1:] * A + afp[:, 1:])
+    assert bool((flat == idx).all())                                                     # children_index[parent, action] = child
+    assert bool(((ci >= 0).sum((1, 2)) == n).all())                                      # exactly n edges are expanded
+    assert bool((dgot["action"] >= 0).all()) and bool((dgot["action"] < A).all())
+    assert torch.allclose(dgot["action_weights"].sum(1), torch.ones(B, device=nv.device), rtol=1e-5, atol=1e-6)
+    assert bool(torch.isfinite(dgot["qvalues"]).all()) and bool((dgot["qvalues_epistemic_variance"] >= 0).all())
+    tpick = torch.as_tensor(pick, device=nv.device)
+    got = {k: host(v[tpick]) for k, v in dgot.items()}
+    del dgot
+    # ---- network accuracy on the sampled trees' expanded nodes (fp32 oracle network, 1e-5)
+    emb = got["embeddings"][:, 1:].reshape(nsample * n, -1)
+    nst = H.uncompact(env, emb)
+    ev = O.mlp_forward_states(net, env, nst)
+    lg = ev["explore_logits"] - ev["explore_logits"].max(1, keepdims=True)
+    term = nst["terminated"].astype(bool)
+    np.testing.assert_allclose(got["children_prior_logits"][:, 1:].reshape(nsample * n, A), lg, rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got["raw_values"][:, 1:].reshape(-1), np.where(term, 0, ev["value"]), rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got["raw_values_epistemic_variance"][:, 1:].reshape(-1), np.where(term, 0, ev["ube"]), rtol=1e-5, atol=2e-6)
+    # ---- oracle replay (the GPU's own per-node network outputs) on the sample: bit for bit
     sub_root = {k: (v[pick] if k != "embedding" else {kk: vv[pick] for kk, vv in v.items()}) for k, v in root.items()}
-    replay = dict(states=got["embeddings"][pick], logits=got["children_prior_logits"][pick], value=got["raw_values"][pick],
-                  var=got["raw_values_epistemic_variance"][pick])
+    replay = dict(states=got["embeddings"], logits=got["children_prior_logits"], value=got["raw_values"],
+                  var=got["raw_values_epistemic_variance"])
     exp = O.search(_abi.default_search_config(num_simulations=n, discount=gamma, exploration=1), env, None, sub_root, want_tree=True, replay=replay)
     assert exp["replay_misses"] == 0
     for name, _, _ in _abi.SUMMARY_FIELDS + _abi.TREE_FIELDS:
-        H.assert_same_bits(got[name][pick], exp[name], name)
+        H.assert_same_bits(got[name], exp[name], name)
 
 
 @pytest.mark.parametrize("kind,kw,steps", [("deepsea", dict(size=6), 10), ("subleq", dict(word_size=16), 6)])
