@@ -41,6 +41,7 @@ struct TensorWeights {
   const uint32_t* img[4][3];
   int k1pad;
   const void* h1[4];  // one-hot observations (DeepSea): pre-activated, pre-split layer-1 rows per cell (mlp_gather.cu)
+  const void* w2_ck16[4];  // one-hot observations: the W2 images once more in K = 16 chunks (persistent search kernel, psearch.cuh)
 };
 size_t gather_table_bytes(const NetDesc& net);
 int prepare_gather_table(const NetDesc& net, int head, void* buf, cudaStream_t st);

@@ -25,7 +25,7 @@
 namespace eaz {
 using namespace umma;
 
-int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, float scale, void* out, cudaStream_t st);
+int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, float scale, void* out, cudaStream_t st, int chunk_k = 32);  // tile_weights.cu
 
 constexpr int kTM = 128;                       // rows per CTA
 constexpr int kCK = 32;                        // K elements (fp16) per pipeline stage: 64 B per row
@@ -622,7 +622,7 @@ size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env) {
   const int np3 = (net.A + 15) & ~15;
   const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? gather_table_bytes(net) : (size_t)k1pad_of(net.D) * 2 * kH * 2;
   const size_t l2 = (size_t)kH * 2 * kH * 2;
-  const size_t per_head = l1 + l2 + (size_t)kH * 2 * np3 * 2;
+  const size_t per_head = l1 + l2 + (size_t)kH * 2 * np3 * 2 + (env.kind == EAZ_ENV_DEEPSEA ? l2 : 0);  // (+ the K = 16 W2 images)
   return 4 * ((per_head + 255) & ~(size_t)255);
 }
 
@@ -642,6 +642,8 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     tw->img[h][1] = (const uint32_t*)(p + l1);
     tw->img[h][2] = (const uint32_t*)(p + l1 + l2);
     tw->h1[h] = has_l1 ? nullptr : p;
+    const size_t l3 = (size_t)kH * 2 * ((net.A + 15) & ~15) * 2;
+    tw->w2_ck16[h] = has_l1 ? nullptr : p + l1 + l2 + l3;
     if (!fill || !(heads_mask & (1 << h))) continue;
     const int nout = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
     if (has_l1) {
@@ -651,6 +653,8 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     }
     if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, kWScale, p + l1, st)) return rc;
     if (int rc = launch_tile_weights_f16(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, kWScale, p + l1 + l2, st)) return rc;
+    if (!has_l1)
+      if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, kWScale, p + l1 + l2 + l3, st, 16)) return rc;
   }
   return 0;
 }

@@ -464,7 +464,72 @@ __global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp,
 
 }  // namespace eaz
 #include "tree_step.cuh"
+#include "psearch.cuh"
 namespace eaz {
+
+// ------------------------------------------------------------------ persistent tile-resident search (psearch.cuh): eligibility + launch
+static unsigned long long* g_ps_trace = nullptr;  // eaz_debug_set_ps_trace
+static bool persistent_eligible(const Tree& t, const SearchParams& sp, const EnvDesc& env, int mlp_mode, const TensorWeights* tw, int* ncap_out) {
+  static const bool disabled = getenv("EAZ_NO_PERSISTENT") != nullptr;  // measurement knob: the per-simulation launch chain instead
+  if (disabled || tl_prof != nullptr) return false;                    // (the profiled variant times per-launch classes)
+  if (env.kind != EAZ_ENV_DEEPSEA || mlp_mode != EAZ_MLP_TENSOR || !tw || !tw->w2_ck16[0] || t.A > ps::kG) return false;
+  if (sp.flags & EAZ_FLAG_PUCT) return false;  // PUCT selection has no staged form: DIRECT chain
+  if (t.N > 16383) return false;               // 16-bit cached selections
+  const int ncap = (t.N + 1) & ~1;
+  int dev = 0, max_optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
+  if (ps::smem_bytes(ncap) > (size_t)max_optin) return false;  // trees too large for the shared-memory caches
+  *ncap_out = ncap;
+  return true;
+}
+
+static int launch_persistent(const Tree& t, const SearchParams& sp, const EnvDesc& env, const NetDesc& net, const TensorWeights& tw,
+                             const eaz_search_inputs* in, int lhead, int ncap, cudaStream_t st) {
+  ps::Args a{};
+  a.t = t;
+  a.sp = sp;
+  a.env = env;
+  a.beta = in->beta;
+  a.invalid = in->invalid_actions;
+  const int heads[ps::kHeads] = {EAZ_HEAD_VALUE, EAZ_HEAD_UBE, lhead};
+  for (int r = 0; r < ps::kHeads; ++r) {
+    const int h = heads[r];
+    a.w2img[r] = (const uint8_t*)tw.w2_ck16[h];
+    a.h1[r] = (const uint8_t*)tw.h1[h];
+    a.b2[r] = net.b[h][1];
+    a.w3[r] = net.w[h][2];
+    a.b3[r] = net.b[h][2];
+    a.nout[r] = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
+    a.head_id[r] = h;
+  }
+  a.ds_seen = t.ds_seen;
+  a.max_u = net.max_u;
+  a.novelty_scale = net.novelty_scale;
+  a.ncap = ncap;
+  a.trace = g_ps_trace;
+  const size_t smem = ps::smem_bytes(ncap);
+  static size_t attr_smem = 0;  // idempotent; a race only repeats the call
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(ps::ds_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ds_search_kernel)");
+    attr_smem = smem;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(ceil_div(t.B, ps::kTile) * ps::kCtas);
+  cfg.blockDim = dim3(ps::kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ps::kCtas;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t le = cudaLaunchKernelEx(&cfg, ps::ds_search_kernel, a);
+  if (le != cudaSuccess) return cuda_fail(le, "ds_search_kernel launch");
+  return 0;
+}
 
 // ------------------------------------------------------------------ Subleq transition on tree states (context.py:127)
 __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_tree_step_kernel(Tree t, EnvDesc env) {
@@ -751,6 +816,19 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, root_logits, root_value, root_var, in->gumbel, in->invalid_actions, root_out_value, root_out_ube);
   }
   EAZ_CHECK_LAUNCH("root_init_kernel");
+  if constexpr (G == ps::kG && J == 1) {
+    int ncap = 0;
+    if (!flags && persistent_eligible(t, sp, env, mlp_mode, tw, &ncap)) {  // ONE launch runs all sp.n simulations (psearch.cuh)
+      {
+        ProfScope ps_scope(CLS_SELECT, st);
+        if (int rc = launch_persistent(t, sp, env, net, *tw, in, lhead, ncap, st)) return rc;
+      }
+      ProfScope pf(CLS_FINAL, st);
+      finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so);
+      EAZ_CHECK_LAUNCH("finalize_kernel");
+      return 0;
+    }
+  }
   // staging area of tree_step_kernel (tree_step.cuh): per warp, sized for the cached selections + states of all N nodes
   static const bool no_staging = getenv("EAZ_NO_STAGING") != nullptr;  // measurement knob: force the DIRECT path
   const int chase_cap = (J == 1 && t.N <= 512 && !no_staging) ? ((t.N + 2 + 7) & ~7) : 0;
@@ -1197,6 +1275,10 @@ int eaz_search_gumbel_profiled(const eaz_search_config* cfg, const eaz_search_in
   if (e != cudaSuccess) return cuda_fail(e, "profiled search sync");
   return rc;
 }
+
+// Debug hook (not in the public header): device buffer of num_simulations * 8 u64 receiving the per-simulation milestones of cluster 0
+// of the persistent search kernel (psearch.cuh: Trace).
+void eaz_debug_set_ps_trace(unsigned long long* device_buffer) { eaz::g_ps_trace = device_buffer; }
 
 // Debug hook (not in the public header): device buffer of (n+1)*B*8 int64 receiving per-tree section stamps of tree_step_kernel.
 void eaz_debug_set_tree_trace(long long* device_buffer) { eaz::g_tree_trace = device_buffer; }

@@ -9,53 +9,7 @@
 namespace eaz {
 using namespace umma;
 
-// W[K][N] (row-major, haiku layout) -> per K-chunk image [hi tile | lo tile], each tile [Npad x 32] in the
-// canonical K-major layout of umma.cuh.  out must hold (Kpad/32) * 2 * Npad * 32 words.
-template <int CK>
-__global__ void tile_weights_kernel(const float* __restrict__ W, int K, int N, int Kpad, int Npad, uint32_t* __restrict__ out) {
-  const int total = Kpad * Npad;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int k = i / Npad, n = i % Npad;  // consecutive threads -> consecutive n (coalesced reads of W rows)
-    const float w = (k < K && n < N) ? W[(size_t)k * N + n] : 0.0f;
-    uint32_t hi, lo;
-    split_tf32(w, hi, lo);
-    const int c = k / CK, kk = k % CK;
-    const size_t base = (size_t)c * 2 * Npad * CK;  // words
-    const int off = tile_offset_ck<CK>(n, kk) >> 2;
-    out[base + off] = hi;
-    out[base + (size_t)Npad * CK + off] = lo;
-  }
-}
-
-// fp16 variant for the network kernel: chunks of 32 k, image per chunk = [hi tile | lo tile], each [Npad x 32] halves;
-// values are scaled by `scale` (a power of two) and clamped to the fp16 range before the hi/lo split.
-__global__ void tile_weights_f16_kernel(const float* __restrict__ W, int K, int N, int Kpad, int Npad, float scale, __half* __restrict__ out) {
-  const int total = Kpad * Npad;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int k = i / Npad, n = i % Npad;
-    float w = (k < K && n < N) ? W[(size_t)k * N + n] * scale : 0.0f;
-    w = fminf(fmaxf(w, -65504.0f), 65504.0f);
-    __half hi, lo;
-    split_f16(w, hi, lo);
-    const int c = k >> 5, kk = k & 31;
-    const size_t base = (size_t)c * 2 * Npad * 32;  // halves
-    const int off = tile_offset_h32(n, kk) >> 1;
-    out[base + off] = hi;
-    out[base + (size_t)Npad * 32 + off] = lo;
-  }
-}
-int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, float scale, void* out, cudaStream_t st) {
-  tile_weights_f16_kernel<<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, scale, (__half*)out);
-  EAZ_CHECK_LAUNCH("tile_weights_f16_kernel");
-  return 0;
-}
-
-int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st, int chunk_k) {
-  if (chunk_k == 16) tile_weights_kernel<16><<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, out);
-  else tile_weights_kernel<32><<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, out);
-  EAZ_CHECK_LAUNCH("tile_weights_kernel");
-  return 0;
-}
+int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st, int chunk_k);  // tile_weights.cu
 
 struct GemmSmem {
   uint64_t full_a[2], full_b[2], empty[2], done;
