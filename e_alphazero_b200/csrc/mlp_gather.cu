@@ -153,8 +153,8 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
     }
     __syncwarp();
   } else if (warp == 8) {
-    // ================= MMA-issue warp =================
-    if (lane == 0) {
+    // ================= MMA-issue warp: warp-uniform loop, one elected lane issues (umma.cuh: elect_one) =================
+    {
       const uint32_t desc_hi = (uint32_t)(kSBO >> 4) | (1u << 14);    // SBO [32,46) + version=1 [46,48)
       const uint32_t lbo_bits = (uint32_t)(kCoreBytes >> 4) << 16;    // LBO [16,30)
       auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
@@ -164,23 +164,25 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
       for (int c = 0; c < kChunks; ++c) {
         const int s = c % kStages, ph = (c / kStages) & 1;
         mbar_wait(&sh->full_b[s], ph);
-        if (tr) trace[16 + c] = clock64();
+        if (tr && lane == 0) trace[16 + c] = clock64();
         mbar_wait(&sh->full_a[s], ph);
         tc_fence_after();
-        if (tr) trace[32 + c] = clock64();
+        if (tr && lane == 0) trace[32 + c] = clock64();
         const uint32_t al = a_base + (uint32_t)((s * kAStage) >> 4), bl = b_base + (uint32_t)((s * kBStage) >> 4);
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < kCK / 16; ++j) {
-          const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
-          mma_f16(tmem, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
-          mma_f16(tmem, mk(al + o), mk(bl + (kBHalf >> 4) + o), idesc, 1);
-          mma_f16(tmem, mk(al + (kAHalf >> 4) + o), mk(bl + o), idesc, 1);
+          for (int j = 0; j < kCK / 16; ++j) {
+            const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
+            mma_f16(tmem, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
+            mma_f16(tmem, mk(al + o), mk(bl + (kBHalf >> 4) + o), idesc, 1);
+            mma_f16(tmem, mk(al + (kAHalf >> 4) + o), mk(bl + o), idesc, 1);
+          }
+          mma_commit(&sh->empty[s]);
+          if (c == kChunks - 1) mma_commit(&sh->acc_done);
         }
-        mma_commit(&sh->empty[s]);
+        __syncwarp();
       }
-      mma_commit(&sh->acc_done);
     }
-    __syncwarp();
   } else {
     // ================= workers: layer-1 row gather, then layer 3 out of TMEM =================
     const int part = warp >> 2, wq = warp & 3;  // hi / lo halves; rows [32 wq, 32 wq + 32)
@@ -230,8 +232,7 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
     auto store_a = [&](int c, const uint4 (&x)[4]) {
       const int s = c % kStages;
       if (c >= kStages) {  // the stage is free once the MMAs of chunk c - kStages have completed; one polling lane per warp
-        if (lane == 0) mbar_wait(&sh->empty[s], ((c / kStages) & 1) ^ 1);
-        __syncwarp();
+        mbar_wait_warp(&sh->empty[s], ((c / kStages) & 1) ^ 1);
       }
       uint8_t* dst = sA + s * kAStage;
 #pragma unroll
@@ -251,8 +252,7 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
 
     // ---- layer 3 on the CUDA cores: y = relu(D + b2) @ W3; worker group `part` takes half of the 256 columns
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
-    if (lane == 0) mbar_wait(&sh->acc_done, 0);  // one polling lane per warp
-    __syncwarp();
+    mbar_wait_warp(&sh->acc_done, 0);  // one polling lane per warp, warp-uniform loop
     tc_fence_after();
     if (tr && threadIdx.x == 0) trace[6] = clock64();
     const int cbase = part * (kH / 2);

@@ -104,10 +104,7 @@ __device__ __forceinline__ void store_a_chunk(uint8_t* stage, int row, const flo
 
 // Barrier wait for a whole warp with ONE polling lane: hundreds of threads spinning on mbarrier.try_wait starve the
 // shared-memory pipe that the operand stores and TMEM loads of the other warps go through (measured in mlp_gather.cu).
-__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) {
-  if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity);
-  __syncwarp();
-}
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity) { mbar_wait_warp(bar, parity); }  // (umma.cuh: warp-uniform loop)
 
 struct TensorHeads {
   int n;
@@ -221,9 +218,9 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
     __syncwarp();
   } else if (warp == 8) {
     // ================= MMA-issue warp =================
-    // Single issuing thread: everything that does not depend on the chunk is hoisted (descriptor high words,
-    // per-stage low words), so a chunk costs two mbarrier waits, 4-6 tcgen05.mma and one commit.
-    if (lane == 0) {
+    // The whole warp runs the loop on warp-uniform values and one ELECTED lane issues (umma.cuh: elect_one): a chunk costs two
+    // mbarrier waits, 4-6 tcgen05.mma with uniform-register descriptors and one commit.
+    {
       const uint32_t desc_hi = (uint32_t)(kSBO >> 4) | (1u << 14);              // SBO [32,46) + version=1 [46,48)
       const uint32_t lbo_bits = (uint32_t)(kCoreBytes >> 4) << 16;              // LBO [16,30)
       uint32_t a_lo32[kStages], b_lo32[kStages];
@@ -247,25 +244,27 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
           mbar_wait(&sh->full_b[s], ph);
           mbar_wait(&sh->full_a[s], ph);
           tc_fence_after();
-          if (tr) trace[8 + t] = clock64();
+          if (tr && lane == 0) trace[8 + t] = clock64();
           uint32_t al = 0, bl = 0;
 #pragma unroll
           for (int q = 0; q < kStages; ++q)
             if (q == s) { al = a_lo32[q]; bl = b_lo32[q]; }
+          if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < kCK / 16; ++j) {
-            const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
-            mma_f16(d, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
-            mma_f16(d, mk(al + o), mk(bl + blo_off + o), idesc, 1);
-            if (layer != 0) mma_f16(d, mk(al + alo_off + o), mk(bl + o), idesc, 1);  // 0/1 inputs are exact in FP16: no lo part
+            for (int j = 0; j < kCK / 16; ++j) {
+              const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
+              mma_f16(d, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
+              mma_f16(d, mk(al + o), mk(bl + blo_off + o), idesc, 1);
+              if (layer != 0) mma_f16(d, mk(al + alo_off + o), mk(bl + o), idesc, 1);  // 0/1 inputs are exact in FP16: no lo part
+            }
+            mma_commit(&sh->empty[s]);
+            if (c == nchunks - 1) mma_commit(&sh->acc_done[layer]);
           }
-          mma_commit(&sh->empty[s]);
-          if (tr) trace[520 + t] = clock64();
+          __syncwarp();
+          if (tr && lane == 0) trace[520 + t] = clock64();
         }
-        if (nchunks > 0) mma_commit(&sh->acc_done[layer]);
       }
     }
-    __syncwarp();
   } else {
     // ================= worker warps: A producer (thread == row) + epilogue =================
     // Stage this thread's compact state record in shared memory first (the A stages are still unused): the observation

@@ -72,7 +72,7 @@ constexpr int kMiscWords = 12;        // [0] considered visit, [8..8+A) leaf pri
 constexpr int kTreeWords = kEdgeWords + kBackWords + kRootWords + kMiscWords;  // + ncap state words + ncap/2 next words
 
 struct Shared {
-  uint64_t full_b[kStages], empty[kStages];  // (A chunks are handed over with named barriers kBarA0 + stage, see the gather warps)
+  uint64_t full_a[kStages], full_b[kStages], empty[kStages];
   uint64_t acc_done;    // the evaluation's MMAs are complete (tcgen05.commit)
   uint64_t cells_full;  // transaction barrier: kTile * 4 bytes of st.async per phase -- every tree of the tile has published its leaf cell
   uint64_t out_full;    // transaction barrier: the three heads' outputs for this CTA's kSlots trees have landed
@@ -111,18 +111,7 @@ __device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, 
   asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v), "r"(cluster_mbar)
                : "memory");
 }
-// One lane polls (hundreds of polling threads starve the shared-memory pipe), but the LOOP is warp-uniform: the poll is a predicated
-// instruction and the exit condition a vote.  The obvious `if (lane == 0) wait(); __syncwarp();` leaves lane 0 and lanes 1..31 as two
-// separately scheduled groups whenever lane 0 actually had to loop, and the code after it then issues every instruction twice and
-// re-synchronises at every shuffle (measured: the same tree step took 4.8 us in warps whose first poll succeeded and 13 us in warps
-// that had to wait; profiles/r2_summary.md).
-__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int lane) {
-  while (true) {
-    uint32_t ok = 0;
-    if (lane == 0) ok = mbar_try_wait(bar, parity) ? 1u : 0u;
-    if (__any_sync(0xffffffffu, ok != 0)) break;
-  }
-}
+__device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int) { mbar_wait_warp(bar, parity); }  // (umma.cuh)
 
 __device__ __forceinline__ uint32_t pack_next16(int packed) {  // NodeRec.pad0 (action | child + 1 << 8) -> 16 bits (action | child + 1 << 2)
   return (uint32_t)(packed & 3) | ((uint32_t)(packed >> 8) << 2);
@@ -152,6 +141,9 @@ struct Trace {
   }
   __device__ __forceinline__ void gather(int it, int c, int k) const {  // region 6 at [n * 200 + 64 + c * 4 + k]: gather milestones, simulation kProbe
     if (buf && it == kProbe) buf[(size_t)n * 200 + 64 + c * 4 + k] = globaltimer_ns();
+  }
+  __device__ __forceinline__ void mma_clock(int it, int c, int k) const {  // region 7 at [n * 200 + 128 + c * 8 + k]: clock64 inside the MMA warp, simulation kProbe
+    if (buf && it == kProbe) buf[(size_t)n * 200 + 128 + c * 8 + k] = (unsigned long long)clock64();
   }
   __device__ __forceinline__ void chunk(int it, int c, int k) const {
     if (buf && it == kProbe) buf[(size_t)n * 136 + c * 2 + k] = globaltimer_ns();
@@ -210,6 +202,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   // ------------------------------------------------------------------ prologue
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sh->full_a[s], 2);  // one elected arrive per gather warp of the stage's group
       mbar_init(&sh->full_b[s], 1);
       mbar_init(&sh->empty[s], 1);
     }
@@ -253,6 +246,9 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
     __syncwarp();
   } else if (warp == kWarpMma) {
     // ================================================================ MMA-issue warp
+    // The whole warp runs the loop with warp-uniform values and ONE ELECTED lane issues: inside an `if (lane == 0)` region the
+    // compiler treats the descriptors as per-thread values and wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST loop (~100 cycles
+    // per instruction, measured: 1000 cycles per 3-MMA chunk against 384 cycles of tensor work).
     regs_dec<kRegsCtrl>();
     if (head_cta) {
       const uint32_t tmem = sh->tmem_base;
@@ -265,14 +261,12 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
 #pragma unroll 1
       for (int g = 0; g < total; ++g) {
         const int s = g % kStages, ph = (g / kStages) & 1, c = g % kChunks;
-        // the A chunk: the stage's two gather warps have stored their pieces (bar.arrive after their proxy fence); this whole warp syncs
-        asm volatile("bar.sync %0, %1;" ::"r"(kBarA0 + s), "r"(3 * 32) : "memory");
-        if (lane == 0) {
-          trc.chunk(g / kChunks, c, 0);
-          mbar_wait(&sh->full_b[s], ph);
-          trc.chunk(g / kChunks, c, 1);
-          tc_fence_after();
-          const uint32_t al = a_base + (uint32_t)((s * kAStage) >> 4), bl = b_base + (uint32_t)((s * kBStage) >> 4);
+        mbar_wait(&sh->full_a[s], ph);  // (all 32 lanes: uniform control flow)
+        mbar_wait(&sh->full_b[s], ph);
+        tc_fence_after();
+        if (lane == 0) trc.chunk(g / kChunks, c, 0);
+        const uint32_t al = a_base + (uint32_t)((s * kAStage) >> 4), bl = b_base + (uint32_t)((s * kBStage) >> 4);
+        if (elect_one()) {
           mma_f16(tmem, mk(al), mk(bl), idesc, c != 0);
           mma_f16(tmem, mk(al), mk(bl + (kBHalf >> 4)), idesc, 1);
           mma_f16(tmem, mk(al + (kAHalf >> 4)), mk(bl), idesc, 1);
@@ -336,8 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
           if (gtr) trc.gather(it, c, 2);  // data arrived and stored
           fence_proxy_async();
           if (gtr) trc.gather(it, c, 3);  // fenced
-          // hand-over by NAMED BARRIER (2 gather warps + the MMA warp), not by an mbarrier release-arrive (one more MEMBAR)
-          asm volatile("bar.arrive %0, %1;" ::"r"(kBarA0 + grp), "r"(3 * 32) : "memory");
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sh->full_a[grp]);
         }
         if (gw == 0 && lane == 0) trc.stamp(it, 1);
       }
@@ -451,18 +445,17 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
     // ---- simulation 0: the root's first selection + descent (DIRECT), then mirror the result
     direct_pair(a, 0, 0, 1, tile_b0 + (int)rank * kSlots + 2 * tw, lane);
     resync(0);
-    if (in_batch && hl < t.A) {  // the root's score terms never change (mctx seq_halving.score_considered)
-      const float lg = t.edges[(size_t)(ub * uA + (unsigned)hl)].pl;  // root prior logits (already max-subtracted / masked by root_init)
-      const bool inval = a.invalid && a.invalid[ub * uA + hl] != 0;
-      float m = lg;
-      int nv = inval ? 0 : 1;
-      for (int s = 1; s < kG; s <<= 1) {
-        m = fmaxf(m, __shfl_xor_sync(0x00030003u << 0, m, s, kW));
-        nv += __shfl_xor_sync(0x00030003u << 0, nv, s, kW);
+    {  // the root's score terms never change (mctx seq_halving.score_considered); lanes hl = 0 .. A-1 of the tree form its group 0
+      const bool rt = in_batch && hl < t.A;
+      const float lg = rt ? t.edges[(size_t)(ub * uA + (unsigned)hl)].pl : -INFINITY;  // root prior logits (max-subtracted / masked by root_init)
+      const bool inval = rt && a.invalid && a.invalid[ub * uA + hl] != 0;
+      const float m = group_max<kG>(lg);
+      const int nvalid = group_sum_i<kG>((rt && !inval) ? 1 : 0);
+      if (rt) {
+        s_root[hl] = __float_as_uint(__fadd_rn(t.gumbel[ub * uA + hl], __fsub_rn(lg, m)));
+        s_root[2 + hl] = inval ? 1u : 0u;
+        if (hl == 0) s_misc[1] = (uint32_t)min(sp.max_considered, nvalid);
       }
-      s_root[hl] = __float_as_uint(__fadd_rn(t.gumbel[ub * uA + hl], __fsub_rn(lg, m)));
-      s_root[2 + hl] = inval ? 1u : 0u;
-      if (hl == 0) s_misc[1] = (uint32_t)min(sp.max_considered, nv);
     }
     __syncwarp();
     publish();

@@ -479,6 +479,33 @@ static bool persistent_eligible(const Tree& t, const SearchParams& sp, const Env
   int dev = 0, max_optin = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
   if (ps::smem_bytes(ncap) > (size_t)max_optin) return false;  // trees too large for the shared-memory caches
+  // One wave only: a tile's chain (network -> tree -> network ...) is latency-bound, so a second wave of clusters doubles the search
+  // time, while the per-simulation launch chain fills the whole machine with every kernel (measured at DeepSea-100 x 8192 trees =
+  // 64 tiles on 33 co-resident clusters: 5.2 ms persistent vs 4.5 ms chain; at 4096 trees = 32 tiles: 1.20 vs 1.29 ms).
+  static int max_clusters[32] = {0};  // per device, queried once (idempotent; a race only repeats the query)
+  if (dev >= 0 && dev < 32 && max_clusters[dev] == 0) {
+    const size_t smem_max = ps::smem_bytes(212);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(ps::kCtas * 64);
+    cfg.blockDim = dim3(ps::kThreads);
+    cfg.dynamicSmemBytes = smem_max <= (size_t)max_optin ? smem_max : (size_t)max_optin;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = ps::kCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int nc = 0;
+    if (cudaFuncSetAttribute(ps::ds_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cfg.dynamicSmemBytes) != cudaSuccess ||
+        cudaOccupancyMaxActiveClusters(&nc, ps::ds_search_kernel, &cfg) != cudaSuccess || nc < 1) {
+      cudaGetLastError();
+      nc = -1;
+    }
+    max_clusters[dev] = nc;
+  }
+  static const bool any_waves = getenv("EAZ_PERSISTENT_WAVES") != nullptr;  // measurement knob: allow more tiles than co-resident clusters
+  if (!any_waves && (dev < 0 || dev >= 32 || ceil_div(t.B, ps::kTile) > max_clusters[dev])) return false;
   *ncap_out = ncap;
   return true;
 }
@@ -508,12 +535,7 @@ static int launch_persistent(const Tree& t, const SearchParams& sp, const EnvDes
   a.ncap = ncap;
   a.trace = g_ps_trace;
   const size_t smem = ps::smem_bytes(ncap);
-  static size_t attr_smem = 0;  // idempotent; a race only repeats the call
-  if (smem > attr_smem) {
-    cudaError_t e = cudaFuncSetAttribute(ps::ds_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(ds_search_kernel)");
-    attr_smem = smem;
-  }
+  // (cudaFuncAttributeMaxDynamicSharedMemorySize was raised to the largest eligible size by persistent_eligible)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ceil_div(t.B, ps::kTile) * ps::kCtas);
   cfg.blockDim = dim3(ps::kThreads);

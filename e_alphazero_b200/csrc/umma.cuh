@@ -65,6 +65,34 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// One lane polls (hundreds of polling threads starve the shared-memory pipe), but the LOOP is warp-uniform: the poll is a predicated
+// instruction and the exit condition a vote.  `if (lane == 0) mbar_wait(); __syncwarp();` leaves lane 0 and lanes 1..31 as two
+// separately scheduled groups whenever lane 0 actually had to loop; the code after it then issues every instruction twice and
+// re-synchronises at every shuffle (measured in psearch.cuh: the same tree step took 4.8 us in warps whose first poll succeeded and
+// 13 us in warps that had to wait; profiles/r2_summary.md).
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  const bool poller = (threadIdx.x & 31) == 0;
+  while (true) {
+    uint32_t ok = 0;
+    if (poller) ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+    if (__any_sync(0xffffffffu, ok != 0)) break;
+  }
+}
+// One lane of the (converged) warp.  tcgen05.mma issued under `if (elect_one())` from warp-uniform values takes its descriptors from
+// uniform registers; inside an `if (lane == 0)` region the compiler wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST loop
+// (~100 cycles per instruction).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---- 1-D bulk async copy global -> shared (SASS UBLKCP), completion on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),

@@ -24,7 +24,7 @@ states = ops.env_init(env, B)
 for _ in range(4):
     states, _ = runner.step(states)
 torch.cuda.synchronize()
-buf = torch.zeros(n * 200 + 128, dtype=torch.int64, device="cuda")
+buf = torch.zeros(n * 200 + 256, dtype=torch.int64, device="cuda")
 lib = _lib.load()
 lib.eaz_debug_set_ps_trace(C.c_void_p(buf.data_ptr()))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -74,3 +74,4 @@ ga = raw[n * 200 + 64: n * 200 + 128].reshape(16, 4)
 print("simulation 8, head CTA 0, gather groups: per chunk loads issued / stage free / stored / fenced (ns since cells_full)")
 for c in range(16):
     print(f"  chunk {c:2d} (group {c % 4}): " + " ".join(f"{int(v - t[8, 0]):6d}" for v in ga[c]) + f"   MMA warp saw A at {int(ch[c, 0] - t[8, 0])}")
+
