@@ -64,39 +64,71 @@ def synth_params(kind, kw, seed=0):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md): an NVML polling thread (about one sample
+    per millisecond -- `nvidia-smi -lms` cannot sample a region of a few tens of milliseconds), started a second before the region."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("sw_thermal_slowdown", 0x20), ("hw_thermal_slowdown", 0x40), ("hw_power_brake_slowdown", 0x80),
+               ("sw_power_cap", 0x4))
 
-    def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+    def __init__(self, torch_device_index):
+        self.rows, self.stop_flag, self.thread, self.h, self.nv = [], False, None, None, None
+        try:
+            import pynvml as nv
+            import torch
+
+            nv.nvmlInit()
+            try:
+                uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+                self.h = nv.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001 -- older torch / NVML: fall back to the ordinal
+                self.h = nv.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.nv = nv
+        except Exception as e:  # noqa: BLE001
+            self.err = repr(e)
+
+    def _poll(self):
+        nv, h = self.nv, self.h
+        while not self.stop_flag:
+            try:
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except AttributeError:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.rows.append((time.time(), nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0, int(reasons)))
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(0.0008)
 
     def start(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.idx)],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._read, daemon=True).start()
-        except OSError:
-            self.proc = None
-
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
+        if self.nv is None:
+            return
+        self.thread = threading.Thread(target=self._poll, daemon=True)
+        self.thread.start()
 
     def stop(self, t0, t1):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 8] or [r for _, r in self.rows if len(r) >= 8]
+        if self.nv is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.thread.join(timeout=1.0)
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        where = "timed region"
+        if not rows:  # region shorter than one polling interval: the samples closest to it
+            rows, where = [r for r in self.rows if t0 - 0.05 <= r[0] <= t1 + 0.05], "timed region +- 50 ms"
         if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
-        sm = sorted(float(r[1]) for r in rows)
-        reasons = [n for i, n in ((4, "hw_slowdown"), (5, "hw_thermal_slowdown"), (6, "sw_thermal_slowdown"), (7, "sw_power_cap"))
-                   if any(r[i].lower().startswith("active") for r in rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "power_w_max": max(float(r[3]) for r in rows),
-                "samples": len(rows), "reasons": reasons}
+        sm = sorted(r[1] for r in rows)
+        mask = 0
+        for r in rows:
+            mask |= r[3]
+        return {"sm_mhz": float(sm[len(sm) // 2]), "sm_max_mhz": float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM)),
+                "power_w_max": max(r[2] for r in rows), "samples": len(rows), "sampled": where + " (NVML, ~1 ms period)",
+                "reasons": [name for name, bit in self.REASONS if mask & bit]}
+
+
+def workload_config(desc, B, n):
+    """The workload-defining part of `config`, identical in both arms (the driver compares the two lines)."""
+    return {"workload": desc, "envs_per_gpu": B, "num_simulations": n, "directed_exploration": True, "beta": "linspace(0,1,B)",
+            "l2": "GPU arm: flushed between timed steps (256 MiB write); CPU arm: not applicable"}
 
 
 def measured_peaks():
@@ -149,6 +181,10 @@ def cpu_baseline(kind, kw, n, gamma, budget_s=12.0):
 
 
 def run_reference(args, kind, kw, B, n, gamma, desc):
+    """The reference's CPU implementation of the path (the C/OpenMP restatement: JAX / emctx / pgx are not installable here), all host
+    threads, on THIS workload at FULL size: every step searches all B envs (the same config as the GPU arm).  At ~1.4 k env-steps/s
+    on 16 cores a C2 step takes ~3 s, so K + W steps stay within a few minutes; only if a probe shows that the whole run would take
+    longer than ~6 minutes is the per-step batch cut (and `config.envs_per_gpu` then says so)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -158,8 +194,8 @@ def run_reference(args, kind, kw, B, n, gamma, desc):
     cores = O.set_threads(os.cpu_count() or 1)
     probe_B = max(cores * 4, 32)
     t = oracle_step_time(kind, kw, n, gamma, probe_B, seed=1)
-    per_step_budget = min(6.0, 150.0 / max(args.steps + args.warmup, 1))
-    B_sample = int(min(B, max(cores, probe_B * per_step_budget / max(t, 1e-3))))
+    est = t / probe_B * B * (args.steps + args.warmup)
+    B_sample = B if est <= 360.0 else max(cores, int(B * 360.0 / est) // cores * cores)
     for _ in range(args.warmup):
         oracle_step_time(kind, kw, n, gamma, B_sample, seed=3)
     t0 = time.perf_counter()
@@ -169,8 +205,9 @@ def run_reference(args, kind, kw, B, n, gamma, desc):
     value = B_sample * args.steps / dt
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": desc, "envs_per_step_sample": B_sample, "num_simulations": n,
-                                            "note": "CPU restatement of the reference (oracle/eaz_oracle.c), not JAX: jax/emctx/pgx are not installable here"},
+            "data": "synthetic", "config": workload_config(desc, B_sample, n),
+            "notes": {"arm": "CPU restatement of the reference (oracle/eaz_oracle.c, OpenMP over envs), not JAX: jax/emctx/pgx are not installable here",
+                      "full_batch": B_sample == B},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": f"{B_sample} envs per step x {args.steps} steps ({n} simulations each)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -209,7 +246,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
 
     # shard = this rank's envs (weak scaling: B per GPU fixed); directed exploration with beta = linspace(0,1,B) (UBE on)
     runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=100 + rank,
-                            use_graph=not args.no_graph, fused_root=not args.no_fused_root, streams=args.streams)
+                            use_graph=not args.no_graph, fused_root=not args.no_fused_root, streams=args.streams, device_noise=True)
     gen = torch.Generator(device=dev).manual_seed(7 + rank)
     states = ops.env_init(env, B, task_ids=torch.ones(B, dtype=torch.int32, device=dev) if kind == "subleq" else None, device=dev)
     A = env.num_actions
@@ -222,14 +259,37 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
             states[k] = torch.where(m, nxt[k], states[k]).contiguous()
 
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    gather_buf = torch.empty((world, B, 4), dtype=torch.int32, device=dev) if world > 1 else None
+    # Trajectory all-gather into the replay buffer: like the reference, which gathers ONCE per selfplay() scan of
+    # selfplay_steps steps (main.py:383-385), every step packs its 16-byte-per-env record into a [T,B,4] scan buffer (one small
+    # kernel) and the all-gather of a finished scan runs on a side stream under the next scan's searches (double-buffered).
+    T = args.param_refresh
+    scan = [torch.empty((T, B, 4), dtype=torch.int32, device=dev) for _ in range(2)]
+    gathered = [torch.empty((world, T, B, 4), dtype=torch.int32, device=dev) for _ in range(2)] if world > 1 else None
+    side = torch.cuda.Stream(device=dev) if world > 1 else None
+    gather_done = [None, None]
+    tick = [0]
 
     def one_step(st):
+        i = tick[0]
+        buf, row = (i // T) & 1, i % T
+        if world > 1 and row == 0 and gather_done[buf] is not None:
+            torch.cuda.current_stream().wait_event(gather_done[buf])  # the gather that last read this scan buffer has finished
         st, out = runner.step(st)
-        if world > 1:  # trajectory all-gather into the replay buffer (compact: action, reward bits, flags, state)
-            traj = torch.stack([out.action, st["rewards"][:, 0].view(torch.int32), st["terminated"].to(torch.int32), st["step_count"]], 1).contiguous()
-            dist.all_gather_into_tensor(gather_buf.view(-1), traj.view(-1))
+        runner.trajectory(st, out, scan[buf][row])
+        if world > 1 and row == T - 1:
+            ready = torch.cuda.Event()
+            ready.record()
+            side.wait_event(ready)
+            with torch.cuda.stream(side):
+                dist.all_gather_into_tensor(gathered[buf].view(-1), scan[buf].view(-1))
+                gather_done[buf] = torch.cuda.Event()
+                gather_done[buf].record()
+        tick[0] = i + 1
         return st, out
+
+    def join_gathers():
+        if world > 1:
+            torch.cuda.current_stream().wait_stream(side)
 
     for _ in range(max(args.warmup, 3)):
         states, _ = one_step(states)
@@ -241,7 +301,10 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-        time.sleep(0.25)
+    for k in range(40):  # keep the GPU under this workload's load before the region, so that the sampled clocks are the loaded ones
+        states, _ = one_step(states)
+        if k % 8 == 7:
+            torch.cuda.synchronize()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     if world > 1:
         dist.barrier()
@@ -254,11 +317,15 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         ev[i][0].record()
         states, out = one_step(states)
         ev[i][1].record()
+    tail = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+    tail[0].record()
+    join_gathers()  # any all-gather still in flight is part of the job: its non-overlapped remainder is timed
+    tail[1].record()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_wall1 = time.time()
-    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    ms_total = sum(a.elapsed_time(b) for a, b in ev) + tail[0].elapsed_time(tail[1])
     clocks = sampler.stop(t_wall0, t_wall1) if rank == 0 else None
     if world > 1:
         t = torch.tensor([ms_total], device=dev)
@@ -292,6 +359,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
             d2h = sum(v.numel() * v.element_size() for v in host_out.values()) + sum(r.numel() * r.element_size() for r in res)
         for hr, r in zip(host_res, res):
             hr.copy_(r, non_blocking=True)
+        join_gathers()
         b.record()
         torch.cuda.synchronize()
         if i >= 2:
@@ -324,18 +392,23 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         tree_bytes = V * (32 * A + 68) + B * n * (2 * S + 4 * A + 44)
         io_bytes = B * (8 * A + A + 16 + S) + B * (4 + 20 * A + 8)
         tree_ms = prof["select"][0] + prof["expand_backward"][0] + prof["env_step"][0]
+        persistent = kind == "deepsea" and args.mlp_mode == 1 and prof["select"][1] == 1  # ONE launch ran all simulations (psearch.cuh)
         hbm_peak, tf_peak, which = measured_peaks()
         D, H = netp["in_dim"], 256
         l1 = 0 if kind == "deepsea" else 2 * D * H  # one-hot DeepSea layer 1 is a row gather
         flops_fwd = 3 * (l1 + 2 * H * H) + 2 * (2 * H) + 2 * H * A  # 3 heads evaluated per node (value, UBE, one policy head)
-        mlp_ms = prof["network"][0]
+        mlp_ms = prof["network"][0] + (tree_ms if persistent else 0.0)  # (persistent: the network runs inside the same kernel)
         tensor_kernel = "mlp_gather_kernel" if kind == "deepsea" else "mlp_tensor_kernel"  # one-hot rows: mlp_gather.cu
+        if persistent:
+            tensor_kernel = "ds_search_kernel"
         total_ms = sum(v[0] for v in prof.values())
-        dominant = "network" if mlp_ms >= tree_ms else "tree"
+        dominant = "tree" if persistent else ("network" if mlp_ms >= tree_ms else "tree")
         tree_gbs = (tree_bytes + io_bytes) / (tree_ms * 1e-3) / 1e9
         mlp_tfs = flops_fwd * B * n / (mlp_ms * 1e-3) / 1e12
         tree_obj = {"bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tree_gbs / hbm_peak, "traffic": None,
-                    "kernels": "tree_step_kernel (expand + backward + action refresh + descent)" + (" + subleq_tree_step_kernel" if kind == "subleq" else ""),
+                    "kernels": ("ds_search_kernel (persistent: all simulations of a 128-tree tile in one 4-CTA cluster -- tree steps, DeepSea transition AND "
+                                "the tcgen05 network evaluation; its whole duration is charged to the tree bytes)") if persistent else
+                               ("tree_step_kernel (expand + backward + action refresh + descent)" + (" + subleq_tree_step_kernel" if kind == "subleq" else "")),
                     "algorithmic_bytes_per_search": tree_bytes + io_bytes, "ms_per_search": tree_ms,
                     "avg_launch_us": 1e3 * tree_ms / max(prof["select"][1] + prof["expand_backward"][1] + prof["env_step"][1], 1),
                     "edge_traversals": V, "peak_source": which}
@@ -343,16 +416,21 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
                    "kernels": "mlp_exact_kernel (fp32 FMA chains, bit-exact mode)" if args.mlp_mode == 0 else f"{tensor_kernel} (tcgen05)",
                    "flops_per_search": flops_fwd * B * n, "ms_per_search": mlp_ms, "avg_launch_us": 1e3 * mlp_ms / max(prof["network"][1], 1),
                    "peak_source": which}
-        try:  # DRAM traffic per launch from the committed ncu --set full capture (profiles/r1_traffic.json)
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json"))).get(args.workload, {})
-            tree_obj["traffic"] = traffic.get("tree_step_kernel")
+        try:  # DRAM traffic per launch from the committed ncu --set full captures (profiles/r2_traffic.json, r1_traffic.json)
+            traffic = {}
+            for name in ("r1_traffic.json", "r2_traffic.json"):
+                pth = os.path.join(ROOT, "profiles", name)
+                if os.path.exists(pth):
+                    traffic.update(json.load(open(pth)).get(args.workload, {}))
+            tree_obj["traffic"] = traffic.get("ds_search_kernel" if persistent else "tree_step_kernel")
             mlp_obj["traffic"] = traffic.get(tensor_kernel) if args.mlp_mode == 1 else None
         except (OSError, ValueError):
             pass
         roofline = dict(mlp_obj if dominant == "network" else tree_obj)
-        roofline["timing"] = ("per-launch CUDA events in a separate profiled pass of the same search on the same stream (eaz_search_gumbel_profiled): the "
-                              "events serialise the PDL chain and the sub-batch streams, so these durations are upper bounds -- in the timed region the tree "
-                              "kernel stages its data under the network kernel and sub-batches overlap (value / ms_per_step is the overlapped time)")
+        roofline["timing"] = ("CUDA events around every launch in a separate profiled pass of the same search on the same stream (eaz_search_gumbel_profiled)" +
+                              ("; the persistent kernel is ONE launch per search, so its event time is its real duration" if persistent else
+                               ": the events serialise the PDL chain and the sub-batch streams, so these durations are upper bounds -- in the timed region the "
+                               "tree kernel stages its data under the network kernel and sub-batches overlap (value / ms_per_step is the overlapped time)"))
         roofline["dominant"] = dominant
         roofline["share_of_search_time"] = (mlp_ms if dominant == "network" else tree_ms) / total_ms
         roofline["other"] = tree_obj if dominant == "network" else mlp_obj
@@ -370,14 +448,15 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
-            "config": {"workload": desc, "envs_per_gpu": B, "num_simulations": n, "mlp_mode": "exact_fp32" if args.mlp_mode == 0 else "tensor",
-                       "l2": "flushed between timed steps (256 MiB write)", "cuda_graph": not args.no_graph, "fused_root": not args.no_fused_root, "directed_exploration": True, "beta": "linspace(0,1,B)",
-                       "streams": args.streams,
-                       "param_refresh": f"weight images / novelty / seq-halving tables rebuilt every {args.param_refresh} steps (selfplay_steps of the reference, config.py:37,105), reused in between",
-                       "multi_gpu": "envs sharded per rank, params broadcast once, compact trajectory all-gather per step" if world > 1 else "single GPU"},
+            "config": workload_config(desc, B, n),
+            "notes": {"mlp_mode": "exact_fp32" if args.mlp_mode == 0 else "tensor", "cuda_graph": not args.no_graph, "fused_root": not args.no_fused_root,
+                      "streams": args.streams, "root_noise": "drawn inside the search (counter-based stream)",
+                      "param_refresh": f"weight images / novelty / seq-halving tables rebuilt every {args.param_refresh} steps (selfplay_steps of the reference, config.py:37,105), reused in between",
+                      "multi_gpu": (f"envs sharded per rank, params broadcast once, per-step trajectory records packed into a [{args.param_refresh},B,4] scan "
+                                    "buffer and all-gathered once per scan on a side stream (main.py:383-385)") if world > 1 else "single GPU"},
             "simulations_per_s": value * n, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": n_full * runner.launches_per_step + (args.steps - n_full) * runner.launches_per_step_reuse, "roofline": roofline,
+            "gpu_launches": n_full * runner.launches_per_step + (args.steps - n_full) * runner.launches_per_step_reuse + args.steps, "roofline": roofline,
             "cpu_baseline": cpu}
     emit(line)
     if world > 1:

@@ -19,7 +19,7 @@ _lib = None
 # every symbol include/eaz_b200.h declares
 EXPORTS = [
     "eaz_abi_version", "eaz_last_error",
-    "eaz_env_init", "eaz_env_step", "eaz_env_observe", "eaz_env_compact", "eaz_env_uncompact",
+    "eaz_env_init", "eaz_env_step", "eaz_env_observe", "eaz_env_compact", "eaz_env_uncompact", "eaz_trajectory_pack",
     "eaz_env_num_actions", "eaz_env_obs_dim", "eaz_env_obs_cols", "eaz_env_hash_dim", "eaz_env_compact_bytes",
     "eaz_subleq_test_cases",
     "eaz_xxhash_indices", "eaz_hash_lookup", "eaz_hash_update",

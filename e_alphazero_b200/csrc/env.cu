@@ -201,6 +201,25 @@ __global__ void subleq_observe_kernel(EnvDesc env, StateSoA s, uint8_t* __restri
 
 using namespace eaz;
 
+namespace eaz {
+// One 16-byte trajectory record per env for the replay buffer's wire format (main.py:383-385): the chosen action, the
+// reward bits, terminated | truncated << 8 | solved << 16, and the first word of the compact state (DeepSea: the whole state;
+// Subleq: step count | task << 16 -- the memory image travels separately when the caller stores full states).
+__global__ void trajectory_pack_kernel(EnvDesc env, StateSoA s, const int32_t* __restrict__ action, int4* __restrict__ out, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const int term = s.terminated[b] != 0, trunc = s.truncated ? (s.truncated[b] != 0) : 0;
+  int flags = term | (trunc << 8), word;
+  if (env.kind == EAZ_ENV_DEEPSEA) {
+    word = (int)ds_pack(s.step_count[b], s.col[b], term, trunc);
+  } else {
+    flags |= (s.solved[b] != 0) << 16;
+    word = (s.step_count[b] & 0xffff) | (s.task[b] << 16);
+  }
+  out[b] = make_int4(action[b], __float_as_int(s.rewards[b]), flags, word);
+}
+}  // namespace eaz
+
 extern "C" {
 
 int eaz_abi_version(void) { return EAZ_ABI_VERSION; }
@@ -300,6 +319,17 @@ int eaz_env_step(const eaz_env* env, eaz_state* state, const int32_t* action, in
   else subleq_kernel<<<ceil_div(B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, 0, st>>>(d, s, action, task_ids, auto_reset ? 2 : 1, B);
   EAZ_CHECK_LAUNCH("eaz_env_step");
   if (state->observation) return eaz_env_observe(env, state, state->observation, B, stream);
+  return 0;
+}
+
+int eaz_trajectory_pack(const eaz_env* env, const eaz_state* state, const int32_t* action, int32_t* out, int32_t B, void* stream) {
+  EnvDesc d;
+  if (int rc = make_env_desc(env, &d)) return rc;
+  if (int rc = check_state(d, state)) return rc;
+  EAZ_CHECK_ARG(action != nullptr && out != nullptr && B >= 0, "eaz_trajectory_pack: NULL action / out or negative batch");
+  if (B == 0) return 0;
+  trajectory_pack_kernel<<<ceil_div(B, 256), 256, 0, (cudaStream_t)stream>>>(d, soa_of(state), action, reinterpret_cast<int4*>(out), B);
+  EAZ_CHECK_LAUNCH("trajectory_pack_kernel");
   return 0;
 }
 

@@ -36,12 +36,12 @@ constexpr int kCtas = 4;              // CTAs per cluster
 constexpr int kSlots = kTile / kCtas; // trees per CTA
 constexpr int kHeads = 3;             // CTAs 0..2 run one head each
 // Warp roles, aligned to warpgroups (4 warps) because the register file is re-split per warpgroup with setmaxnreg: the kernel starts
-// with 72 registers per thread (65536 / 896); the tree warps -- whose spills would go to an L1 that the 200 KB of shared memory leave
-// almost no room for -- then grow to kRegsTree, paid for by the gather warps and the control warpgroup shrinking.
+// with 72 registers per thread (65536 / 896); the gather warps, which hold a whole A chunk (16 x 16 bytes per thread) in registers, then
+// grow to kRegsGather, paid for by the control warpgroup shrinking (the tree warps ran no faster with 88 than with 72).
 constexpr int kTWarps = 16, kGWarps = 8;
 constexpr int kWarpTree0 = 0, kWarpGather0 = kTWarps, kWarpMma = kTWarps + kGWarps, kWarpCopy = kWarpMma + 1;
 constexpr int kThreads = (kTWarps + kGWarps + 4) * 32;  // 896: 4 tree warpgroups, 2 gather warpgroups, 1 control warpgroup (MMA, copy, 2 idle)
-constexpr int kRegsTree = 88, kRegsGather = 56, kRegsCtrl = 32;  // 16 * 88 + 8 * 56 + 4 * 32 = 1984 <= 2048 register rows of 32
+constexpr int kRegsTree = 72, kRegsGather = 88, kRegsCtrl = 32;  // the increase (8 warps x 16) must fit what the control warpgroup releases (4 x 40): the pool is per CTA
 template <int N>
 __device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -72,7 +72,10 @@ constexpr int kMiscWords = 12;        // [0] considered visit, [8..8+A) leaf pri
 constexpr int kTreeWords = kEdgeWords + kBackWords + kRootWords + kMiscWords;  // + ncap state words + ncap/2 next words
 
 struct Shared {
-  uint64_t full_a[kStages], full_b[kStages], empty[kStages];
+  uint64_t full_a[kStages], full_b[kStages];
+  // "stage consumed" barriers, split by the parity of the stage's use count: two gather warps alternate on a stage, so each of them
+  // observes only every other use -- on ONE barrier it could not tell phase u - 1 from phase u - 3 (same parity)
+  uint64_t empty[2][kStages];
   uint64_t acc_done;    // the evaluation's MMAs are complete (tcgen05.commit)
   uint64_t cells_full;  // transaction barrier: kTile * 4 bytes of st.async per phase -- every tree of the tile has published its leaf cell
   uint64_t out_full;    // transaction barrier: the three heads' outputs for this CTA's kSlots trees have landed
@@ -85,8 +88,11 @@ struct Shared {
 };
 
 __host__ __device__ inline int tree_words(int ncap) { return kTreeWords + ncap + ncap / 2; }  // ncap even
-__host__ __device__ inline size_t smem_bytes(int ncap) {
-  return 1024 + (size_t)kStages * (kAStage + kBStage) + ((sizeof(Shared) + 15) & ~(size_t)15) + (size_t)kSlots * tree_words(ncap) * 4;
+constexpr int kAmapMax = 16384;  // the DeepSea action map (N x N bytes) is mirrored in shared memory when it fits (N <= 128)
+__host__ __device__ inline int amap_bytes(int size) { return size * size <= kAmapMax ? ((size * size + 15) & ~15) : 0; }
+__host__ __device__ inline size_t smem_bytes(int ncap, int size) {
+  return 1024 + (size_t)kStages * (kAStage + kBStage) + ((sizeof(Shared) + 15) & ~(size_t)15) + (size_t)kSlots * tree_words(ncap) * 4 +
+         (size_t)amap_bytes(size);
 }
 
 // ---- cluster / DSMEM plumbing
@@ -187,6 +193,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   uint8_t* sB = smem + kStages * kAStage;
   Shared* sh = reinterpret_cast<Shared*>(sB + kStages * kBStage);
   uint32_t* tree_smem = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sh) + ((sizeof(Shared) + 15) & ~(size_t)15));
+  uint8_t* const s_amap = reinterpret_cast<uint8_t*>(tree_smem + (size_t)kSlots * tree_words(a.ncap));  // mirror of env.action_map (or unused)
+  const int amap_n = a.env.action_map ? amap_bytes(a.env.size) : 0;
   const Tree& t = a.t;
   const SearchParams& sp = a.sp;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -202,9 +210,10 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   // ------------------------------------------------------------------ prologue
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sh->full_a[s], 2);  // one elected arrive per gather warp of the stage's group
+      mbar_init(&sh->full_a[s], 1);  // one elected arrive by the chunk's gather warp
       mbar_init(&sh->full_b[s], 1);
-      mbar_init(&sh->empty[s], 1);
+      mbar_init(&sh->empty[0][s], 1);
+      mbar_init(&sh->empty[1][s], 1);
     }
     mbar_init(&sh->acc_done, 1);
     mbar_init(&sh->cells_full, 1);
@@ -220,6 +229,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
     sh->w3t[0][j] = __ldg(a.w3[rank] + (size_t)j * nout);
     sh->w3t[1][j] = nout > 1 ? __ldg(a.w3[rank] + (size_t)j * nout + 1) : 0.0f;
   }
+  if (amap_n)
+    for (int i = threadIdx.x; i < a.env.size * a.env.size; i += kThreads) s_amap[i] = a.env.action_map[i];
   if (head_cta && warp == kWarpMma) {
     tmem_alloc(&sh->tmem_base, kH);
     tmem_relinquish();
@@ -237,8 +248,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       const int total = n * kChunks;
 #pragma unroll 1
       for (int g = 0; g < total; ++g) {
-        const int s = g % kStages;
-        if (g >= kStages) mbar_wait(&sh->empty[s], ((g / kStages) & 1) ^ 1);
+        const int s = g % kStages, u = g / kStages;  // u-th use of stage s: the (u - 1)-th must have been consumed
+        if (u > 0) mbar_wait(&sh->empty[(u - 1) & 1][s], ((u - 1) >> 1) & 1);
         mbar_arrive_expect_tx(&sh->full_b[s], (uint32_t)kBStage);
         bulk_g2s(sB + s * kBStage, img + (size_t)(g % kChunks) * kBStage, kBStage, &sh->full_b[s]);
       }
@@ -261,8 +272,18 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
 #pragma unroll 1
       for (int g = 0; g < total; ++g) {
         const int s = g % kStages, ph = (g / kStages) & 1, c = g % kChunks;
-        mbar_wait(&sh->full_a[s], ph);  // (all 32 lanes: uniform control flow)
-        mbar_wait(&sh->full_b[s], ph);
+        // The issue of a tcgen05.mma blocks while the tensor pipe's queue is full, so the ~200 cycles of the two waits would be added to
+        // every chunk's 384 cycles of tensor work: wait for chunk g + 1 BEFORE issuing chunk g (within one evaluation: the first chunk
+        // of the next evaluation only arrives after this one's outputs).
+        if (c == 0) {
+          mbar_wait(&sh->full_a[s], ph);  // (all 32 lanes: uniform control flow)
+          mbar_wait(&sh->full_b[s], ph);
+        }
+        if (c + 1 < kChunks) {
+          const int s1 = (g + 1) % kStages, ph1 = ((g + 1) / kStages) & 1;
+          mbar_wait(&sh->full_a[s1], ph1);
+          mbar_wait(&sh->full_b[s1], ph1);
+        }
         tc_fence_after();
         if (lane == 0) trc.chunk(g / kChunks, c, 0);
         const uint32_t al = a_base + (uint32_t)((s * kAStage) >> 4), bl = b_base + (uint32_t)((s * kBStage) >> 4);
@@ -270,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
           mma_f16(tmem, mk(al), mk(bl), idesc, c != 0);
           mma_f16(tmem, mk(al), mk(bl + (kBHalf >> 4)), idesc, 1);
           mma_f16(tmem, mk(al + (kAHalf >> 4)), mk(bl), idesc, 1);
-          mma_commit(&sh->empty[s]);
+          mma_commit(&sh->empty[(g / kStages) & 1][s]);
           if (c == kChunks - 1) mma_commit(&sh->acc_done);
         }
         __syncwarp();
@@ -279,26 +300,19 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   } else if (warp > kWarpCopy) {
     regs_dec<kRegsCtrl>();  // (the two spare warps of the control warpgroup)
   } else if (warp >= kWarpGather0) {
-    regs_dec<kRegsGather>();
     // ================================================================ gather warps: layer 1 = copy of the leaf cells' h1 rows into the A ring
-    // Four groups of two warps; group g owns ring stage g and fills it with chunks g, g + 4, g + 8, g + 12 of every evaluation.  The
-    // proxy fence that publishes a chunk to the tensor core is a MEMBAR, which also waits for the warp's own loads in flight; with one
-    // chunk in flight PER GROUP the four groups' L2 round trips overlap each other instead of serialising (one software-prefetching
-    // group would pay one round trip per chunk: measured 1400 cycles per chunk).
+    // EIGHT independent single-warp producers: warp g fills chunks g and g + 8 of every evaluation (ring stage = chunk % 4), all 128
+    // rows x (hi, lo) x 32 bytes of a chunk = 16 LDG.128 per thread.  The proxy fence that publishes a chunk to the tensor core is a
+    // MEMBAR, which also waits for the warp's own loads in flight, so a producer cannot usefully prefetch past its current chunk; with
+    // eight producers the L2 round trips of eight chunks overlap instead (one software-prefetching producer group: 1400 cycles per
+    // chunk; four two-warp producers: 520; the tensor work of a chunk is 384).
+    regs_inc<kRegsGather>();
     if (head_cta) {
       const int gw = warp - kWarpGather0;
-      const int grp = gw >> 1;                        // ring stage
-      const int gt = (gw & 1) * 32 + lane;            // thread within the group (64)
-      const int piece = gt & 1;                       // 16-byte piece of the 32 bytes a row contributes to a chunk (per hi / lo part)
-      const int r0 = gt >> 1;                         // rows r0, r0 + 32, r0 + 64, r0 + 96
-      const uint8_t* table = a.h1[rank];
-      uint8_t* const dst = sA + grp * kAStage;
-      uint32_t doff[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = r0 + 32 * j;
-        doff[j] = (uint32_t)((r >> 3) * kSBO + piece * kCoreBytes + (r & 7) * 16);
-      }
+      const int piece = lane & 1;                     // 16-byte piece of the 32 bytes a row contributes to a chunk (per hi / lo part)
+      const int r0 = lane >> 1;                       // rows r0 + 16 j, j = 0..7
+      const uint8_t* const table = a.h1[rank] + piece * 16;
+      const uint32_t doff0 = (uint32_t)((r0 >> 3) * kSBO + piece * kCoreBytes + (r0 & 7) * 16);  // + j * 2 * kSBO per row step of 16
 #pragma unroll 1
       for (int it = 0; it < n; ++it) {
         warp_wait(&sh->cells_full, it & 1, lane);
@@ -306,39 +320,42 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
           trc.stamp(it, 0);
           if (it + 1 < n) mbar_arrive_expect_tx(&sh->cells_full, kTile * 4);  // arm the next phase (nobody publishes before this evaluation's outputs)
         }
-        const uint8_t* src[4];
+        int cellv[8];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) src[j] = table + (size_t)sh->cells[r0 + 32 * j] * (4 * kH) + piece * 16;
+        for (int j = 0; j < 8; ++j) cellv[j] = sh->cells[r0 + 16 * j];
 #pragma unroll 1
-        for (int c = grp; c < kChunks; c += kStages) {
-          uint4 vh[4], vl[4];
+        for (int c = gw; c < kChunks; c += kGWarps) {
+          uint4 vh[8], vl[8];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            vh[j] = __ldg(reinterpret_cast<const uint4*>(src[j] + c * (kCK * 2)));
-            vl[j] = __ldg(reinterpret_cast<const uint4*>(src[j] + 2 * kH + c * (kCK * 2)));
+          for (int j = 0; j < 8; ++j) {
+            const uint8_t* src = table + (size_t)cellv[j] * (4 * kH) + c * (kCK * 2);
+            vh[j] = __ldg(reinterpret_cast<const uint4*>(src));
+            vl[j] = __ldg(reinterpret_cast<const uint4*>(src + 2 * kH));
           }
-          const bool gtr = (gw & 1) == 0 && lane == 0;
-          if (gtr) trc.gather(it, c, 0);  // loads issued
+          const int stage = c % kStages;
           const int use = it * (kChunks / kStages) + c / kStages;  // how often this stage has been filled before
-          if (use > 0) warp_wait(&sh->empty[grp], (use & 1) ^ 1, lane);
+          const bool gtr = lane == 0;
+          if (gtr) trc.gather(it, c, 0);  // loads issued
+          if (use > 0) warp_wait(&sh->empty[(use - 1) & 1][stage], ((use - 1) >> 1) & 1, lane);
           if (gtr) trc.gather(it, c, 1);  // stage free
+          uint8_t* const dst = sA + stage * kAStage + doff0;
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            *reinterpret_cast<uint4*>(dst + doff[j]) = vh[j];
-            *reinterpret_cast<uint4*>(dst + kAHalf + doff[j]) = vl[j];
+          for (int j = 0; j < 8; ++j) {
+            *reinterpret_cast<uint4*>(dst + j * 2 * kSBO) = vh[j];
+            *reinterpret_cast<uint4*>(dst + kAHalf + j * 2 * kSBO) = vl[j];
           }
           if (gtr) trc.gather(it, c, 2);  // data arrived and stored
           fence_proxy_async();
           if (gtr) trc.gather(it, c, 3);  // fenced
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sh->full_a[grp]);
+          if (lane == 0) mbar_arrive(&sh->full_a[stage]);
         }
         if (gw == 0 && lane == 0) trc.stamp(it, 1);
       }
     }
   } else {
     // ================================================================ tree warps: two trees each (16 lanes per tree)
-    regs_inc<kRegsTree>();
+    // (the tree warps keep the launch allocation of 72)
     const int tw = warp - kWarpTree0;
     const int hl = lane & (kW - 1), hbase = lane & kW, sub = lane >> 4;
     const int slot = 2 * tw + sub;
@@ -359,6 +376,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
     const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
     uint32_t* const st_global = reinterpret_cast<uint32_t*>(t.states);
     const bool tstamp = tw == 0;  // (with trc.buf: cluster 0, CTA 0)
+    const float b3_0 = head_cta ? __ldg(a.b3[rank]) : 0.0f, b3_1 = (head_cta && a.nout[rank] > 1) ? __ldg(a.b3[rank] + 1) : 0.0f;
 
     // this tree's pending simulation: path length, leaf, reward / terminal flag of the leaf's state, its observation cell
     int L = 0, leaf = 0, cell = 0;
@@ -470,11 +488,14 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
         const int q = warp & 3, cg = tw >> 2;  // a warp reads the TMEM lane quarter (warp id % 4); four warps share a quarter
         const int row = 32 * q + lane;
         const int nout = a.nout[rank];
+        int seen = 0;  // novelty bit of the row's cell (fully_connected.py:83-90), fetched while the MMAs run
+        if (cg == 0 && a.head_id[rank] == EAZ_HEAD_UBE) {
+          warp_wait(&sh->cells_full, it & 1, lane);
+          seen = a.ds_seen[sh->cells[row]];
+        }
         warp_wait(&sh->acc_done, it & 1, lane);
         tc_fence_after();
         if (tstamp) trc.stamp(it, 2);
-        int seen = 0;  // novelty bit of the row's cell (fully_connected.py:83-90); cells[] is complete once the accumulator is
-        if (cg == 0 && a.head_id[rank] == EAZ_HEAD_UBE) seen = a.ds_seen[sh->cells[row]];
         const uint32_t taddr = sh->tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * cg);
         float y0 = 0.0f, y1 = 0.0f;
         uint32_t ra[16], rb[16];
@@ -520,10 +541,10 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
           const uint32_t obar = map_to_cta(&sh->out_full, owner);
           const int hid = a.head_id[rank];
           if (hid >= EAZ_HEAD_EXPLOIT) {
-            st_async_u32(map_to_cta(&sh->out_logits[lane][0], owner), __float_as_uint(__fadd_rn(y0, __ldg(a.b3[rank]))), obar);
-            if (nout > 1) st_async_u32(map_to_cta(&sh->out_logits[lane][1], owner), __float_as_uint(__fadd_rn(y1, __ldg(a.b3[rank] + 1))), obar);
+            st_async_u32(map_to_cta(&sh->out_logits[lane][0], owner), __float_as_uint(__fadd_rn(y0, b3_0)), obar);
+            if (nout > 1) st_async_u32(map_to_cta(&sh->out_logits[lane][1], owner), __float_as_uint(__fadd_rn(y1, b3_1)), obar);
           } else {
-            const float y = __fadd_rn(y0, __ldg(a.b3[rank]));
+            const float y = __fadd_rn(y0, b3_0);
             if (hid == EAZ_HEAD_VALUE) {
               st_async_u32(map_to_cta(&sh->out_value[lane], owner), __float_as_uint(eaz_tanh(y)), obar);
             } else {  // fully_connected.py:92-96
@@ -566,10 +587,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       const unsigned lslot = (unsigned)leaf * uB + ub;
       const float lg = (in_batch && hl < t.A) ? sh->out_logits[slot][hl] : -INFINITY;
       const float nv = in_batch ? sh->out_value[slot] : 0.0f, nu = in_batch ? sh->out_ube[slot] : 0.0f;
-      float m = lg;
-#pragma unroll
-      for (int s = kW / 2; s > 0; s >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, s));  // context.py:135 (within the tree's 16 lanes)
-      const float pl_leaf = __fsub_rn(lg, m);                                                  // legal_action_mask is all True (:137)
+      const float m = __shfl_sync(0xffffffffu, group_max<kG>(lg), hbase);  // context.py:135: max over the A <= kG logit lanes (the rest hold -inf)
+      const float pl_leaf = __fsub_rn(lg, m);                              // legal_action_mask is all True (:137)
       if (in_batch && hl < t.A) {
         t.edges[(size_t)(lslot * uA + hl)].pl = pl_leaf;
         s_misc[8 + hl] = __float_as_uint(pl_leaf);
@@ -743,7 +762,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
         if (in_batch) {
           const int new_leaf = child < 0 ? sim + 1 : child;  // search.py: node first expanded on simulation i gets index i+1
           float rw;
-          const uint32_t ns = deepsea_step(s_state[node], action, a.env.size, a.env.action_map, &rw);  // context.py:127 env.step fused here
+          const uint32_t ns = deepsea_step(s_state[node], action, a.env.size, amap_n ? s_amap : a.env.action_map, &rw);  // context.py:127 env.step fused here
           L = depth;
           leaf = new_leaf;
           reward = rw;

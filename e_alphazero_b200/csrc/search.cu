@@ -77,6 +77,7 @@ struct Tree {
   int2* path;     // [max_depth][B] (node, action) per level of the current descent
   int32_t* path_len;
   int32_t* tile_ctr;  // [2][tiles] completion counters of the tile-flag protocol (common.cuh)
+  uint32_t* draw_ctr;  // [1] number of searches that drew their own root noise on this workspace (counter-based generator)
 };
 
 struct Layout {
@@ -114,6 +115,7 @@ static void make_layout(int B, int N, int A, int S, int table_len, int obs_dim, 
   put((size_t)max_depth * B * 8);  // 25 path
   put((size_t)B * 4);              // 26 path_len
   put((size_t)2 * ceil_div(B, kTileRows) * 4);  // 27 tile counters: [tiles] tree done, [tiles] network done
+  put(16);                                      // 28 draw counter of the in-kernel root noise
   L->total = o;
 }
 
@@ -139,6 +141,7 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
   t.path = (int2*)(p + L.off[25]);
   t.path_len = (int32_t*)(p + L.off[26]);
   t.tile_ctr = (int32_t*)(p + L.off[27]);
+  t.draw_ctr = (uint32_t*)(p + L.off[28]);
   return t;
 }
 
@@ -433,7 +436,7 @@ template <int G, int J>
 __global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp, const float* __restrict__ prior_logits,
                                                          const float* __restrict__ value, const float* __restrict__ var,
                                                          const float* __restrict__ gumbel, const uint8_t* __restrict__ invalid,
-                                                         float* __restrict__ out_value, float* __restrict__ out_ube) {
+                                                         float* __restrict__ out_value, float* __restrict__ out_ube, int batch_offset) {
   EAZ_GROUP_PROLOGUE();
   float lg[J];
   float m = -INFINITY;
@@ -450,7 +453,21 @@ __global__ void __launch_bounds__(128) root_init_kernel(Tree t, SearchParams sp,
     const int a = gl + G * j;
     const bool inv = invalid && invalid[(size_t)b * t.A + a];
     t.edges[(size_t)b * t.A + a].pl = inv ? EAZ_F32_MIN : __fsub_rn(lg[j], m);  // _mask_invalid_actions (reanalyze.py:16-29)
-    t.gumbel[(size_t)b * t.A + a] = __fmul_rn(sp.gumbel_scale, gumbel[(size_t)b * t.A + a]);
+    // jax.random.gumbel(gumbel_rng) of mctx policies.py: pre-drawn by the caller, or (gumbel == NULL) drawn here from a counter-based
+    // stream keyed by (noise_seed, draw counter of this workspace, tree, action): u in (0, 1) with 24 bits, g = -log(-log(u))
+    float g;
+    if (gumbel) {
+      g = gumbel[(size_t)b * t.A + a];
+    } else {
+      uint32_t h = sp.noise_seed + EAZ_XX_P1;
+      h = xx_round(h, t.draw_ctr[0]);
+      h = xx_round(h, (uint32_t)(batch_offset + b));
+      h = xx_round(h, (uint32_t)a);
+      h ^= h >> 15; h *= EAZ_XX_P2; h ^= h >> 13; h *= EAZ_XX_P3; h ^= h >> 16;
+      const float u = __fmul_rn(__fadd_rn((float)(h >> 8), 0.5f), 5.9604644775390625e-08f);
+      g = -eaz_log(-eaz_log(u));
+    }
+    t.gumbel[(size_t)b * t.A + a] = __fmul_rn(sp.gumbel_scale, g);
   }
   if (gl == 0) {
     NodeRec r;
@@ -469,26 +486,26 @@ namespace eaz {
 
 // ------------------------------------------------------------------ persistent tile-resident search (psearch.cuh): eligibility + launch
 static unsigned long long* g_ps_trace = nullptr;  // eaz_debug_set_ps_trace
-static bool persistent_eligible(const Tree& t, const SearchParams& sp, const EnvDesc& env, int mlp_mode, const TensorWeights* tw, int* ncap_out) {
+static bool persistent_eligible(int B, int N, int A, int flags, const EnvDesc& env, int mlp_mode, int* ncap_out) {
   static const bool disabled = getenv("EAZ_NO_PERSISTENT") != nullptr;  // measurement knob: the per-simulation launch chain instead
-  if (disabled || tl_prof != nullptr) return false;                    // (the profiled variant times per-launch classes)
-  if (env.kind != EAZ_ENV_DEEPSEA || mlp_mode != EAZ_MLP_TENSOR || !tw || !tw->w2_ck16[0] || t.A > ps::kG) return false;
-  if (sp.flags & EAZ_FLAG_PUCT) return false;  // PUCT selection has no staged form: DIRECT chain
-  if (t.N > 16383) return false;               // 16-bit cached selections
-  const int ncap = (t.N + 1) & ~1;
+  static const int tile_flags = getenv("EAZ_TILE_FLAGS") ? atoi(getenv("EAZ_TILE_FLAGS")) : 0;
+  if (disabled || tile_flags > 0) return false;
+  if (env.kind != EAZ_ENV_DEEPSEA || mlp_mode != EAZ_MLP_TENSOR || A > ps::kG) return false;
+  if (flags & EAZ_FLAG_PUCT) return false;  // PUCT selection has no staged form: DIRECT chain
+  if (N > 16383) return false;              // 16-bit cached selections
+  const int ncap = (N + 1) & ~1;
   int dev = 0, max_optin = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
-  if (ps::smem_bytes(ncap) > (size_t)max_optin) return false;  // trees too large for the shared-memory caches
+  if (ps::smem_bytes(ncap, env.size) > (size_t)max_optin) return false;  // trees too large for the shared-memory caches
   // One wave only: a tile's chain (network -> tree -> network ...) is latency-bound, so a second wave of clusters doubles the search
   // time, while the per-simulation launch chain fills the whole machine with every kernel (measured at DeepSea-100 x 8192 trees =
   // 64 tiles on 33 co-resident clusters: 5.2 ms persistent vs 4.5 ms chain; at 4096 trees = 32 tiles: 1.20 vs 1.29 ms).
   static int max_clusters[32] = {0};  // per device, queried once (idempotent; a race only repeats the query)
   if (dev >= 0 && dev < 32 && max_clusters[dev] == 0) {
-    const size_t smem_max = ps::smem_bytes(212);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(ps::kCtas * 64);
     cfg.blockDim = dim3(ps::kThreads);
-    cfg.dynamicSmemBytes = smem_max <= (size_t)max_optin ? smem_max : (size_t)max_optin;
+    cfg.dynamicSmemBytes = (size_t)max_optin;  // (any eligible shape: one CTA per SM either way)
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = ps::kCtas;
@@ -505,8 +522,8 @@ static bool persistent_eligible(const Tree& t, const SearchParams& sp, const Env
     max_clusters[dev] = nc;
   }
   static const bool any_waves = getenv("EAZ_PERSISTENT_WAVES") != nullptr;  // measurement knob: allow more tiles than co-resident clusters
-  if (!any_waves && (dev < 0 || dev >= 32 || ceil_div(t.B, ps::kTile) > max_clusters[dev])) return false;
-  *ncap_out = ncap;
+  if (!any_waves && (dev < 0 || dev >= 32 || ceil_div(B, ps::kTile) > max_clusters[dev])) return false;
+  if (ncap_out) *ncap_out = ncap;
   return true;
 }
 
@@ -534,7 +551,7 @@ static int launch_persistent(const Tree& t, const SearchParams& sp, const EnvDes
   a.novelty_scale = net.novelty_scale;
   a.ncap = ncap;
   a.trace = g_ps_trace;
-  const size_t smem = ps::smem_bytes(ncap);
+  const size_t smem = ps::smem_bytes(ncap, env.size);
   // (cudaFuncAttributeMaxDynamicSharedMemorySize was raised to the largest eligible size by persistent_eligible)
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(ceil_div(t.B, ps::kTile) * ps::kCtas);
@@ -617,7 +634,7 @@ struct SummaryOut {
 
 template <int G, int J>
 __global__ void __launch_bounds__(128) finalize_kernel(Tree t, SearchParams sp, const float* __restrict__ beta_in,
-                                                        const uint8_t* __restrict__ invalid, SummaryOut out) {
+                                                        const uint8_t* __restrict__ invalid, SummaryOut out, int bump_draw_ctr) {
   EAZ_GROUP_PROLOGUE();
   const float beta = (in_range && beta_in) ? beta_in[b] : 0.0f;
   float gum[J];
@@ -671,6 +688,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(Tree t, SearchParams sp, 
     for (int j = 0; j < J; ++j) x[j] = inval[j] ? EAZ_F32_MIN : __fsub_rn(x[j], m);
     group_softmax<G, J>(x, valid, p);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0 && bump_draw_ctr) t.draw_ctr[0] += 1u;  // (root_init of this search has long finished)
   if (!in_range) return;
   if (gl == 0) {
     out.action[b] = act;
@@ -799,7 +817,7 @@ __global__ void export_tree_kernel(Tree t, TreeOut o) {
 template <int G, int J>
 static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env, const NetDesc& net, const eaz_search_inputs* in,
                       const SummaryOut& so, int mlp_mode, int exploration, const TensorWeights* tw, float* root_out_value, float* root_out_ube,
-                      cudaStream_t st) {
+                      int batch_offset, cudaStream_t st) {
   const int envs_per_block = 4 * (32 / G);
   const int grid = ceil_div(t.B, envs_per_block);
   const int lhead = exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;  // context.py:132
@@ -835,18 +853,19 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   }
   {
     ProfScope ps(CLS_INIT, st);
-    root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, root_logits, root_value, root_var, in->gumbel, in->invalid_actions, root_out_value, root_out_ube);
+    root_init_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, root_logits, root_value, root_var, in->gumbel, in->invalid_actions, root_out_value, root_out_ube,
+                                                  batch_offset);
   }
   EAZ_CHECK_LAUNCH("root_init_kernel");
   if constexpr (G == ps::kG && J == 1) {
     int ncap = 0;
-    if (!flags && persistent_eligible(t, sp, env, mlp_mode, tw, &ncap)) {  // ONE launch runs all sp.n simulations (psearch.cuh)
+    if (!flags && tw && tw->w2_ck16[0] && persistent_eligible(t.B, t.N, t.A, sp.flags, env, mlp_mode, &ncap)) {  // ONE launch runs all sp.n simulations
       {
         ProfScope ps_scope(CLS_SELECT, st);
         if (int rc = launch_persistent(t, sp, env, net, *tw, in, lhead, ncap, st)) return rc;
       }
       ProfScope pf(CLS_FINAL, st);
-      finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so);
+      finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so, (int)(in->gumbel == nullptr));
       EAZ_CHECK_LAUNCH("finalize_kernel");
       return 0;
     }
@@ -895,7 +914,7 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   }
   {
     ProfScope ps(CLS_FINAL, st);
-    finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so);
+    finalize_kernel<G, J><<<grid, 128, 0, st>>>(t, sp, in->beta, in->invalid_actions, so, (int)(in->gumbel == nullptr));
   }
   EAZ_CHECK_LAUNCH("finalize_kernel");
   return 0;
@@ -918,7 +937,7 @@ static int check_search(const eaz_search_config* cfg, const eaz_search_inputs* i
   EAZ_CHECK_ARG(cfg->max_depth >= 0, "max_depth must be >= 0 (0 = None)");
   if (int rc = make_env_desc(in->env, env)) return rc;
   if (int rc = make_net_desc(in->net, env, net)) return rc;
-  EAZ_CHECK_ARG(in->gumbel && in->embedding, "search inputs: gumbel / embedding must be non-NULL");
+  EAZ_CHECK_ARG(in->embedding != nullptr, "search inputs: embedding must be non-NULL");
   const bool fused_root = !in->prior_logits && !in->value && !in->value_epistemic_variance;
   EAZ_CHECK_ARG(fused_root || (in->prior_logits && in->value && in->value_epistemic_variance),
                 "search inputs: prior_logits / value / value_epistemic_variance must be all non-NULL, or all NULL (fused root)");
@@ -1022,16 +1041,18 @@ int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env
   if (!cfg || make_env_desc(env, &d)) return -1;
   const int per_sim = 1 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
   const bool build_tables = (cfg->flags & EAZ_FLAG_REUSE_PREPARED) == 0;
-  const int prep = (cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * 3 : 0) + 1 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0);  // weight images, seq-halving + seen tables
+  const int prep = (cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * (d.kind == EAZ_ENV_DEEPSEA ? 4 : 3) : 0) + 1 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0);  // weight images, seq-halving + seen tables
   // 1 memset + pack + root init + [tables] + per simulation + last tree step + finalize  (+1 network launch with a fused root)
   int sizes[8], parts = 1;
   if (cfg->batch >= 1) sub_batches(cfg, sizes, &parts);  // EAZ_FLAG_STREAMS: every sub-batch launches its own sequence
+  if (cfg->batch >= 1 && persistent_eligible(cfg->batch, cfg->num_simulations + 1, d.num_actions, cfg->flags, d, cfg->mlp_mode, nullptr))
+    return 1 + 2 + (build_tables ? prep : 0) + 1 + 1;  // memset + pack + root init + [tables] + ONE persistent kernel + finalize (+1 with a fused root)
   return parts * (1 + 2 + (build_tables ? prep : 0) + per_sim * cfg->num_simulations + 1 + 1);
 }
 
 // one search over the whole batch of `cfg` on one stream
 static int search_one(const eaz_search_config* cfg, const eaz_search_inputs* in, eaz_search_outputs* out, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      size_t workspace_bytes, void* stream, int batch_offset = 0) {
   EnvDesc env;
   NetDesc net;
   if (int rc = check_search(cfg, in, out, &env, &net)) return rc;
@@ -1070,7 +1091,7 @@ static int search_one(const eaz_search_config* cfg, const eaz_search_inputs* in,
   SummaryOut so{out->action, out->action_weights, out->value, out->value_epistemic_std, out->visit_counts, out->visit_probs,
                 out->qvalues, out->qvalues_epistemic_variance};
   int rc;
-#define EAZ_RUN(G, J) rc = run_search<G, J>(t, sp, env, net, in, so, cfg->mlp_mode, cfg->exploration, cfg->mlp_mode == EAZ_MLP_TENSOR ? &tw : nullptr, out->root_value, out->root_ube, st)
+#define EAZ_RUN(G, J) rc = run_search<G, J>(t, sp, env, net, in, so, cfg->mlp_mode, cfg->exploration, cfg->mlp_mode == EAZ_MLP_TENSOR ? &tw : nullptr, out->root_value, out->root_ube, batch_offset, st)
   if (A <= 2) EAZ_RUN(2, 1);
   else if (A <= 4) EAZ_RUN(4, 1);
   else if (A <= 8) EAZ_RUN(8, 1);
@@ -1151,7 +1172,13 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   EAZ_CHECK_ARG(cfg && in && out, "search: NULL config / inputs / outputs");
   int sizes[8], parts = 1;
   if (cfg->batch >= 1) sub_batches(cfg, sizes, &parts);
-  if (parts <= 1 || tl_prof != nullptr) {
+  bool persistent = false;
+  {
+    EnvDesc d;
+    if (cfg->batch >= 1 && in->env && make_env_desc(in->env, &d) == 0)
+      persistent = persistent_eligible(cfg->batch, cfg->num_simulations + 1, d.num_actions, cfg->flags, d, cfg->mlp_mode, nullptr);
+  }
+  if (parts <= 1 || tl_prof != nullptr || persistent) {  // (the persistent kernel's clusters are independent chains already: nothing to split)
     eaz_search_config c = *cfg;
     c.flags = (c.flags & ~kFlagManyTrees) | (cfg->batch >= kManyTrees ? kFlagManyTrees : 0);
     return search_one(&c, in, out, workspace, workspace_bytes, stream);
@@ -1239,7 +1266,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
     const size_t bytes = layout_bytes(cfg, env, sizes[p]);
     cudaStream_t sp = aux->s[p];
     if (cudaError_t e = cudaStreamWaitEvent(sp, aux->fork, 0); e != cudaSuccess) return cuda_fail(e, "fork wait");
-    const int rc = search_one(&c, &si, &so, (uint8_t*)workspace + ws_off, bytes, sp);
+    const int rc = search_one(&c, &si, &so, (uint8_t*)workspace + ws_off, bytes, sp, (int)b0);
     if (rc && !rc_all) rc_all = rc;
     // always rejoin, also after an error: a forked stream must not be left dangling inside a stream capture
     if (cudaError_t e = cudaEventRecord(aux->join[p], sp); e != cudaSuccess) return cuda_fail(e, "join event");

@@ -222,6 +222,17 @@ def env_uncompact(env: EnvSpec, compact, rewards=None, with_obs=False, out: dict
     return st
 
 
+def trajectory_pack(env: EnvSpec, st: dict, action, out=None):
+    """eaz_trajectory_pack: int32 [B,4] replay records {action, reward bits, flags, first compact-state word} in one kernel."""
+    torch = require_cuda()
+    B = _batch(st)
+    if out is None:
+        out = torch.empty((B, 4), dtype=torch.int32, device=st["step_count"].device)
+    e, s = env.struct(), state_struct(env, st)
+    check(load().eaz_trajectory_pack(C.byref(e), C.byref(s), _ptr(action, torch.int32), _ptr(out, torch.int32), B, _stream()), "eaz_trajectory_pack")
+    return out
+
+
 def subleq_test_cases(task: int, ws: int):
     import numpy as np
 
@@ -396,7 +407,8 @@ class SearchPlan:
 
     def run(self, root: dict, profile: bool = False, reuse_prepared: bool | None = False):
         """root: prior_logits [B,A], value [B], value_epistemic_variance [B], beta [B], embedding (state dict),
-        gumbel [B,A] pre-drawn standard Gumbel noise, optional invalid_actions [B,A] (bool/uint8).
+        gumbel [B,A] pre-drawn standard Gumbel noise (absent / None: drawn inside the search from cfg.noise_seed and the
+        workspace's draw counter), optional invalid_actions [B,A] (bool/uint8).
 
         The returned tensors are THIS PLAN'S buffers: the next run() overwrites them (clone what must survive).
         reuse_prepared: False = rebuild the parameter-derived tables, True = the caller promises env / net are unchanged,
@@ -409,7 +421,7 @@ class SearchPlan:
             inv = inv.to(u8)
         e, n, s = self.env.struct(), self.net.struct(), state_struct(self.env, root["embedding"])
         inp = _abi.EazSearchInputs(_ptr(root.get("prior_logits"), f32), _ptr(root.get("value"), f32), _ptr(root.get("value_epistemic_variance"), f32),
-                                   _ptr(root["beta"], f32), C.pointer(s), _ptr(inv), _ptr(root["gumbel"], f32), C.pointer(e), C.pointer(n))
+                                   _ptr(root["beta"], f32), C.pointer(s), _ptr(inv), _ptr(root.get("gumbel"), f32), C.pointer(e), C.pointer(n))
         o = _abi.EazSearchOutputs()
         for name, _, _ in _abi.SEARCH_OUTPUT_FIELDS:
             setattr(o, name, _ptr(self.out.get(name)))

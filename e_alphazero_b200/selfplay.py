@@ -22,17 +22,27 @@ class SelfplayOutput:  # selfplay.py:17-23
 
 
 class SelfplayRunner:
-    """Pre-allocates the search plan; `step(states, gumbel=None)` advances a batch of envs by one move."""
+    """Pre-allocates the search plan; `step(states, gumbel=None)` advances a batch of envs by one move.
+
+    ALIASING: the returned SelfplayOutput fields (and `states`) are views of buffers this runner reuses on every step -- the
+    plan's output tensors, the CUDA graph's static buffers, the in-place state dict.  The reference's lax.scan stacks per-step
+    outputs (selfplay.py:148); a caller collecting outputs over several steps must clone what it keeps, or pass
+    `clone_outputs=True`, or use `trajectory()` (one packed int32 [B,4] record per step, written into a caller-owned [T,B,4] buffer).
+
+    device_noise=True draws the root Gumbel noise inside the search (counter-based stream keyed by `seed`, the number of searches run
+    and the tree index) instead of five elementwise torch kernels per step; parity tests pass `gumbel=` explicitly."""
 
     def __init__(self, env_spec: ops.EnvSpec, net: ops.FcParams, batch: int, num_simulations: int, discount: float,
                  exploration_beta: float = 0.0, directed_exploration: bool = False, rescale_values: bool = True,
                  mlp_mode: int = _abi.MLP_EXACT, tasks=(1,), device="cuda", seed: int = 0, use_graph: bool = False, fused_root: bool = False,
-                 streams: int = 1):
+                 streams: int = 1, device_noise: bool = False, clone_outputs: bool = False):
         torch = require_cuda()
         self.env, self.net, self.B, self.device = env_spec, net, batch, device
         self.directed = directed_exploration
         self.cfg = _abi.default_search_config(batch=batch, num_simulations=num_simulations, discount=discount,
                                               exploration=int(directed_exploration), rescale_values=int(rescale_values), mlp_mode=mlp_mode)
+        self.cfg.noise_seed = int(seed) & 0xFFFFFFFF
+        self.device_noise, self.clone_outputs = bool(device_noise), bool(clone_outputs)
         if streams > 1:  # EAZ_FLAG_STREAMS: sub-batches searched concurrently (tree kernel of one overlaps the network kernel of another)
             self.cfg.flags |= _abi.flag_streams(streams)
         self.plan = ops.SearchPlan(self.cfg, env_spec, net, want_tree=False, device=device)
@@ -89,16 +99,18 @@ class SelfplayRunner:
             self._static = (st, sg, stt)
         st, sg, stt = self._static
         draw = gumbel is None and (task_ids is None or not subleq)  # noise drawn inside the graph unless the caller supplies it
-        key = (not self._stale, draw)
+        in_search = draw and self.device_noise                      # ... by the search itself (no torch kernels)
+        key = (not self._stale, draw, in_search)
         if key not in self._graphs:
             g = torch.cuda.CUDAGraph()
             g.register_generator_state(self.gen)
             with torch.cuda.graph(g):
                 if draw:
-                    sg.copy_(self.draw_gumbel())
+                    if not in_search:
+                        sg.copy_(self.draw_gumbel())
                     if subleq:
                         stt.copy_(self._draw_tasks())
-                _, out = self._step_eager(st, sg, stt, reuse_prepared=key[0])
+                _, out = self._step_eager(st, None if in_search else sg, stt, reuse_prepared=key[0])
             self._graphs[key] = (g, out)
         g, out = self._graphs[key]
         for k in st:
@@ -121,19 +133,29 @@ class SelfplayRunner:
 
     def _step_eager(self, states: dict, gumbel=None, task_ids=None, reuse_prepared=None):
         torch = require_cuda()
+        if gumbel is None and not self.device_noise:
+            gumbel = self.draw_gumbel()
         if self.fused_root:  # selfplay.py:89 inside the search call (policy head = the recurrent_fn's: main.py:262)
-            root = dict(beta=self.beta, embedding=states, gumbel=self.draw_gumbel() if gumbel is None else gumbel)
+            root = dict(beta=self.beta, embedding=states, gumbel=gumbel)
         else:
             ev = ops.mlp_forward_states(self.net, self.env, states)  # selfplay.py:89
             logits = ev["explore_logits"] if self.directed else ev["exploit_logits"]  # :93-95
             root = dict(prior_logits=logits, value=ev["value"], value_epistemic_variance=ev["ube"], beta=self.beta, embedding=states,
-                        gumbel=self.draw_gumbel() if gumbel is None else gumbel)
+                        gumbel=gumbel)
         out = self.plan.run(root, reuse_prepared=reuse_prepared)  # :107-117 (invalid_actions = ~legal_action_mask = none)
         if self.fused_root:
             ev = dict(value=out["root_value"], ube=out["root_ube"])
         if task_ids is None and self.env.kind == _abi.ENV_SUBLEQ:
             task_ids = self._draw_tasks()
         ops.env_step_(self.env, states, out["action"], auto_reset=True, task_ids=task_ids)  # :135
-        return states, SelfplayOutput(state=states, root_value=out["value"], root_epistemic_std=out["value_epistemic_std"],
-                                      value_prediction=ev["value"], ube_prediction=ev["ube"],
-                                      q_values_epistemic_variance=out["qvalues_epistemic_variance"], action=out["action"])
+        res = SelfplayOutput(state=states, root_value=out["value"], root_epistemic_std=out["value_epistemic_std"],
+                             value_prediction=ev["value"], ube_prediction=ev["ube"],
+                             q_values_epistemic_variance=out["qvalues_epistemic_variance"], action=out["action"])
+        if self.clone_outputs and not torch.cuda.is_current_stream_capturing():
+            res = SelfplayOutput(**{k: (v.clone() if torch.is_tensor(v) else v) for k, v in vars(res).items() if k != "state"}, state=states)
+        return states, res
+
+    def trajectory(self, states: dict, out: SelfplayOutput, dst):
+        """Pack this step's replay record (ops.trajectory_pack: action, reward bits, flags, compact-state word) into `dst`
+        (int32 [B,4], e.g. one row of a [T,B,4] scan buffer): one small kernel, nothing aliased."""
+        return ops.trajectory_pack(self.env, states, out.action, dst)

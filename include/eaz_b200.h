@@ -100,6 +100,11 @@ int eaz_env_init(const eaz_env* env, const int32_t* task_ids, eaz_state* out, in
 int eaz_env_step(const eaz_env* env, eaz_state* state, const int32_t* action, int32_t auto_reset,
                  const int32_t* task_ids, int32_t B, void* stream);
 
+/* One int32[4] trajectory record per env for the replay buffer (main.py:217-225,383-385: what the reference gathers from every
+ * device after a selfplay() scan): {action, reward bits, terminated | truncated << 8 | solved << 16, first word of the compact
+ * state}.  out: int32 [B,4].  A single small kernel, so that a whole self-play step stays graph-capturable without tensor glue. */
+int eaz_trajectory_pack(const eaz_env* env, const eaz_state* state, const int32_t* action, int32_t* out, int32_t B, void* stream);
+
 /* pgx.Env.observe: DeepSea._observe deep_sea.py:83-85 (one-hot cell),
  * Subleq._observe subleq.py:679-707 with the encoders subleq.py:26-98.
  * Writes bool [B, obs_dim]. */
@@ -253,7 +258,9 @@ typedef struct eaz_search_inputs {
   const eaz_state* embedding;            /* root states (pgx.State) */
   const uint8_t* invalid_actions;        /* [B,A] bool, NULL = none (selfplay.py:113) */
   const float* gumbel;                   /* [B,A] pre-drawn standard Gumbel noise (replaces
-                                            jax.random.gumbel(gumbel_rng), mctx policies.py) */
+                                            jax.random.gumbel(gumbel_rng), mctx policies.py); NULL = drawn inside the
+                                            search from a counter-based stream keyed by (cfg.noise_seed, number of such
+                                            searches run on this workspace so far, tree, action) */
   const eaz_env* env;
   const eaz_fc_params* net;              /* params=model */
 } eaz_search_inputs;
