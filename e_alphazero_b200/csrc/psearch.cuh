@@ -49,11 +49,12 @@ __device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.a
 constexpr int kH = 256;
 constexpr int kCK = 16;               // K (halves) per chunk = one tcgen05.mma kind::f16 K-step
 constexpr int kChunks = kH / kCK;     // 16 per evaluation
-constexpr int kStages = 4;
-constexpr int kAHalf = kTile * kCK * 2;  // 4 KB: hi or lo tile of an A chunk
-constexpr int kAStage = 2 * kAHalf;
+constexpr int kStages = 6;            // W2 chunk ring (the A operand lives in tensor memory: no A ring)
 constexpr int kBHalf = kH * kCK * 2;     // 8 KB: hi or lo tile of a W2 chunk
 constexpr int kBStage = 2 * kBHalf;
+// tensor memory (512 columns x 128 lanes): D = relu-input accumulator [0, 256); A operand of the whole K = 256, written by the gather
+// warps with tcgen05.st and read by tcgen05.mma straight from TMEM: hi halves [256, 384), lo halves [384, 512), 8 columns per chunk
+constexpr int kTmemCols = 512, kTmemAhi = 256, kTmemAlo = 384, kAColsPerChunk = kCK / 2;
 constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 256 B between 8-row groups
 constexpr int kBarL3 = 1, kBarA0 = 2;  // named barriers: layer-3 partial sums; A-ring stage s = kBarA0 + s
 constexpr float kActScale = 16.0f, kWScale = 256.0f, kUnscale = 1.0f / (kActScale * kWScale);  // (mlp_gather.cu)
@@ -72,10 +73,8 @@ constexpr int kMiscWords = 12;        // [0] considered visit, [8..8+A) leaf pri
 constexpr int kTreeWords = kEdgeWords + kBackWords + kRootWords + kMiscWords;  // + ncap state words + ncap/2 next words
 
 struct Shared {
-  uint64_t full_a[kStages], full_b[kStages];
-  // "stage consumed" barriers, split by the parity of the stage's use count: two gather warps alternate on a stage, so each of them
-  // observes only every other use -- on ONE barrier it could not tell phase u - 1 from phase u - 3 (same parity)
-  uint64_t empty[2][kStages];
+  uint64_t full_a[kChunks];  // chunk c of this evaluation's A operand is in tensor memory (4 arrivals: one per 32-row quarter)
+  uint64_t full_b[kStages], empty[kStages];
   uint64_t acc_done;    // the evaluation's MMAs are complete (tcgen05.commit)
   uint64_t cells_full;  // transaction barrier: kTile * 4 bytes of st.async per phase -- every tree of the tile has published its leaf cell
   uint64_t out_full;    // transaction barrier: the three heads' outputs for this CTA's kSlots trees have landed
@@ -91,7 +90,7 @@ __host__ __device__ inline int tree_words(int ncap) { return kTreeWords + ncap +
 constexpr int kAmapMax = 16384;  // the DeepSea action map (N x N bytes) is mirrored in shared memory when it fits (N <= 128)
 __host__ __device__ inline int amap_bytes(int size) { return size * size <= kAmapMax ? ((size * size + 15) & ~15) : 0; }
 __host__ __device__ inline size_t smem_bytes(int ncap, int size) {
-  return 1024 + (size_t)kStages * (kAStage + kBStage) + ((sizeof(Shared) + 15) & ~(size_t)15) + (size_t)kSlots * tree_words(ncap) * 4 +
+  return 1024 + (size_t)kStages * kBStage + ((sizeof(Shared) + 15) & ~(size_t)15) + (size_t)kSlots * tree_words(ncap) * 4 +
          (size_t)amap_bytes(size);
 }
 
@@ -189,8 +188,7 @@ __device__ __noinline__ void direct_pair(const Args& a, int sim, int do_backward
 __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_constant__ Args a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // (pointer arithmetic on the __shared__ symbol: LDS / STS, not generic)
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kAStage;
+  uint8_t* sB = smem;
   Shared* sh = reinterpret_cast<Shared*>(sB + kStages * kBStage);
   uint32_t* tree_smem = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(sh) + ((sizeof(Shared) + 15) & ~(size_t)15));
   uint8_t* const s_amap = reinterpret_cast<uint8_t*>(tree_smem + (size_t)kSlots * tree_words(a.ncap));  // mirror of env.action_map (or unused)
@@ -210,11 +208,10 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   // ------------------------------------------------------------------ prologue
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
-      mbar_init(&sh->full_a[s], 1);  // one elected arrive by the chunk's gather warp
       mbar_init(&sh->full_b[s], 1);
-      mbar_init(&sh->empty[0][s], 1);
-      mbar_init(&sh->empty[1][s], 1);
+      mbar_init(&sh->empty[s], 1);
     }
+    for (int c = 0; c < kChunks; ++c) mbar_init(&sh->full_a[c], 4);
     mbar_init(&sh->acc_done, 1);
     mbar_init(&sh->cells_full, 1);
     mbar_init(&sh->out_full, 1);
@@ -232,7 +229,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   if (amap_n)
     for (int i = threadIdx.x; i < a.env.size * a.env.size; i += kThreads) s_amap[i] = a.env.action_map[i];
   if (head_cta && warp == kWarpMma) {
-    tmem_alloc(&sh->tmem_base, kH);
+    tmem_alloc(&sh->tmem_base, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -248,8 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       const int total = n * kChunks;
 #pragma unroll 1
       for (int g = 0; g < total; ++g) {
-        const int s = g % kStages, u = g / kStages;  // u-th use of stage s: the (u - 1)-th must have been consumed
-        if (u > 0) mbar_wait(&sh->empty[(u - 1) & 1][s], ((u - 1) >> 1) & 1);
+        const int s = g % kStages;
+        if (g >= kStages) mbar_wait(&sh->empty[s], ((g / kStages) & 1) ^ 1);
         mbar_arrive_expect_tx(&sh->full_b[s], (uint32_t)kBStage);
         bulk_g2s(sB + s * kBStage, img + (size_t)(g % kChunks) * kBStage, kBStage, &sh->full_b[s]);
       }
@@ -267,31 +264,22 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       const uint32_t lbo_bits = (uint32_t)(kCoreBytes >> 4) << 16;  // LBO [16,30)
       auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
       const uint32_t idesc = idesc_f16(kTile, kH);
-      const uint32_t a_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | lbo_bits, b_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | lbo_bits;
+      const uint32_t b_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | lbo_bits;
       const int total = n * kChunks;
 #pragma unroll 1
       for (int g = 0; g < total; ++g) {
-        const int s = g % kStages, ph = (g / kStages) & 1, c = g % kChunks;
-        // The issue of a tcgen05.mma blocks while the tensor pipe's queue is full, so the ~200 cycles of the two waits would be added to
-        // every chunk's 384 cycles of tensor work: wait for chunk g + 1 BEFORE issuing chunk g (within one evaluation: the first chunk
-        // of the next evaluation only arrives after this one's outputs).
-        if (c == 0) {
-          mbar_wait(&sh->full_a[s], ph);  // (all 32 lanes: uniform control flow)
-          mbar_wait(&sh->full_b[s], ph);
-        }
-        if (c + 1 < kChunks) {
-          const int s1 = (g + 1) % kStages, ph1 = ((g + 1) / kStages) & 1;
-          mbar_wait(&sh->full_a[s1], ph1);
-          mbar_wait(&sh->full_b[s1], ph1);
-        }
+        const int s = g % kStages, ph = (g / kStages) & 1, c = g % kChunks, it = g / kChunks;
+        mbar_wait(&sh->full_a[c], it & 1);  // (all 32 lanes: uniform control flow)
+        mbar_wait(&sh->full_b[s], ph);
         tc_fence_after();
-        if (lane == 0) trc.chunk(g / kChunks, c, 0);
-        const uint32_t al = a_base + (uint32_t)((s * kAStage) >> 4), bl = b_base + (uint32_t)((s * kBStage) >> 4);
+        if (lane == 0) trc.chunk(it, c, 0);
+        const uint32_t bl = b_base + (uint32_t)((s * kBStage) >> 4);
+        const uint32_t a_hi = tmem + (uint32_t)(kTmemAhi + c * kAColsPerChunk), a_lo = tmem + (uint32_t)(kTmemAlo + c * kAColsPerChunk);
         if (elect_one()) {
-          mma_f16(tmem, mk(al), mk(bl), idesc, c != 0);
-          mma_f16(tmem, mk(al), mk(bl + (kBHalf >> 4)), idesc, 1);
-          mma_f16(tmem, mk(al + (kAHalf >> 4)), mk(bl), idesc, 1);
-          mma_commit(&sh->empty[(g / kStages) & 1][s]);
+          mma_f16_ts(tmem, a_hi, mk(bl), idesc, c != 0);
+          mma_f16_ts(tmem, a_hi, mk(bl + (kBHalf >> 4)), idesc, 1);
+          mma_f16_ts(tmem, a_lo, mk(bl), idesc, 1);
+          mma_commit(&sh->empty[s]);
           if (c == kChunks - 1) mma_commit(&sh->acc_done);
         }
         __syncwarp();
@@ -300,19 +288,19 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   } else if (warp > kWarpCopy) {
     regs_dec<kRegsCtrl>();  // (the two spare warps of the control warpgroup)
   } else if (warp >= kWarpGather0) {
-    // ================================================================ gather warps: layer 1 = copy of the leaf cells' h1 rows into the A ring
-    // EIGHT independent single-warp producers: warp g fills chunks g and g + 8 of every evaluation (ring stage = chunk % 4), all 128
-    // rows x (hi, lo) x 32 bytes of a chunk = 16 LDG.128 per thread.  The proxy fence that publishes a chunk to the tensor core is a
-    // MEMBAR, which also waits for the warp's own loads in flight, so a producer cannot usefully prefetch past its current chunk; with
-    // eight producers the L2 round trips of eight chunks overlap instead (one software-prefetching producer group: 1400 cycles per
-    // chunk; four two-warp producers: 520; the tensor work of a chunk is 384).
+    // ================================================================ gather warps: layer 1 = copy of the leaf cells' h1 rows into TENSOR MEMORY
+    // The A operand never touches shared memory: thread = row (TMEM lane), a chunk of a row is 32 bytes of hi and 32 bytes of lo halves
+    // = 2 x 8 tensor-memory columns, written with tcgen05.st and consumed by tcgen05.mma with A in TMEM.  (With A in shared memory a
+    // chunk moved 60 KB through the SM's shared-memory port -- 36 KB of operand reads for the three split-precision products, 24 KB
+    // of ring writes -- i.e. >= 470 cycles against 384 cycles of tensor work; measured 630.)  The whole K = 256 of a row fits beside
+    // the accumulator, so there is no A ring and no "stage free" wait either.  Warp g serves the 32 rows of TMEM quarter g % 4 and the
+    // chunks of parity g / 4, four chunks per batch: one MEMBAR-carrying hand-over per batch instead of per chunk.
     regs_inc<kRegsGather>();
     if (head_cta) {
       const int gw = warp - kWarpGather0;
-      const int piece = lane & 1;                     // 16-byte piece of the 32 bytes a row contributes to a chunk (per hi / lo part)
-      const int r0 = lane >> 1;                       // rows r0 + 16 j, j = 0..7
-      const uint8_t* const table = a.h1[rank] + piece * 16;
-      const uint32_t doff0 = (uint32_t)((r0 >> 3) * kSBO + piece * kCoreBytes + (r0 & 7) * 16);  // + j * 2 * kSBO per row step of 16
+      const int q = warp & 3, half = gw >> 2;
+      const uint8_t* const table = a.h1[rank];
+      const uint32_t tq = sh->tmem_base + ((uint32_t)(32 * q) << 16);
 #pragma unroll 1
       for (int it = 0; it < n; ++it) {
         warp_wait(&sh->cells_full, it & 1, lane);
@@ -320,35 +308,31 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
           trc.stamp(it, 0);
           if (it + 1 < n) mbar_arrive_expect_tx(&sh->cells_full, kTile * 4);  // arm the next phase (nobody publishes before this evaluation's outputs)
         }
-        int cellv[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cellv[j] = sh->cells[r0 + 16 * j];
+        const uint4* const src = reinterpret_cast<const uint4*>(table + (size_t)sh->cells[32 * q + lane] * (4 * kH));  // [hi 512 B | lo 512 B]
 #pragma unroll 1
-        for (int c = gw; c < kChunks; c += kGWarps) {
-          uint4 vh[8], vl[8];
+        for (int batch = 0; batch < 2; ++batch) {
+          uint4 v[4][4];  // [chunk of the batch][hi0, hi1, lo0, lo1]
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const uint8_t* src = table + (size_t)cellv[j] * (4 * kH) + c * (kCK * 2);
-            vh[j] = __ldg(reinterpret_cast<const uint4*>(src));
-            vl[j] = __ldg(reinterpret_cast<const uint4*>(src + 2 * kH));
+          for (int k = 0; k < 4; ++k) {
+            const int c = 2 * (4 * batch + k) + half;
+            v[k][0] = __ldg(src + 2 * c);
+            v[k][1] = __ldg(src + 2 * c + 1);
+            v[k][2] = __ldg(src + 2 * c + (2 * kH) / 16);
+            v[k][3] = __ldg(src + 2 * c + (2 * kH) / 16 + 1);
           }
-          const int stage = c % kStages;
-          const int use = it * (kChunks / kStages) + c / kStages;  // how often this stage has been filled before
-          const bool gtr = lane == 0;
-          if (gtr) trc.gather(it, c, 0);  // loads issued
-          if (use > 0) warp_wait(&sh->empty[(use - 1) & 1][stage], ((use - 1) >> 1) & 1, lane);
-          if (gtr) trc.gather(it, c, 1);  // stage free
-          uint8_t* const dst = sA + stage * kAStage + doff0;
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            *reinterpret_cast<uint4*>(dst + j * 2 * kSBO) = vh[j];
-            *reinterpret_cast<uint4*>(dst + kAHalf + j * 2 * kSBO) = vl[j];
+          for (int k = 0; k < 4; ++k) {
+            const int c = 2 * (4 * batch + k) + half;
+            tmem_st8(tq + (uint32_t)(kTmemAhi + c * kAColsPerChunk), v[k][0], v[k][1]);
+            tmem_st8(tq + (uint32_t)(kTmemAlo + c * kAColsPerChunk), v[k][2], v[k][3]);
           }
-          if (gtr) trc.gather(it, c, 2);  // data arrived and stored
-          fence_proxy_async();
-          if (gtr) trc.gather(it, c, 3);  // fenced
+          tmem_st_wait();
+          tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&sh->full_a[stage]);
+          if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mbar_arrive(&sh->full_a[2 * (4 * batch + k) + half]);
+          }
         }
         if (gw == 0 && lane == 0) trc.stamp(it, 1);
       }
@@ -793,7 +777,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
   // ------------------------------------------------------------------ teardown
   tc_fence_before();
   __syncthreads();
-  if (head_cta && warp == kWarpMma) tmem_dealloc(sh->tmem_base, kH);
+  if (head_cta && warp == kWarpMma) tmem_dealloc(sh->tmem_base, kTmemCols);
   cluster_sync_all();  // no CTA leaves while a peer might still address its shared memory
 }
 
