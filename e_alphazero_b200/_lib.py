@@ -13,7 +13,7 @@ import subprocess
 from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libeaz_b200.so")
+SO_PATH = os.environ.get("EAZ_LIB_PATH") or os.path.join(_HERE, "libeaz_b200.so")  # (EAZ_LIB_PATH: A/B measurements of two builds)
 _lib = None
 
 # every symbol include/eaz_b200.h declares
@@ -24,7 +24,7 @@ EXPORTS = [
     "eaz_subleq_test_cases",
     "eaz_xxhash_indices", "eaz_hash_lookup", "eaz_hash_update",
     "eaz_mlp_forward", "eaz_mlp_forward_states",
-    "eaz_search_workspace_bytes", "eaz_search_gumbel", "eaz_search_gumbel_profiled", "eaz_search_num_launches",
+    "eaz_search_workspace_bytes", "eaz_search_gumbel", "eaz_search_gumbel_profiled", "eaz_search_num_launches", "eaz_search_numeric_status",
     "eaz_reanalyze_targets",
 ]
 

@@ -42,9 +42,21 @@ struct TensorWeights {
   int k1pad;
   const void* h1[4];  // one-hot observations (DeepSea): pre-activated, pre-split layer-1 rows per cell (mlp_gather.cu)
   const void* w2_ck16[4];  // one-hot observations: the W2 images once more in K = 16 chunks (persistent search kernel, psearch.cuh)
+  // Range guard of the scaled 3xFP16 split (numeric status block at the end of the image buffer):
+  const float* wscale;     // [4][3] power-of-two scale the weight image of (head, layer) was multiplied with, chosen from max |w|
+  uint32_t* num_flags;     // sticky bits: EAZ_NUM_* below (read back by eaz_search_numeric_status)
+};
+constexpr uint32_t kNumWeightsNonFinite = 1u;   // a weight matrix holds inf / nan, or max |w| > 2^20 (no power-of-two scale fits)
+constexpr uint32_t kNumActSaturated = 2u;       // a hidden activation exceeded the fp16 range of the scaled split (|h| * 16 > 65504)
+constexpr float kActScale = 16.0f;              // activations are multiplied by 16 before the hi / lo split: |h| < 4094 representable
+struct NumStatus {
+  float wscale[4][3];
+  uint32_t wmax_bits[4][3];
+  uint32_t flags;
+  uint32_t pad[7];
 };
 size_t gather_table_bytes(const NetDesc& net);
-int prepare_gather_table(const NetDesc& net, int head, void* buf, cudaStream_t st);
+int prepare_gather_table(const NetDesc& net, int head, void* buf, uint32_t* num_flags, cudaStream_t st);
 int launch_mlp_gather(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,
                       const MlpOutputs& out, cudaStream_t stream);
 size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env);

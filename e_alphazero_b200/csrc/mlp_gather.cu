@@ -35,9 +35,7 @@ constexpr int kBHalf = kH * kCK * 2;      // 16 KB: hi or lo tile of one W2 chun
 constexpr int kBStage = 2 * kBHalf;
 constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 512 B
 constexpr int kOutMax = 4;
-constexpr float kActScale = 16.0f;
-constexpr float kWScale = 256.0f;
-constexpr float kUnscale = 1.0f / (kActScale * kWScale);
+// (kActScale = 16, mlp.cuh; the W2 image carries a per-matrix power-of-two scale, tile_weights.cu)
 
 struct Smem {
   uint64_t full_a[kStages], full_b[kStages], empty[kStages], acc_done;
@@ -51,12 +49,16 @@ constexpr size_t kSmemBytes = (size_t)kStages * (kAStage + kBStage) + sizeof(Sme
 using namespace gk;
 
 // h1 table: out[cell][hi 256 halves | lo 256 halves] = split(clamp(relu(W1[cell] + b1) * kActScale))
-__global__ void h1_table_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int D, __half* __restrict__ out) {
+__global__ void h1_table_kernel(const float* __restrict__ W1, const float* __restrict__ b1, int D, __half* __restrict__ out, uint32_t* num_flags) {
   const int total = D * kH;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int cell = i / kH, k = i % kH;
     // same operations as the in-kernel layer-1 epilogue of mlp_tensor.cu: fma(w, S, b*S) == (w + b) * S for S = 2^k
-    const float v = fminf(fmaxf(__fmaf_rn(W1[i], kActScale, b1[k] * kActScale), 0.0f), 65504.0f);
+    float v = fmaxf(__fmaf_rn(W1[i], kActScale, b1[k] * kActScale), 0.0f);
+    if (!(v <= 65504.0f)) {  // range guard: clamped AND reported (eaz_search_numeric_status)
+      atomicOr(num_flags, kNumActSaturated);
+      v = 65504.0f;
+    }
     __half hi, lo;
     split_f16(v, hi, lo);
     out[(size_t)cell * 2 * kH + k] = hi;
@@ -117,6 +119,7 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
+  const float kUnscale = 1.0f / (kActScale * __ldg(tw.wscale + 3 * head + 1));  // exact: both scales are powers of two
   const uint8_t* w2img = reinterpret_cast<const uint8_t*>(tw.img[head][1]);  // per chunk: [hi tile 256 x 32 | lo tile]
   auto issue_b = [&](int c) {
     const int s = c % kStages;
@@ -329,9 +332,9 @@ __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc
 // ---------------------------------------------------------------- host side
 size_t gather_table_bytes(const NetDesc& net) { return (size_t)net.D * 2 * kH * sizeof(__half); }
 
-int prepare_gather_table(const NetDesc& net, int head, void* buf, cudaStream_t st) {
+int prepare_gather_table(const NetDesc& net, int head, void* buf, uint32_t* num_flags, cudaStream_t st) {
   const int total = net.D * kH;
-  h1_table_kernel<<<min(ceil_div(total, 256), 148 * 8), 256, 0, st>>>(net.w[head][0], net.b[head][0], net.D, (__half*)buf);
+  h1_table_kernel<<<min(ceil_div(total, 256), 148 * 8), 256, 0, st>>>(net.w[head][0], net.b[head][0], net.D, (__half*)buf, num_flags);
   EAZ_CHECK_LAUNCH("h1_table_kernel");
   return 0;
 }

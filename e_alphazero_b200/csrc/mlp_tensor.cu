@@ -25,7 +25,8 @@
 namespace eaz {
 using namespace umma;
 
-int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, float scale, void* out, cudaStream_t st, int chunk_k = 32);  // tile_weights.cu
+int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, const float* scale, void* out, cudaStream_t st, int chunk_k = 32);  // tile_weights.cu
+int launch_weight_scales(const NetDesc& net, int heads_mask, NumStatus* ns, cudaStream_t st);                                                     // tile_weights.cu
 
 constexpr int kTM = 128;                       // rows per CTA
 constexpr int kCK = 32;                        // K elements (fp16) per pipeline stage: 64 B per row
@@ -34,10 +35,8 @@ constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 8-row group stride inside 
 constexpr int kAHalf = kTM * kCK * 2;          // one of hi / lo
 constexpr int kAStage = 2 * kAHalf;
 constexpr int kBStageMax = 2 * 256 * kCK * 2;  // hi + lo, N = 256
-constexpr float kActScale = 16.0f;             // activations: |h| < 4094 representable, lo part normal down to 2^-7
-constexpr float kWScale = 256.0f;              // weights: |w| < 255
-constexpr float kUnscaleBits = 1.0f / kWScale;               // layer 1 on 0/1 observations: A unscaled
-constexpr float kUnscaleAct = 1.0f / (kActScale * kWScale);  // layers fed by activations
+// (kActScale = 16, mlp.cuh: activations |h| < 4094 representable, lo part normal down to 2^-7; the weight scale is a per-matrix power
+//  of two chosen from max |w| -- tile_weights.cu -- and removed exactly in the epilogues)
 constexpr int kH = 256;
 constexpr int kLayerChunks = kH / kCK;         // chunks of layers 2 and 3
 constexpr int kBitsWordsMax = 40;              // observation bit-strings cached in smem up to 40*32 bits per row
@@ -181,6 +180,10 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
+  // the power-of-two scales the three weight images of this head carry (tile_weights.cu), removed exactly in the epilogues
+  const float un_bits = 1.0f / __ldg(tw.wscale + 3 * head + 0);                 // layer 1 on 0/1 observations: A unscaled
+  const float un_l2 = 1.0f / (kActScale * __ldg(tw.wscale + 3 * head + 1));   // layers fed by (16x-scaled) activations
+  const float un_l3 = 1.0f / (kActScale * __ldg(tw.wscale + 3 * head + 2));
   // everything above reads only weights: under PDL it overlaps the tail of the previous kernel.  From here on the
   // kernel consumes the previous kernel's outputs (leaf indices, states).
   const int row = threadIdx.x & (kTM - 1);
@@ -409,15 +412,22 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         const bool from_tmem = !(layer == 1 && gather);
         if (from_tmem) tmem_ld_wait();
         // accumulators carry the operand scales: layer 1 of bit inputs kWScale, everything else kActScale * kWScale
-        const float un = (!from_tmem ? 1.0f : ((layer == 1) ? kUnscaleBits : kUnscaleAct)) * kActScale;
+        const float un = (!from_tmem ? 1.0f : ((layer == 1) ? un_bits : un_l2)) * kActScale;
         const float4* bs = reinterpret_cast<const float4*>(&sh->bias_s[layer - 1][c * kCK]);
 #pragma unroll
         for (int q = 0; q < kCK / 4; ++q) {
           const float4 bq = bs[q];
-          v[4 * q + 0] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 0]), un, bq.x), 0.0f), 65504.0f);
-          v[4 * q + 1] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 1]), un, bq.y), 0.0f), 65504.0f);
-          v[4 * q + 2] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 2]), un, bq.z), 0.0f), 65504.0f);
-          v[4 * q + 3] = fminf(fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 3]), un, bq.w), 0.0f), 65504.0f);
+          v[4 * q + 0] = fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 0]), un, bq.x), 0.0f);
+          v[4 * q + 1] = fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 1]), un, bq.y), 0.0f);
+          v[4 * q + 2] = fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 2]), un, bq.z), 0.0f);
+          v[4 * q + 3] = fmaxf(__fmaf_rn(__uint_as_float(r[4 * q + 3]), un, bq.w), 0.0f);
+          // range guard: a hidden activation beyond the fp16 range of the scaled split is clamped AND reported (sticky flag)
+          const float mx4 = fmaxf(fmaxf(v[4 * q + 0], v[4 * q + 1]), fmaxf(v[4 * q + 2], v[4 * q + 3]));
+          if (!(mx4 <= 65504.0f)) {
+            if (live) atomicOr(tw.num_flags, kNumActSaturated);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) v[4 * q + i] = fminf(v[4 * q + i], 65504.0f);
+          }
         }
         if (!live) {
 #pragma unroll
@@ -548,7 +558,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int k = kbase + kk + i;
-          const float h = fmaxf(__fmaf_rn(__uint_as_float(r[i]), kUnscaleAct, sh->bias[1][k]), 0.0f);
+          const float h = fmaxf(__fmaf_rn(__uint_as_float(r[i]), un_l2, sh->bias[1][k]), 0.0f);
           if (nout == 1) {  // value / UBE heads
             y3[0] = __fmaf_rn(h, sh->w3[k][0], y3[0]);
           } else {
@@ -587,7 +597,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       if (policy) {
 #pragma unroll
         for (int i = 0; i < 16; ++i)
-          if (n0 + i < nout) logits[(size_t)b * nout + n0 + i] = __fadd_rn(simt3 ? __uint_as_float(r[i]) : __fmul_rn(__uint_as_float(r[i]), kUnscaleAct), sh->bias[2][n0 + i]);
+          if (n0 + i < nout) logits[(size_t)b * nout + n0 + i] = __fadd_rn(simt3 ? __uint_as_float(r[i]) : __fmul_rn(__uint_as_float(r[i]), un_l3), sh->bias[2][n0 + i]);
       } else {
         const float y = __fadd_rn(__uint_as_float(r[0]), sh->bias[2][0]);
         if (head == EAZ_HEAD_VALUE) {
@@ -622,7 +632,7 @@ size_t tensor_weights_bytes(const NetDesc& net, const EnvDesc& env) {
   const size_t l1 = env.kind == EAZ_ENV_DEEPSEA ? gather_table_bytes(net) : (size_t)k1pad_of(net.D) * 2 * kH * 2;
   const size_t l2 = (size_t)kH * 2 * kH * 2;
   const size_t per_head = l1 + l2 + (size_t)kH * 2 * np3 * 2 + (env.kind == EAZ_ENV_DEEPSEA ? l2 : 0);  // (+ the K = 16 W2 images)
-  return 4 * ((per_head + 255) & ~(size_t)255);
+  return 4 * ((per_head + 255) & ~(size_t)255) + 256;  // (+ the numeric status block: per-matrix scales, saturation flags)
 }
 
 int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mask, void* buf, TensorWeights* tw, cudaStream_t st, bool fill) {
@@ -633,8 +643,13 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
   const int k1pad = k1pad_of(net.D);
   const bool has_l1 = env.kind != EAZ_ENV_DEEPSEA;
   const size_t l1 = has_l1 ? (size_t)k1pad * 2 * kH * 2 : gather_table_bytes(net), l2 = (size_t)kH * 2 * kH * 2;
-  const size_t per_head = tensor_weights_bytes(net, env) / 4;
+  const size_t per_head = (tensor_weights_bytes(net, env) - 256) / 4;
+  NumStatus* ns = reinterpret_cast<NumStatus*>((uint8_t*)buf + 4 * per_head);
   tw->k1pad = k1pad;
+  tw->wscale = &ns->wscale[0][0];
+  tw->num_flags = &ns->flags;
+  if (fill)
+    if (int rc = launch_weight_scales(net, heads_mask, ns, st)) return rc;
   for (int h = 0; h < 4; ++h) {
     uint8_t* p = (uint8_t*)buf + (size_t)h * per_head;
     tw->img[h][0] = (const uint32_t*)p;
@@ -646,14 +661,14 @@ int prepare_tensor_weights(const NetDesc& net, const EnvDesc& env, int heads_mas
     if (!fill || !(heads_mask & (1 << h))) continue;
     const int nout = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
     if (has_l1) {
-      if (int rc = launch_tile_weights_f16(net.w[h][0], net.D, kH, k1pad, kH, kWScale, p, st)) return rc;
+      if (int rc = launch_tile_weights_f16(net.w[h][0], net.D, kH, k1pad, kH, tw->wscale + 3 * h + 0, p, st)) return rc;
     } else {
-      if (int rc = prepare_gather_table(net, h, p, st)) return rc;
+      if (int rc = prepare_gather_table(net, h, p, tw->num_flags, st)) return rc;
     }
-    if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, kWScale, p + l1, st)) return rc;
-    if (int rc = launch_tile_weights_f16(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, kWScale, p + l1 + l2, st)) return rc;
+    if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, tw->wscale + 3 * h + 1, p + l1, st)) return rc;
+    if (int rc = launch_tile_weights_f16(net.w[h][2], kH, nout, kH, (nout + 15) & ~15, tw->wscale + 3 * h + 2, p + l1 + l2, st)) return rc;
     if (!has_l1)
-      if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, kWScale, p + l1 + l2 + l3, st, 16)) return rc;
+      if (int rc = launch_tile_weights_f16(net.w[h][1], kH, kH, kH, kH, tw->wscale + 3 * h + 1, p + l1 + l2 + l3, st, 16)) return rc;
   }
   return 0;
 }

@@ -57,7 +57,7 @@ constexpr int kBStage = 2 * kBHalf;
 constexpr int kTmemCols = 512, kTmemAhi = 256, kTmemAlo = 384, kAColsPerChunk = kCK / 2;
 constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 256 B between 8-row groups
 constexpr int kBarL3 = 1, kBarA0 = 2;  // named barriers: layer-3 partial sums; A-ring stage s = kBarA0 + s
-constexpr float kActScale = 16.0f, kWScale = 256.0f, kUnscale = 1.0f / (kActScale * kWScale);  // (mlp_gather.cu)
+// (activation scale kActScale = 16: mlp.cuh; the W2 images carry a per-matrix power-of-two scale: Args::unscale)
 
 // per-tree staging area (uint32 words); layout of tree_step.cuh Stage2<2>, sized for kNodes staged nodes (path + leaf)
 constexpr int kW = 16;                // lanes per tree
@@ -169,6 +169,7 @@ struct Args {
   const float* b3[kHeads];
   int nout[kHeads];
   int head_id[kHeads];  // EAZ_HEAD_*
+  const float* wscale;  // [4][3] power-of-two scales of the weight images (tile_weights.cu)
   const uint8_t* ds_seen;
   float max_u, novelty_scale;
   int ncap;
@@ -360,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
     const bool std_backup = (sp.flags & EAZ_FLAG_BACKUP_STD) != 0;
     uint32_t* const st_global = reinterpret_cast<uint32_t*>(t.states);
     const bool tstamp = tw == 0;  // (with trc.buf: cluster 0, CTA 0)
+    const float kUnscale = head_cta ? 1.0f / (kActScale * __ldg(a.wscale + 3 * a.head_id[rank] + 1)) : 0.0f;  // exact (powers of two)
     const float b3_0 = head_cta ? __ldg(a.b3[rank]) : 0.0f, b3_1 = (head_cta && a.nout[rank] > 1) ? __ldg(a.b3[rank] + 1) : 0.0f;
 
     // this tree's pending simulation: path length, leaf, reward / terminal flag of the leaf's state, its observation cell

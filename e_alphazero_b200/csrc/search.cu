@@ -546,6 +546,7 @@ static int launch_persistent(const Tree& t, const SearchParams& sp, const EnvDes
     a.nout[r] = h >= EAZ_HEAD_EXPLOIT ? net.A : 1;
     a.head_id[r] = h;
   }
+  a.wscale = tw.wscale;
   a.ds_seen = t.ds_seen;
   a.max_u = net.max_u;
   a.novelty_scale = net.novelty_scale;
@@ -1275,6 +1276,40 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
     ws_off += bytes;
   }
   return rc_all;
+}
+
+int eaz_search_numeric_status(const eaz_search_config* cfg, const eaz_env* env_in, const void* workspace, size_t workspace_bytes, void* stream,
+                              int32_t* flags_out) {
+  EAZ_CHECK_ARG(cfg && workspace, "numeric status: NULL config / workspace");
+  EnvDesc env;
+  if (int rc = make_env_desc(env_in, &env)) return rc;
+  if (flags_out) *flags_out = 0;
+  if (cfg->mlp_mode != EAZ_MLP_TENSOR || cfg->batch < 1) return 0;  // the fp32 FMA path has no scaled split
+  int sizes[8], parts = 1;
+  sub_batches(cfg, sizes, &parts);
+  if (persistent_eligible(cfg->batch, cfg->num_simulations + 1, env.num_actions, cfg->flags, env, cfg->mlp_mode, nullptr)) parts = 1;
+  if (parts == 1) sizes[0] = cfg->batch;
+  if (cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream); e != cudaSuccess) return cuda_fail(e, "numeric status sync");
+  const size_t wbytes = wimg_bytes_for(cfg->mlp_mode, env);
+  uint32_t flags = 0;
+  size_t ws_off = 0;
+  for (int p = 0; p < parts; ++p) {
+    Layout L;
+    make_layout(sizes[p], cfg->num_simulations + 1, env.num_actions, env.compact_bytes, (cfg->max_num_considered_actions + 1) * cfg->num_simulations,
+                env.obs_dim, wbytes, cfg->max_depth > 0 ? cfg->max_depth : cfg->num_simulations, &L);
+    if (ws_off + L.total > workspace_bytes) break;
+    const uint8_t* ns = (const uint8_t*)workspace + ws_off + L.off[24] + wbytes - 256;
+    uint32_t f = 0;
+    if (cudaError_t e = cudaMemcpy(&f, ns + offsetof(NumStatus, flags), sizeof(f), cudaMemcpyDeviceToHost); e != cudaSuccess) return cuda_fail(e, "numeric status read");
+    flags |= f;
+    ws_off += L.total;
+  }
+  if (flags_out) *flags_out = (int32_t)flags;
+  if (flags == 0) return 0;
+  set_error("tensor-core network path out of range:%s%s -- use mlp_mode EXACT for this model",
+            (flags & kNumWeightsNonFinite) ? " a weight matrix holds inf / nan or |w| > 2^20;" : "",
+            (flags & kNumActSaturated) ? " a hidden activation exceeded 4094 (fp16 range of the 16x-scaled split) and was clamped;" : "");
+  return EAZ_ERR_UNSUPPORTED;
 }
 
 int eaz_reanalyze_targets(const eaz_reanalyze_config* cfg, int32_t B, int32_t A, const int32_t* action, const float* qvalues,

@@ -403,6 +403,15 @@ class SearchPlan:
         cfg_reuse.flags |= _abi.FLAG_REUSE_PREPARED
         self.num_launches_reuse = load().eaz_search_num_launches(C.byref(cfg_reuse), C.byref(e))
 
+    def numeric_status(self) -> int:
+        """eaz_search_numeric_status: synchronises, raises EazError if the tensor-core network path left its representable range
+        (non-finite weights, clamped hidden activations) since the tables were last rebuilt; returns the flag bits (0)."""
+        e = self.env.struct()
+        flags = C.c_int32(0)
+        check(load().eaz_search_numeric_status(C.byref(self.cfg), C.byref(e), self._ws_ptr, self._ws_bytes, _stream(), C.byref(flags)),
+              "eaz_search_numeric_status")
+        return int(flags.value)
+
     PROFILE_CLASSES = ("init", "select", "env_step", "network", "expand_backward", "finalize", "export")
 
     def run(self, root: dict, profile: bool = False, reuse_prepared: bool | None = False):

@@ -317,6 +317,14 @@ int eaz_search_gumbel_profiled(const eaz_search_config* cfg, const eaz_search_in
                                void* workspace, size_t workspace_bytes, void* stream, float* ms_by_class,
                                int32_t* launches_by_class);
 
+/* Range guard of mlp_mode TENSOR (the scaled 3xFP16 split, fully_connected.py:41-101 evaluated on tcgen05): every weight image carries
+ * a power-of-two scale chosen from the matrix's own max |w|, so weights never saturate; what CAN leave the representable range is a
+ * hidden activation above 4094 (clamped) or a non-finite weight.  Both set sticky device flags in the workspace (reset whenever the
+ * parameter-derived tables are rebuilt).  This call SYNCHRONISES `stream`, reads them (bit 0: weights non-finite / > 2^20, bit 1:
+ * activation clamped) into *flags_out and returns EAZ_ERR_UNSUPPORTED with a message if any is set, 0 otherwise. */
+int eaz_search_numeric_status(const eaz_search_config* cfg, const eaz_env* env, const void* workspace, size_t workspace_bytes,
+                              void* stream, int32_t* flags_out);
+
 /* Number of kernel launches one eaz_search_gumbel call enqueues (for bench.py's
  * gpu_launches accounting). */
 int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env);

@@ -92,3 +92,36 @@ def test_product_never_imports_oracle():
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f
                 assert not re.search(r"#\s*include[^\n]*oracle", text), f
                 assert "libeaz_oracle" not in text, f
+
+
+def test_xla_ffi_shim_builds_and_validates(lib):
+    """csrc/xla_ffi_shim.cc (the JAX-side binding) compiles with -Wall -Werror against the XLA-FFI stand-in, exports one
+    handler per hot-path entry point, and its argument checks answer with ffi::Error before anything touches a device."""
+    from tests.xla_ffi_stub import harness as X
+
+    shim = X.load()
+    for h in X.HANDLERS:
+        assert hasattr(shim, h), h
+    env_attrs = dict(env_kind=_abi.ENV_DEEPSEA, size=10, word_size=0, binary_encoding=0, reward_fn=0)
+    one = X.buf("s32", None, 1)
+    # wrong number of state leaves
+    rc, msg = X.call(shim, "EazEnvStep", [X.buf("s32", None, 4), one, X.buf("u8", None, 10, 10)], [], dict(env_attrs, auto_reset=0))
+    assert rc == 3 and "number of state leaves" in msg  # kInvalidArgument
+    # a missing attribute / a dtype mismatch are rejected by the binding itself
+    rc, msg = X.call(shim, "EazEnvStep", [X.buf("s32", None, 4), one, X.buf("u8", None, 10, 10)], [], env_attrs)
+    assert rc == 3 and "auto_reset" in msg
+    rc, msg = X.call(shim, "EazHashUpdate", [X.buf("s32", None, 4, 8), X.buf("u8", None, 16)], [X.buf("u8", None, 16)], dict(bits=24))
+    assert rc == 3 and "dtype" in msg
+    # library-side validation travels back as the error message (hashes.py:210: D % 4 == 0)
+    rc, msg = X.call(shim, "EazHashUpdate", [X.buf("f32", None, 4, 25), X.buf("u8", None, 16)], [X.buf("u8", None, 16)], dict(bits=24))
+    assert rc == 3 and "eaz_hash_update" in msg
+    # Subleq word size outside 16..256 (subleq.py:606) through the search handler
+    f = lambda *d: X.buf("f32", None, *d)
+    args = [f(4), f(4, 8), X.buf("pred", None, 1), X.buf("u8", None, 1), X.buf("u8", None, 1 << 21), f(4, 8), f(4), f(4), X.buf("u8", None, 1)]
+    rets = [X.buf("s32", None, 4), f(4, 8), f(4), f(4), f(4, 8), f(4, 8), f(4, 8), f(4, 8), f(4), f(4), X.buf("u8", None, 1)]
+    attrs = dict(env_kind=_abi.ENV_SUBLEQ, size=0, word_size=8, binary_encoding=1, reward_fn=0, num_simulations=4, max_depth=0,
+                 max_num_considered_actions=16, gumbel_scale=1.0, discount=0.97, two_players_game=0, exploration=0, value_scale=0.1,
+                 maxvisit_init=50.0, rescale_values=1, flags=7, mlp_mode=0, fused_root=0, draw_gumbel=0, noise_seed=0, reuse_prepared=0,
+                 hash_bits=24, hash_io=1, max_u=1.0, novelty_scale=1.0)
+    rc, msg = X.call(shim, "EazSearch", args, rets, attrs)
+    assert rc == 3 and "word_size" in msg

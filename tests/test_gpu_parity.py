@@ -298,6 +298,87 @@ def test_search_tensor_mode(ops, kind, kw, B, cfg_kw, root_kw):
     assert_tree_equal(exp, got)
 
 
+def _wide_range_net(env, seed, w_big):
+    """Sparse network with |w| up to `w_big` in layers 2 / 3 (two non-zeros per output column), small dense layer 1."""
+    net = H.make_net(env, seed=seed, fill=0.5)
+    rng = np.random.default_rng(seed + 100)
+    for h in range(4):
+        net.w[h][0] *= 0.25  # hidden layer 1 stays below 1, so layer 2 (two terms of up to 1e3) stays inside the split's range
+        if h < _abi.HEAD_EXPLOIT:
+            net.w[h][2] *= 0.01  # value / UBE heads: keep the pre-tanh output O(1) so that the comparison is not saturated
+        for l in ((1, 2) if h >= _abi.HEAD_EXPLOIT else (1,)):
+            w = net.w[h][l]
+            K, N = w.shape
+            w[:] = 0
+            for n in range(N):
+                rows = rng.choice(K, 2, replace=False)
+                w[rows, n] = rng.uniform(-w_big, w_big, 2).astype(np.float32)
+            w[rng.integers(0, K), rng.integers(0, N)] = w_big  # the extreme itself is present
+    return net
+
+
+def _net_terms_bound(net, env, st, head):
+    """sum_k |h2_k| |W3_kn| + |b3_n|: the magnitude the 1e-5 relative bound of the scaled split refers to (cancellation-free)."""
+    obs = O.env_observe(env, st).reshape(len(st["step_count"]), -1).astype(np.float32)
+    h = obs
+    for l in range(2):
+        h = np.maximum(h @ net.w[head][l] + net.b[head][l], 0)
+    return np.abs(h) @ np.abs(net.w[head][2]) + np.abs(net.b[head][2])
+
+
+@pytest.mark.parametrize("kind,kw,B,n", [("deepsea", dict(size=10), 150, 24), ("deepsea", dict(size=10), 5000, 8), ("subleq", dict(word_size=16), 64, 16)])
+def test_tensor_mode_range_guard(ops, kind, kw, B, n):
+    """The scaled 3xFP16 split of mlp_mode TENSOR (north_star tolerance 1e-5): weights up to 1e3 keep the bound (per-matrix
+    power-of-two scale from max |w|, tile_weights.cu) and leave the sticky status clean; a network whose hidden activations
+    exceed the split's range (|h| > 4094) or whose weights are non-finite is REPORTED by eaz_search_numeric_status
+    (persistent kernel B=150, per-simulation kernels B=5000 / Subleq)."""
+    env = H.make_env(kind, seed=21, **kw)
+    net = _wide_range_net(env, 22, 1000.0)
+    root = H.make_root(env, net, B, seed=23)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(mlp_mode=_abi.MLP_TENSOR, num_simulations=n, discount=0.97)
+    cfg.batch = B
+    plan = ops.SearchPlan(cfg, denv, dnet, want_tree=True)
+    got = {k: host(v) for k, v in plan.run(H.device_root(env, denv, root)).items()}
+    assert plan.numeric_status() == 0
+    A = env.num_actions
+    st = H.uncompact(env, got["embeddings"][:, 1:].reshape(B * n, -1))
+    ev = O.mlp_forward_states(net, env, st)
+    live = ~st["terminated"].astype(bool)
+    for name, ref, head in (("raw_values", ev["value"], _abi.HEAD_VALUE), ("raw_values_epistemic_variance", ev["ube"], _abi.HEAD_UBE)):
+        bound = 1e-5 * _net_terms_bound(net, env, st, head)[:, 0] + 2e-6
+        err = np.abs(got[name][:, 1:].reshape(-1) - ref)
+        assert (err[live] <= bound[live]).all(), (name, float((err[live] / bound[live]).max()))
+    lg = ev["exploit_logits"]
+    bound = 1e-5 * _net_terms_bound(net, env, st, _abi.HEAD_EXPLOIT) + 2e-6
+    d = got["children_prior_logits"][:, 1:].reshape(B * n, A) - (lg - lg.max(1, keepdims=True))
+    assert (np.abs(d) <= 2 * bound.max(1, keepdims=True)).all()
+    # the search logic stays bit-exact under the GPU's own network outputs
+    replay = dict(states=got["embeddings"], logits=got["children_prior_logits"], value=got["raw_values"], var=got["raw_values_epistemic_variance"])
+    exp = O.search(_abi.default_search_config(num_simulations=n, discount=0.97), env, None, root, want_tree=True, replay=replay)
+    assert exp["replay_misses"] == 0
+    assert_tree_equal(exp, got)
+
+    # (2) hidden activations beyond 4094: clamped AND reported
+    big = H.make_net(env, seed=22, fill=0.5)
+    big.b[_abi.HEAD_VALUE][0][:8] = 6000.0  # layer-1 outputs are the (only) activations that are split for the tensor pipe in every kernel
+    plan2 = ops.SearchPlan(cfg, denv, H.device_net(big), want_tree=False)
+    plan2.run(H.device_root(env, denv, root))
+    with pytest.raises(ops.EazError, match="activation"):
+        plan2.numeric_status()
+    # (3) a non-finite weight
+    bad = H.make_net(env, seed=22, fill=0.5)
+    bad.w[_abi.HEAD_UBE][1][3, 5] = np.inf
+    plan3 = ops.SearchPlan(cfg, denv, H.device_net(bad), want_tree=False)
+    plan3.run(H.device_root(env, denv, root))
+    with pytest.raises(ops.EazError, match="weight"):
+        plan3.numeric_status()
+    # rebuilding the tables from a sane model clears the sticky flags
+    plan3.net = dnet
+    plan3.run(H.device_root(env, denv, root))
+    assert plan3.numeric_status() == 0
+
+
 @pytest.mark.parametrize("kind,kw,B,expl", [("deepsea", dict(size=10), 64, 0), ("subleq", dict(word_size=16), 40, 1)])
 def test_search_fused_root(ops, kind, kw, B, expl):
     """prior_logits/value/variance == NULL: the library evaluates the root network itself (selfplay.py:89); with the
