@@ -224,60 +224,144 @@ __device__ __forceinline__ unsigned long long sq_pack_vec(const SubleqVec& v, in
     if (i < v.len) p |= (unsigned long long)(unsigned)floormod(v.v[i], ws) << (8 * i);
   return p;
 }
-// The interpreter keeps the input as (packed vector, cursor) instead of shifting an array, the output as
-// (packed bytes, count), and the "output == expected" test as `no mismatch so far && count == expected length`
-// (a written word is < ws, so it can never equal the pad token ws: the arrays are equal iff exactly the expected
-// words were written and all matched).  Results are expanded into SubleqSim at the end.
-// The loop body is written branch-free (selects and predicated stores): the 32 lanes of a warp interpret 32 different
-// programs, so every data-dependent branch of a straightforward transcription (operand kind, IN / OUT handling, jump)
-// would split the warp and serialise its paths.  Loads go to clamped (always valid) addresses and are discarded by selects.
-template <typename MemT>
-__device__ __forceinline__ void subleq_simulate(int ws, MemT* mem, int trow, int k, SubleqSim& r) {
+// The interpreter keeps the input as (packed vector, cursor), the output as (packed bytes, count), and the "output == expected"
+// test as `no mismatch so far && count == expected length` (a written word is < ws, so it can never equal the pad token ws: the
+// arrays are equal iff exactly the expected words were written and all matched).  Results are expanded into SubleqSim at the end.
+// The loop body is branch-free apart from its exits (selects and predicated stores): the 32 lanes of a warp interpret 32 different
+// programs.  Loads go to clamped (always valid) addresses and are discarded by selects.
+//
+// CYCLE DETECTION (exact).  43 % of the programs a search visits never halt and never err: the reference lets them spin until
+// MAX_CYCLE_COUNT = 200 (subleq.py:19,297-299).  Everything that determines the machine's future -- memory, program counter, input
+// cursor, output count (`bad` is 0 while running: a mismatch errs at once) -- is a deterministic function of itself, so when that
+// state recurs the machine is in a loop it can never leave: it runs to the cap without halting or erring, its outputs / consumed
+// inputs (monotone counters that were equal at both ends of the loop) and bytes_used (a running max that has already seen every
+// instruction of the loop) are final, and `correct` is false (a program that has produced the expected output halts, :340-345).
+// So the result equals the reference's with cycles = 200, and the remaining iterations are skipped.  Recurrence is found with
+// Brent's algorithm against ONE snapshot (taken at cycles 0, 1, 2, 4, 8, ...): `diff` counts the bytes in which memory differs from
+// the snapshot and is updated incrementally by the single store of each cycle, so the check costs one extra load per cycle for any
+// word size.  Measured on the states of a C3 search: mean executed cycles 88 -> 5.3, worst lane of a warp 194 -> 22.
+// `snap`: ws bytes of scratch next to `mem` (kDetect = false: the plain loop, `snap` unused).
+// shared-memory byte accesses as opaque 32-bit operations: the compiler neither narrows the interpreter's arithmetic to 16-bit
+// registers (PRMT / LOP3 packing on the dependence chain) nor reorders them -- their order below IS the issue order
+__device__ __forceinline__ uint32_t sq_lds8(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sq_sts8(uint32_t addr, uint32_t v) { asm volatile("st.shared.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+
+// `mem`, `snap`: shared memory, sq_img_stride(ws) bytes each (>= ws + 4: a fetch at any reachable program counter stays inside).
+template <bool kDetect>
+__device__ __forceinline__ void subleq_simulate(int ws, uint8_t* mem, uint8_t* snap, int trow, int k, SubleqSim& r) {
   const int AMAX = ws - 4, AIN = ws - 3, AOUT = ws - 2;
+  const unsigned half1 = (unsigned)((ws + 1) >> 1) - 1u;  // jump <=> value == 0 || 2 * value >= ws <=> (unsigned)(value - 1) >= ceil(ws / 2) - 1
   const int in_len = c_sq_in[trow][k].len, out_len = c_sq_out[trow][k].len;
   const unsigned long long tin = sq_pack_vec(c_sq_in[trow][k], ws), tout = sq_pack_vec(c_sq_out[trow][k], ws);
+  const uint32_t m0 = (uint32_t)__cvta_generic_to_shared(mem), s0 = (uint32_t)__cvta_generic_to_shared(snap);
   unsigned long long outp = 0ull;
-  unsigned long long in_rest = tin, exp_rest = tout;  // unread input words / not yet matched expected words, next one in the low byte
-  int in_cur = 0, out_cur = 0, out_shift = 0, cur = 0, bytes = 0, cycles = 0, err = 0, bad = 0;
-  bool run = true;
-  while (run) {  // :297-299
+  int in_cur = 0, out_cur = 0, cur = 0, bytes = 0, cycles = 0, err = 0, bad = 0;
+  // Brent: the snapshot is the state after 0, 1, 2, 4, 8, ... cycles (initially the start state: the caller passes snap == copy of mem)
+  int diff = 0, lam = 0, pw = 1;
+  uint32_t io_meta = 0u, snap_meta = 0u;  // io_meta = in_cur << 16 | out_cur << 20; a state's meta word = cur | io_meta
+  bool hit = false;
+  const int nwords = (ws + 3) >> 2;
+  // One cycle's dependence chain is fetch (a, b, c) -> load operands -> subtract / wrap -> store, jump test -> next fetch: two
+  // shared-memory round trips (29 cycles each) and ~8 ALU operations.  The few programs that really run to the cap set the kernel's
+  // duration, and their warp runs alone on its scheduler, so the loop is built for LATENCY:
+  //   * the operand loads go out (to clamped, always valid addresses) before anything is decided about the cycle, and the next
+  //     fetch goes out as soon as the program counter is known -- both branches of the loop resolve under a load's latency;
+  //   * the COMMON cycle (both operands plain memory cells, program counter in range, no snapshot due: nothing but the
+  //     subtraction can happen, :322-329) takes a short path without any IO / error / halt bookkeeping;
+  //   * the loop detector hangs off the chain (one extra load, a few compares).
+  // (Measured per cycle, one warp alone: 120 ns for the first transcription, 190 ns with early-out branches on the chain or with a
+  // generic-pointer null test in the loop -- S2UR every iteration --, see profiles/r2_summary.md for this version.)
+  bool oob = false;  // cur + 2 >= ws (:364-370: costs a cycle, sets the error, changes nothing else); never at cur = 0 (ws >= 16)
+  uint32_t a = sq_lds8(m0), b = sq_lds8(m0 + 1), c = sq_lds8(m0 + 2);
+  while (true) {  // :297-299
+    // ---- the tight loop: consecutive COMMON cycles, ~40 instructions each.  The operand loads go out (to clamped, always valid
+    // addresses) BEFORE the cycle is classified, so the exit test resolves under their latency and the chain is
+    // fetch -> clamp -> operand loads -> subtract, wrap -> jump test -> fetch; the back edge is unconditional.
+    uint32_t am, bm;
+    int ma, mb, sv;
+    while (true) {
+      am = min(a, (uint32_t)AMAX);
+      bm = min(b, (uint32_t)AMAX);
+      ma = (int)sq_lds8(m0 + am);
+      mb = (int)sq_lds8(m0 + bm);
+      sv = kDetect ? (int)sq_lds8(s0 + am) : 0;
+      if (!(max(a, b) <= (uint32_t)AMAX && !oob && (!kDetect || lam + 1 != pw) && !hit && cycles < EAZ_SUBLEQ_MAX_CYCLES)) break;
+      cycles += 1;
+      const int dlt = ma - mb;  // both in [0, ws): floor-mod is one conditional add
+      const int value = (int)min((unsigned)dlt, (unsigned)(dlt + ws));
+      sq_sts8(m0 + am, (uint32_t)value);
+      const int cur_n = ((unsigned)(value - 1) >= half1) ? (int)min(c, (uint32_t)(ws - 1)) : cur + 3;  // :329
+      const uint32_t fa = m0 + (uint32_t)cur_n;  // cur_n <= ws: the fetch stays inside the image even when the next cycle is out of range
+      a = sq_lds8(fa);
+      b = sq_lds8(fa + 1);
+      c = sq_lds8(fa + 2);
+      bytes = max(bytes, cur + 3);  // :311
+      cur = cur_n;
+      oob = cur_n + 2 >= ws;
+      if (kDetect) {
+        diff += (int)(value != sv) - (int)(ma != sv);
+        lam += 1;
+        hit = diff == 0 && ((uint32_t)cur_n | io_meta) == snap_meta;  // the state after this cycle == the snapshot
+      }
+    }
+    if (hit || cycles >= EAZ_SUBLEQ_MAX_CYCLES) break;
+    // ---- the general cycle: an operand is IN / OUT / HALT, the program counter ran out of range, or a snapshot is due
+    // (operands already loaded above, from the clamped addresses)
     cycles += 1;
-    const bool oob = cur + 2 >= ws;  // :364-370: costs a cycle, sets the error, changes nothing else
     const bool live = !oob;
-    const int cc = oob ? 0 : cur;
-    const int a = mem[cc], b = mem[cc + 1], c = mem[cc + 2];
     const bool have_in = in_cur < in_len;  // input_state[0] < word_size (:197,218)
-    const int in0 = (int)((unsigned)in_rest & 0xffu);
-    const bool a_mem = a <= AMAX, b_mem = b <= AMAX, a_in = a == AIN, b_in = b == AIN;
-    const int ma = mem[a_mem ? a : 0], mb = mem[b_mem ? b : 0];
-    const int va = a_mem ? ma : ((a_in && have_in) ? in0 : 0);  // reads of OUT / HALT give 0 (:225-228)
-    const int vb = b_mem ? mb : ((b_in && have_in) ? in0 : 0);
+    const int in0 = have_in ? (int)((unsigned)(tin >> (8 * in_cur)) & 0xffu) : 0;
+    const bool a_mem = a <= (uint32_t)AMAX, b_mem = b <= (uint32_t)AMAX, a_in = a == (uint32_t)AIN, b_in = b == (uint32_t)AIN;
+    const int va = a_mem ? ma : (a_in ? in0 : 0);  // reads of OUT / HALT give 0 (:225-228)
+    const int vb = b_mem ? mb : (b_in ? in0 : 0);
+    const int dlt = va - vb;
+    const int value = (int)min((unsigned)dlt, (unsigned)(dlt + ws));
+    const bool wr = live && a_mem;  // writes to IN / HALT are ignored (:277-278,290-291)
+    if (wr) {
+      sq_sts8(m0 + am, (uint32_t)value);
+      diff += (int)(value != sv) - (int)(ma != sv);
+    }
+    const int cur_n = live ? (((unsigned)(value - 1) >= half1) ? (int)min(c, (uint32_t)(ws - 1)) : cur + 3) : cur;
     const bool uses_in = a_in || b_in;
-    int value = va - vb;  // both in [0, ws): floor-mod is one conditional add (:322)
-    value += value < 0 ? ws : 0;
-    if (live && a_mem) mem[a] = (MemT)value;  // writes to IN / HALT are ignored (:277-278,290-291)
-    const bool to_out = live && a == AOUT;
+    const bool to_out = live && a == (uint32_t)AOUT;
     const bool out_ok = to_out && out_cur < 8;  // a write to a full output is an error (:282-283)
-    const bool last_ok = !out_ok || (out_cur < out_len && value == (int)((unsigned)exp_rest & 0xffu));
+    const bool last_ok = !out_ok || (out_cur < out_len && value == (int)((unsigned)(tout >> (8 * out_cur)) & 0xffu));
     if (out_ok) {
-      outp |= (unsigned long long)(unsigned)value << out_shift;
-      out_shift += 8;
-      exp_rest >>= 8;
+      outp |= (unsigned long long)(unsigned)value << (8 * out_cur);
       out_cur += 1;
     }
     bad |= (out_ok && !last_ok) ? 1 : 0;
-    const bool jump = (value == 0) || (2 * value >= ws);  // :329
-    if (live && uses_in && have_in) {                     // :333-338 (at most one word per instruction)
-      in_cur += 1;
-      in_rest >>= 8;
-    }
-    const bool all_eq = !bad && out_cur == out_len;
-    const bool halt = live && (((((jump ? 1 : 0) & c) > AMAX)) || all_eq);  // :340-345, precedence as written
+    in_cur += (live && uses_in && have_in) ? 1 : 0;  // :333-338 (at most one word per instruction)
+    io_meta = ((uint32_t)in_cur << 16) | ((uint32_t)out_cur << 20);
+    // :340-345 as written, `jump & c > AMAX`, parses as (jump & c) > AMAX = (c & 1) > ws - 4: never true for ws >= 16 -- the only
+    // halt is "the expected output has been produced"
+    const bool halt = live && !bad && out_cur == out_len;
     err = (oob || (live && uses_in && !have_in) || (to_out && !out_ok) || (out_ok && !last_ok)) ? 1 : 0;  // :346-350
     bytes = live ? max(bytes, cur + 3) : bytes;  // :311
-    cur = live ? (jump ? c : cur + 3) : cur;
-    run = !err && !halt && cycles < EAZ_SUBLEQ_MAX_CYCLES;
+    if (err || halt) break;
+    if (kDetect) {
+      hit = diff == 0 && ((uint32_t)cur_n | io_meta) == snap_meta;  // (against the current snapshot, before it is replaced)
+      if (hit) break;
+      if (++lam == pw) {  // new snapshot (the same cycles in every lane: 1, 2, 4, 8, ...)
+        for (int i = 0; i < nwords; ++i) reinterpret_cast<uint32_t*>(snap)[i] = reinterpret_cast<const uint32_t*>(mem)[i];
+        snap_meta = (uint32_t)cur_n | io_meta;
+        diff = 0;
+        lam = 0;
+        pw <<= 1;
+      }
+    }
+    const uint32_t fa = m0 + (uint32_t)cur_n;
+    a = sq_lds8(fa);
+    b = sq_lds8(fa + 1);
+    c = sq_lds8(fa + 2);
+    cur = cur_n;
+    oob = cur_n + 2 >= ws;
   }
+  if (hit && !err) cycles = EAZ_SUBLEQ_MAX_CYCLES;  // the reference's result after MAX_CYCLE_COUNT cycles is the current one
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     r.in[i] = (in_cur + i < in_len) ? (int)((tin >> (8 * (in_cur + i))) & 0xffull) : ws;
@@ -366,8 +450,7 @@ __device__ __forceinline__ int group_argmax(float v, int idx) {
 #define EAZ_SQ_IMG 264  // >= 256 + slack, multiple of 8
 namespace eaz {
 struct SqShared {
-  uint8_t img[3 * EAZ_SQ_EPB][EAZ_SQ_IMG];  // per-(env,test) scratch memory image
-  uint8_t base[EAZ_SQ_EPB][EAZ_SQ_IMG];     // program after writing the action
+  alignas(16) uint8_t base[EAZ_SQ_EPB][EAZ_SQ_IMG];  // program after writing the action
   int16_t in_after[EAZ_SQ_EPB][8];
   int16_t out_after[EAZ_SQ_EPB][8];
   int correct[EAZ_SQ_EPB][3];
@@ -375,17 +458,35 @@ struct SqShared {
   int run[EAZ_SQ_EPB];   // 1 = execute the program for this env
   int trow[EAZ_SQ_EPB];  // row of the test-case table
 };
+// Per-(env, test) scratch in DYNAMIC shared memory: the memory image the test runs on and the cycle detector's snapshot of it.
+// The stride is a whole number of words, odd in words whenever ws is a multiple of 8 (same-offset accesses of a warp: no conflicts).
+__host__ __device__ inline int sq_img_stride(int ws) { return ((ws + 3) & ~3) + 4; }
+__host__ __device__ inline size_t sq_dyn_smem_bytes(int ws) { return (size_t)2 * 3 * EAZ_SQ_EPB * sq_img_stride(ws); }
+// launch helper: dynamic shared memory above 48 KB (ws > ~200) needs the opt-in attribute, set once per kernel
+template <typename K>
+inline cudaError_t sq_prepare_launch(K kernel, int ws, size_t* dyn_out) {
+  const size_t dyn = sq_dyn_smem_bytes(ws);
+  *dyn_out = dyn;
+  if (dyn + sizeof(SqShared) + 1024 <= 48 * 1024) return cudaSuccess;
+  return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sq_dyn_smem_bytes(256));
+}
 
-// All 3*EPB threads call this after base/run/trow are filled and synced.
-// On return (after its trailing __syncthreads) in_after/out_after/correct/bytes hold the results.
-__device__ __forceinline__ void sq_run_tests_block(SqShared& sh, int ws) {
+// All 3*EPB threads call this after base/run/trow are filled and synced; `dyn` = the kernel's dynamic shared memory
+// (sq_dyn_smem_bytes).  On return (after its trailing __syncthreads) in_after/out_after/correct/bytes hold the results.
+__device__ __forceinline__ void sq_run_tests_block(SqShared& sh, uint8_t* dyn, int ws) {
   const int e = threadIdx.x / 3, k = threadIdx.x % 3;
   if (sh.run[e]) {
-    uint8_t* img = sh.img[threadIdx.x];
-    const uint8_t* base = sh.base[e];
-    for (int i = 0; i < ws; i += 8) *reinterpret_cast<uint2*>(img + i) = *reinterpret_cast<const uint2*>(base + i);
+    const int stride = sq_img_stride(ws);
+    uint8_t* img = dyn + (size_t)threadIdx.x * stride;
+    uint8_t* snap = dyn + (size_t)(3 * EAZ_SQ_EPB + threadIdx.x) * stride;
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(sh.base[e]);
+    for (int i = 0; i < (ws + 3) >> 2; ++i) {
+      const uint32_t w = base[i];
+      reinterpret_cast<uint32_t*>(img)[i] = w;
+      reinterpret_cast<uint32_t*>(snap)[i] = w;  // the detector's first snapshot: the start state
+    }
     SubleqSim r;
-    subleq_simulate<uint8_t>(ws, img, sh.trow[e], k, r);
+    subleq_simulate<true>(ws, img, snap, sh.trow[e], k, r);
     sh.correct[e][k] = r.correct;
     sh.bytes[e][k] = r.bytes_used;
     if (k == 0) {

@@ -102,6 +102,7 @@ __global__ void deepsea_observe_kernel(EnvDesc env, StateSoA s, uint8_t* __restr
 __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_kernel(EnvDesc env, StateSoA s, const int32_t* __restrict__ action,
                                                                  const int32_t* __restrict__ task_ids, int mode, int B) {
   __shared__ SqShared sh;
+  extern __shared__ __align__(16) uint8_t sq_dyn[];  // per-(env, test) memory images + cycle-detector snapshots
   __shared__ int kind[EAZ_SQ_EPB];  // 0 absorbing, 1 terminate now, 2 execute, 3 init/reset
   const int ws = env.ws;
   const int e = threadIdx.x / 3, k = threadIdx.x % 3;
@@ -138,7 +139,7 @@ __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_kernel(EnvDesc env, Sta
     sh.run[e] = run;
   }
   __syncthreads();
-  sq_run_tests_block(sh, ws);
+  sq_run_tests_block(sh, sq_dyn, ws);
   if (k != 0 || b >= B) return;
   const int kd = kind[e];
   if (kd == 0) {
@@ -300,7 +301,11 @@ int eaz_env_init(const eaz_env* env, const int32_t* task_ids, eaz_state* out, in
   cudaStream_t st = (cudaStream_t)stream;
   const StateSoA s = soa_of(out);
   if (d.kind == EAZ_ENV_DEEPSEA) deepsea_init_kernel<<<ceil_div(B, 256), 256, 0, st>>>(s, B);
-  else subleq_kernel<<<ceil_div(B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, 0, st>>>(d, s, nullptr, task_ids, 0, B);
+  else {
+    size_t dyn = 0;
+    if (cudaError_t e = sq_prepare_launch(subleq_kernel, d.ws, &dyn); e != cudaSuccess) return cuda_fail(e, "subleq_kernel attribute");
+    subleq_kernel<<<ceil_div(B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, dyn, st>>>(d, s, nullptr, task_ids, 0, B);
+  }
   EAZ_CHECK_LAUNCH("eaz_env_init");
   if (out->observation) return eaz_env_observe(env, out, out->observation, B, stream);
   return 0;
@@ -316,7 +321,11 @@ int eaz_env_step(const eaz_env* env, eaz_state* state, const int32_t* action, in
   cudaStream_t st = (cudaStream_t)stream;
   const StateSoA s = soa_of(state);
   if (d.kind == EAZ_ENV_DEEPSEA) deepsea_step_kernel<<<ceil_div(B, 256), 256, 0, st>>>(d, s, action, auto_reset, B);
-  else subleq_kernel<<<ceil_div(B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, 0, st>>>(d, s, action, task_ids, auto_reset ? 2 : 1, B);
+  else {
+    size_t dyn = 0;
+    if (cudaError_t e = sq_prepare_launch(subleq_kernel, d.ws, &dyn); e != cudaSuccess) return cuda_fail(e, "subleq_kernel attribute");
+    subleq_kernel<<<ceil_div(B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, dyn, st>>>(d, s, action, task_ids, auto_reset ? 2 : 1, B);
+  }
   EAZ_CHECK_LAUNCH("eaz_env_step");
   if (state->observation) return eaz_env_observe(env, state, state->observation, B, stream);
   return 0;

@@ -574,6 +574,7 @@ static int launch_persistent(const Tree& t, const SearchParams& sp, const EnvDes
 // ------------------------------------------------------------------ Subleq transition on tree states (context.py:127)
 __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_tree_step_kernel(Tree t, EnvDesc env) {
   __shared__ SqShared sh;
+  extern __shared__ __align__(16) uint8_t sq_dyn[];  // per-(env, test) memory images + cycle-detector snapshots
   __shared__ int kind[EAZ_SQ_EPB];  // 0 absorbing, 1 terminate now, 2 execute
   __shared__ __align__(8) uint8_t hdr[EAZ_SQ_EPB][EAZ_SQ_HDR];
   const int ws = env.ws, S = t.S;
@@ -607,7 +608,7 @@ __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_tree_step_kernel(Tree t
     sh.run[e] = run;
   }
   __syncthreads();
-  sq_run_tests_block(sh, ws);
+  sq_run_tests_block(sh, sq_dyn, ws);
   if (k != 0 || b >= t.B) return;
   float reward = 0.0f;
   if (kind[e] == 2) {
@@ -903,7 +904,9 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     if (sim == sp.n) break;
     if (env.kind == EAZ_ENV_SUBLEQ) {
       ProfScope ps(CLS_ENV, st);
-      subleq_tree_step_kernel<<<ceil_div(t.B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, 0, st>>>(t, env);
+      size_t dyn = 0;
+      if (cudaError_t e = sq_prepare_launch(subleq_tree_step_kernel, env.ws, &dyn); e != cudaSuccess) return cuda_fail(e, "subleq_tree_step_kernel attribute");
+      subleq_tree_step_kernel<<<ceil_div(t.B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, dyn, st>>>(t, env);
       EAZ_CHECK_LAUNCH("subleq_tree_step_kernel");
     }
     {

@@ -113,7 +113,8 @@ def test_shim_env_step_and_forward(shim, kind, kw, B):
     leaves_in = [dst[k] for k in LEAVES[env.kind]]
     leaves_out = [torch.zeros_like(t) for t in leaves_in]
     stream = torch.cuda.current_stream().cuda_stream
-    rc, msg = X.call(lib, "EazEnvStep", [X.tbuf(torch.as_tensor(act, device=dev)), X.tbuf(torch.as_tensor(tasks, device=dev)), X.tbuf(amap)] +
+    d_act, d_tasks = torch.as_tensor(act, device=dev), torch.as_tensor(tasks, device=dev)  # (kept alive: tbuf only takes the pointer)
+    rc, msg = X.call(lib, "EazEnvStep", [X.tbuf(d_act), X.tbuf(d_tasks), X.tbuf(amap)] +
                      [X.tbuf(t) for t in leaves_in], [X.tbuf(t) for t in leaves_out], dict(env_attrs(env), auto_reset=1), stream)
     assert rc == 0, msg
     torch.cuda.synchronize()
