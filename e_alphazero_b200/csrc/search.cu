@@ -147,6 +147,16 @@ static Tree make_tree(void* ws, const Layout& L, int B, int N, int A, int S) {
 
 constexpr int kFlagManyTrees = 1 << 30;  // internal (set by eaz_search_gumbel): the whole batch is >= kManyTrees trees
 constexpr int kManyTrees = 6144;
+// Subleq transition inside the tree kernel (tree_step.cuh: subleq_expand_fused) or as its own launch: fused saves a launch boundary
+// and a pass over the states per simulation, but parks a whole warp (and the tree kernel's registers) behind three interpreting
+// lanes -- measured: 5 % faster at 8192 trees (C3), 7 % slower at 16384 and 35 % slower at 65536 x 128 (C5), where the dense
+// 3-threads-per-env kernel wins.  The caller-visible batch decides.
+constexpr int kFlagSqFused = 1 << 29;  // internal, like kFlagManyTrees
+constexpr int kSqFusedMaxTrees = 8192;
+static bool subleq_fused_for(int batch) {
+  static const bool separate = getenv("EAZ_SUBLEQ_SEPARATE") != nullptr, fused = getenv("EAZ_SUBLEQ_FUSED") != nullptr;  // measurement knobs
+  return !separate && (fused || batch <= kSqFusedMaxTrees);
+}
 
 // Search scalars, by value into the kernels.
 struct SearchParams {
@@ -885,6 +895,10 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     // faster with two): the caller-visible batch decides, not the sub-batch of one stream
     two_per_warp = !one_per_warp && (sp.flags & kFlagManyTrees) && chase_cap > 0 && stage2_bytes <= 48 * 1024 && !flags;
   }
+  // Subleq: the transition of the pending expansion runs inside the tree kernel (tree_step.cuh: subleq_expand_fused) for batches up to
+  // kSqFusedMaxTrees, as the separate subleq_tree_step_kernel launch above that
+  const bool sq_fused = env.kind == EAZ_ENV_SUBLEQ && (sp.flags & kFlagSqFused);
+  const size_t sq_bytes = sq_fused ? (size_t)4 * sq_warp_scratch_bytes(env.ws) : 0;
   for (int sim = 0; sim <= sp.n; ++sim) {
     {  // backward of simulation sim-1 fused with the descent of simulation sim
       ProfScope ps(sim < sp.n ? CLS_SELECT : CLS_EXPAND, st);
@@ -895,14 +909,14 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
                           in->beta, in->invalid_actions, g_timeline, g_tree_trace, chase_cap);
       }
       if (!two_per_warp)
-      le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), stage_bytes, st,  // one warp per tree
+      le = launch_pdl(tree_step_kernel<G, J>, dim3(ceil_div(t.B, 4)), dim3(128), stage_bytes + sq_bytes, st,  // one warp per tree
                                   t, sp, env, sim, (int)(sim > 0), (int)(sim < sp.n), in->beta, in->invalid_actions, g_timeline, g_tree_trace,
-                                  chase_cap, tile_done, (const int*)mlp_done, (sim > 0 && flag_mode > 1) ? nheads * mlp_launches : 0);
+                                  chase_cap, tile_done, (const int*)mlp_done, (sim > 0 && flag_mode > 1) ? nheads * mlp_launches : 0, (int)sq_fused);
       if (le != cudaSuccess) return cuda_fail(le, "tree_step_kernel launch");
     }
     EAZ_CHECK_LAUNCH("tree_step_kernel");
     if (sim == sp.n) break;
-    if (env.kind == EAZ_ENV_SUBLEQ) {
+    if (env.kind == EAZ_ENV_SUBLEQ && !sq_fused) {
       ProfScope ps(CLS_ENV, st);
       size_t dyn = 0;
       if (cudaError_t e = sq_prepare_launch(subleq_tree_step_kernel, env.ws, &dyn); e != cudaSuccess) return cuda_fail(e, "subleq_tree_step_kernel attribute");
@@ -1043,7 +1057,7 @@ size_t eaz_search_workspace_bytes(const eaz_search_config* cfg, const eaz_env* e
 int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env) {
   EnvDesc d;
   if (!cfg || make_env_desc(env, &d)) return -1;
-  const int per_sim = 1 + (d.kind == EAZ_ENV_SUBLEQ ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
+  const int per_sim = 1 + ((d.kind == EAZ_ENV_SUBLEQ && !subleq_fused_for(cfg->batch)) ? 1 : 0) + mlp_num_launches(cfg->mlp_mode);
   const bool build_tables = (cfg->flags & EAZ_FLAG_REUSE_PREPARED) == 0;
   const int prep = (cfg->mlp_mode == EAZ_MLP_TENSOR ? 3 * (d.kind == EAZ_ENV_DEEPSEA ? 4 : 3) : 0) + 1 + (d.kind == EAZ_ENV_DEEPSEA ? 1 : 0);  // weight images, seq-halving + seen tables
   // 1 memset + pack + root init + [tables] + per simulation + last tree step + finalize  (+1 network launch with a fused root)
@@ -1184,7 +1198,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
   }
   if (parts <= 1 || tl_prof != nullptr || persistent) {  // (the persistent kernel's clusters are independent chains already: nothing to split)
     eaz_search_config c = *cfg;
-    c.flags = (c.flags & ~kFlagManyTrees) | (cfg->batch >= kManyTrees ? kFlagManyTrees : 0);
+    c.flags = (c.flags & ~(kFlagManyTrees | kFlagSqFused)) | (cfg->batch >= kManyTrees ? kFlagManyTrees : 0) | (subleq_fused_for(cfg->batch) ? kFlagSqFused : 0);
     return search_one(&c, in, out, workspace, workspace_bytes, stream);
   }
   // ---- EAZ_FLAG_STREAMS: independent sub-batches (trees never interact) searched concurrently on auxiliary streams, so that
@@ -1213,7 +1227,7 @@ int eaz_search_gumbel(const eaz_search_config* cfg, const eaz_search_inputs* in,
     eaz_search_config c = *cfg;
     c.batch = sizes[p];
     c.flags &= ~(0xF << EAZ_FLAG_STREAMS_SHIFT);
-    c.flags = (c.flags & ~kFlagManyTrees) | (cfg->batch >= kManyTrees ? kFlagManyTrees : 0);
+    c.flags = (c.flags & ~(kFlagManyTrees | kFlagSqFused)) | (cfg->batch >= kManyTrees ? kFlagManyTrees : 0) | (subleq_fused_for(cfg->batch) ? kFlagSqFused : 0);
     auto offf = [&](const float* q, size_t per) { return q ? q + b0 * per : nullptr; };
     auto offu = [&](const uint8_t* q, size_t per) { return q ? q + b0 * per : nullptr; };
     auto offi = [&](const int32_t* q, size_t per) { return q ? q + b0 * per : nullptr; };

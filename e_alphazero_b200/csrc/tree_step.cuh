@@ -148,9 +148,86 @@ __device__ __forceinline__ int select_action_staged(const SearchParams& sp, cons
 
 // DIRECT path: one warp, one tree, everything loaded as it is needed (also the reference implementation of the arithmetic that
 // the STAGED paths reproduce from staged copies).
+// ---------------------------------------------------------------------------------------------------------------------
+// Subleq transition of the pending expansion, FUSED into the tree step (context.py:127 env.step -> subleq.py:648-677 -> run_tests
+// :504-532 -> simulate :156-395): the warp that has just finished a tree's descent copies the parent's compact state into its
+// scratch, writes the action into the program, lanes 0..2 interpret the three test cases (common.cuh: subleq_simulate with the exact
+// loop shortcut), and the child state + reward go straight into the tree's workspace -- no separate launch, no second pass over
+// the states.  Same steps as subleq_tree_step_kernel (search.cu), which stays as a measurement knob.
+// scratch (per warp, 16-byte aligned): [state S bytes | 3 images | 3 snapshots | results]
+__host__ __device__ inline int sq_warp_scratch_bytes(int ws) {
+  const int S = EAZ_SQ_HDR + ((ws + 7) & ~7);
+  return ((S + 15) & ~15) + ((6 * sq_img_stride(ws) + 15) & ~15) + 32;
+}
+__device__ __forceinline__ void subleq_expand_fused(const Tree& t, const EnvDesc& env, int b, int lane, int node, int action, int new_leaf,
+                                                    uint8_t* scratch) {
+  const int ws = env.ws, S = t.S;
+  uint8_t* const st = scratch;                                // the state record being stepped
+  uint8_t* const imgs = scratch + ((S + 15) & ~15);           // images 0..2, snapshots 3..5
+  int* const res = reinterpret_cast<int*>(imgs + ((6 * sq_img_stride(ws) + 15) & ~15));  // [0..2] correct, [3..5] bytes used
+  const uint8_t* ps = t.states + ((size_t)node * t.B + b) * S;
+  for (int i = lane; i < S / 8; i += 32) reinterpret_cast<uint2*>(st)[i] = reinterpret_cast<const uint2*>(ps)[i];
+  __syncwarp();
+  int kd = 0;  // 0 absorbing, 1 terminate now, 2 execute
+  if (lane == 0) {
+    uint16_t* h = reinterpret_cast<uint16_t*>(st);
+    const int flags = st[35];
+    if (!(flags & (EAZ_SQ_FLAG_TERM | EAZ_SQ_FLAG_TRUNC))) {
+      const int step = h[16] + 1;  // _step_count incremented before _step
+      h[16] = (uint16_t)step;
+      if (step >= ws - 3 || (flags & EAZ_SQ_FLAG_SOLVED)) {  // subleq.py:671-673
+        kd = 1;
+        st[35] = (uint8_t)(flags | EAZ_SQ_FLAG_TERM);
+      } else {
+        st[EAZ_SQ_HDR + step - 1] = (uint8_t)action;  // :654
+        kd = 2;
+      }
+    }
+  }
+  kd = __shfl_sync(0xffffffffu, kd, 0);
+  float reward = 0.0f;
+  if (kd == 2) {  // (warp-uniform)
+    __syncwarp();
+    SubleqSim r;
+    if (lane < 3) {
+      const int stride = sq_img_stride(ws);
+      uint8_t* img = imgs + lane * stride;
+      uint8_t* snap = imgs + (3 + lane) * stride;
+      const uint32_t* base = reinterpret_cast<const uint32_t*>(st + EAZ_SQ_HDR);
+      for (int i = 0; i < (ws + 3) >> 2; ++i) {
+        const uint32_t w = base[i];
+        reinterpret_cast<uint32_t*>(img)[i] = w;
+        reinterpret_cast<uint32_t*>(snap)[i] = w;
+      }
+      subleq_simulate<true>(ws, img, snap, sq_task_row(st[34]), lane, r);
+      res[lane] = r.correct;
+      res[3 + lane] = r.bytes_used;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      const int solved = res[0] & res[1] & res[2];
+      const int bytes = max(res[3], max(res[4], res[5]));
+      reward = subleq_reward(env.reward_fn, solved, bytes);
+      uint16_t* h = reinterpret_cast<uint16_t*>(st);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        h[i] = (uint16_t)r.in[i];
+        h[8 + i] = (uint16_t)r.out[i];
+      }
+      st[35] = (uint8_t)((st[35] & ~EAZ_SQ_FLAG_SOLVED) | (solved ? EAZ_SQ_FLAG_SOLVED : 0));
+    }
+  }
+  __syncwarp();
+  uint8_t* cs = t.states + ((size_t)new_leaf * t.B + b) * S;
+  for (int i = lane; i < S / 8; i += 32) reinterpret_cast<uint2*>(cs)[i] = reinterpret_cast<const uint2*>(st)[i];
+  if (lane == 0) t.reward[b] = reward;
+  __syncwarp();
+}
+
 template <int G, int J>
 __device__ __forceinline__ void tree_step_direct(const Tree& t, const SearchParams& sp, const EnvDesc& env, int sim, int do_backward, int do_select,
-                                                 float beta, const uint8_t* __restrict__ invalid, int b, int lane, long long* trc) {
+                                                 float beta, const uint8_t* __restrict__ invalid, int b, int lane, long long* trc,
+                                                 uint8_t* sq_scratch = nullptr) {
   const unsigned uB = (unsigned)t.B, uA = (unsigned)t.A, ub = (unsigned)b;
   constexpr int kLevelsPerRound = 32 / G;
   const int gl = lane & (G - 1), glev = lane / G;
@@ -343,6 +420,7 @@ __device__ __forceinline__ void tree_step_direct(const Tree& t, const SearchPara
       t.cell[b] = deepsea_obs_index(ns, env.size);
     }
   }
+  if (env.kind == EAZ_ENV_SUBLEQ && sq_scratch) subleq_expand_fused(t, env, b, lane, node, action, child < 0 ? sim + 1 : child, sq_scratch);
 }
 
 // Staging area of one warp (uint32 words); kRounds refresh rounds = kNodes nodes (path + leaf) fit.
@@ -362,8 +440,12 @@ template <int G, int J>
 __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
                                                          const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid,
                                                          unsigned long long* tl, long long* trace, int chase_cap, int* tile_done,
-                                                         const int* mlp_done, int mlp_target) {
+                                                         const int* mlp_done, int mlp_target, int sq_fused) {
   extern __shared__ __align__(16) uint32_t stage_smem[];
+  // (Subleq, fused transition: per-warp interpreter scratch behind the four staging areas)
+  uint8_t* const sq_scratch = sq_fused ? reinterpret_cast<uint8_t*>(stage_smem) + (chase_cap ? (size_t)4 * Stage<G>::words(chase_cap) * sizeof(uint32_t) : 0) +
+                                             (size_t)(threadIdx.x >> 5) * sq_warp_scratch_bytes(env.ws)
+                                       : nullptr;
   unsigned long long t_entry = 0;
   if (tl && blockIdx.x == 0 && threadIdx.x == 0) t_entry = globaltimer_ns();
   const int lane = threadIdx.x & 31;
@@ -663,12 +745,13 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
           t.cell[b] = deepsea_obs_index(ns, env.size);
         }
       }
+      if (env.kind == EAZ_ENV_SUBLEQ && sq_scratch) subleq_expand_fused(t, env, b, lane, node, action, child < 0 ? sim + 1 : child, sq_scratch);
       return;
     }
   }
 
   // ==================================================================== DIRECT path
-  tree_step_direct<G, J>(t, sp, env, sim, do_backward, do_select, beta, invalid, b, lane, trc);
+  tree_step_direct<G, J>(t, sp, env, sim, do_backward, do_select, beta, invalid, b, lane, trc, sq_scratch);
 }
 
 // ======================================================================================================================
