@@ -216,6 +216,69 @@ def run_reference(args, kind, kw, B, n, gamma, desc):
 
 
 # ============================================================================== B200 arm
+def extra_measure(args, name, dev, world, rank, steps=6, B_override=None, n_override=None):
+    """Short device-timed measurement of another BASELINE workload for the `extra` block of the JSON line (same runner, same step;
+    no e2e / trajectory legs): {"ms_per_step", "value", per-class ms of the search on rank 0}.  Max over ranks like the headline."""
+    import torch
+    import torch.distributed as dist
+
+    from e_alphazero_b200 import ops
+    from e_alphazero_b200.selfplay import SelfplayRunner
+
+    kind, kw, B, n, gamma, desc = WORKLOADS[name]
+    B, n = B_override or B, n_override or n
+    envp, netp = synth_params(kind, kw, 0)
+    env = ops.deepsea_spec(envp["size"], envp["action_map"], dev) if kind == "deepsea" else ops.subleq_spec(envp["word_size"], True)
+    net = ops.FcParams.from_numpy(netp["w"], netp["b"], netp["binary_set"], netp["num_actions"], 24, netp["hash_io"], netp["word_size"], device=dev)
+    streams = 3 if kind == "deepsea" else 1
+    runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=200 + rank,
+                            use_graph=not args.no_graph, fused_root=not args.no_fused_root, streams=streams, device_noise=True)
+    gen = torch.Generator(device=dev).manual_seed(17 + rank)
+    states = ops.env_init(env, B, task_ids=torch.ones(B, dtype=torch.int32, device=dev) if kind == "subleq" else None, device=dev)
+    for _ in range(3):
+        states = ops.env_step(env, states, torch.randint(0, env.num_actions, (B,), device=dev, generator=gen, dtype=torch.int32))
+    for _ in range(3):
+        states, _ = runner.step(states)
+    if runner.use_graph:
+        states = runner.static_states()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    for i in range(steps):
+        flush.zero_()
+        ev[i][0].record()
+        states, _ = runner.step(states)
+        ev[i][1].record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    res = {"workload": desc if not (B_override or n_override) else f"{desc.split(':')[0]} shape at {B} envs/GPU x {n} simulations (self-play step)",
+           "envs_per_gpu": B, "num_simulations": n, "steps": steps, "ms_per_step": ms / steps, "value": world * B * steps / (ms * 1e-3), "unit": UNIT,
+           "simulations_per_s": world * B * n * steps / (ms * 1e-3), "streams": streams}
+    if rank == 0:
+        ev0 = ops.mlp_forward_states(net, env, states)
+        root = dict(prior_logits=ev0["explore_logits"], value=ev0["value"], value_epistemic_variance=ev0["ube"], beta=runner.beta, embedding=states,
+                    gumbel=runner.draw_gumbel())
+        _, p = runner.plan.run(root, profile=True)
+        res["per_class_ms"] = {k: round(v[0], 4) for k, v in p.items()}
+        res["per_class_launches"] = {k: v[1] for k, v in p.items()}
+        _, tf_peak, which = measured_peaks()
+        D, H, A = netp["in_dim"], 256, env.num_actions
+        l1 = 0 if kind == "deepsea" else 2 * D * H
+        flops = (3 * (l1 + 2 * H * H) + 2 * (2 * H) + 2 * H * A) * B * n
+        net_ms = p["network"][0] if p["network"][1] else p["select"][0]  # (persistent kernel: the network runs inside it)
+        res["tensor_roofline"] = {"achieved": flops / (net_ms * 1e-3) / 1e12, "peak": tf_peak, "unit": "TFLOP/s", "frac": flops / (net_ms * 1e-3) / 1e12 / tf_peak,
+                                  "peak_source": which, "ms_per_search": net_ms}
+    del runner, flush
+    torch.cuda.empty_cache()
+    return res
+
+
 def run_b200(args, kind, kw, B, n, gamma, desc):
     import torch
     import torch.distributed as dist
@@ -437,6 +500,16 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         roofline["per_class_ms"] = {k: round(v[0], 4) for k, v in prof.items()}
         roofline["per_class_launches"] = {k: v[1] for k, v in prof.items()}
 
+    # ---- extra: the other BASELINE shapes next to the headline (short, device-timed, max over ranks): C4 is the reference's 8-GPU
+    # config (8192 envs / GPU), C3 the Subleq config, and one C5 point (Subleq 65 536 envs x 128 simulations)
+    extra = None
+    if not args.no_extra and args.workload == "c2":
+        del flush
+        torch.cuda.empty_cache()
+        extra = {"c4": extra_measure(args, "c4", dev, world, rank, steps=4)}
+        if world == 1:
+            extra["c3"] = extra_measure(args, "c3", dev, world, rank, steps=4)
+            extra["c5_point"] = extra_measure(args, "c3", dev, world, rank, steps=2, B_override=65536, n_override=128)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -457,7 +530,7 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
             "simulations_per_s": value * n, "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": n_full * runner.launches_per_step + (args.steps - n_full) * runner.launches_per_step_reuse + args.steps, "roofline": roofline,
-            "cpu_baseline": cpu}
+            "cpu_baseline": cpu, "extra": extra}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -490,6 +563,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--mlp-mode", type=int, default=1, help="0 = fp32 FMA chains (bit-exact contract), 1 = tcgen05 3xTF32 (default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the short C3 / C4 / C5-point measurements of the `extra` block")
     ap.add_argument("--streams", type=int, default=0,
                     help="EAZ_FLAG_STREAMS: search this many sub-batches concurrently on auxiliary streams (0 = 3 for DeepSea, 1 for Subleq: measured best)")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the workload's batch (exploration, not a BASELINE config)")
