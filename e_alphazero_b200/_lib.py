@@ -26,6 +26,7 @@ EXPORTS = [
     "eaz_mlp_forward", "eaz_mlp_forward_states",
     "eaz_search_workspace_bytes", "eaz_search_gumbel", "eaz_search_gumbel_profiled", "eaz_search_num_launches", "eaz_search_numeric_status",
     "eaz_reanalyze_targets",
+    "eaz_convnet_workspace_bytes", "eaz_convnet_forward",
 ]
 
 
@@ -54,6 +55,7 @@ def load():
             raise EazError(f"libeaz_b200.so does not export {name}")
     lib.eaz_last_error.restype = C.c_char_p
     lib.eaz_search_workspace_bytes.restype = C.c_size_t
+    lib.eaz_convnet_workspace_bytes.restype = C.c_size_t
     if lib.eaz_abi_version() != _abi.ABI_VERSION:
         raise EazError(f"ABI version mismatch: library {lib.eaz_abi_version()} vs bindings {_abi.ABI_VERSION}")
     _lib = lib

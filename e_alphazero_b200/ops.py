@@ -364,6 +364,47 @@ def mlp_forward_states(net: FcParams, env: EnvSpec, st: dict) -> dict:
     return out
 
 
+# --------------------------------------------------------------------------- convolutional evaluators
+class ConvNetParams:
+    """EpistemicResidualAZNet / EpistemicMinatarAZNet (network/resnet.py, network/minatar.py) as device tensors.
+    `desc`: _abi.convnet_description(params, state, ...) -- numpy / torch leaves are uploaded once."""
+
+    def __init__(self, desc: dict, device="cuda"):
+        torch = require_cuda()
+        self._keep = []
+
+        def up(x):
+            if isinstance(x, dict):
+                return {k: up(v) for k, v in x.items()}
+            if isinstance(x, (list, tuple)):
+                return [up(v) for v in x]
+            if hasattr(x, "shape") and not isinstance(x, (int, float)):
+                t = torch.as_tensor(x)
+                t = t.to(device=device, dtype=torch.uint8 if t.dtype == torch.uint8 else torch.float32).contiguous()
+                self._keep.append(t)
+                return t
+            return x
+
+        self.desc = up(desc)
+        self.device = device
+        self.struct = _abi.fill_convnet_params(self.desc, lambda t: C.c_void_p(t.data_ptr()))
+        self.num_actions = int(desc["num_actions"])
+
+    def forward(self, observation) -> dict:
+        """forward.apply(params, state, observation, is_training=False): observation bool [B,H,W,C] on the device."""
+        torch = require_cuda()
+        obs = observation.to(torch.uint8).reshape(observation.shape[0], -1).contiguous()
+        B = obs.shape[0]
+        out = _mlp_out(B, self.num_actions, obs.device)
+        nbytes = load().eaz_convnet_workspace_bytes(C.byref(self.struct), B)
+        if nbytes == 0:
+            raise EazError("eaz_convnet_workspace_bytes rejected the configuration: " + load().eaz_last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=obs.device)
+        check(load().eaz_convnet_forward(C.byref(self.struct), _ptr(obs), B, _ptr(out["exploit_logits"]), _ptr(out["explore_logits"]), _ptr(out["value"]),
+                                         _ptr(out["ube"]), _ptr(out["novelty"]), _ptr(ws), C.c_size_t(nbytes), _stream()), "eaz_convnet_forward")
+        return out
+
+
 # --------------------------------------------------------------------------- search
 def alloc_search_outputs(B, N, A, S, want_tree, device) -> dict:
     torch = require_cuda()

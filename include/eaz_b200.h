@@ -330,6 +330,62 @@ int eaz_search_numeric_status(const eaz_search_config* cfg, const eaz_env* env, 
 int32_t eaz_search_num_launches(const eaz_search_config* cfg, const eaz_env* env);
 
 /* ------------------------------------------------------------------------ */
+/* Convolutional evaluators: EpistemicResidualAZNet               */
+/* (network/resnet.py:41-135, the default for every pgx env that is not       */
+/* DeepSea / Subleq / MinAtar, context.py:76-82) and EpistemicMinatarAZNet    */
+/* (network/minatar.py:11-114) in inference mode: forward.apply(params, state, */
+/* observation, is_training=False), the root / leaf evaluation of             */
+/* selfplay.py:89 and context.py:128-131.  fp32 in the reference's operation  */
+/* order (the EXACT contract of eaz_mlp_forward: bit-identical to the oracle). */
+
+enum { EAZ_CONVNET_RESNET = 0, EAZ_CONVNET_MINATAR = 1 };
+#define EAZ_CONVNET_MAX_BLOCKS 8
+/* haiku parameter / state leaves as device pointers.  hk.Conv2D: w [kh,kw,in,out] (HWIO), b [out]; hk.Linear: w [in,out], b [out];
+ * hk.BatchNorm(create_scale, create_offset, decay 0.9) in inference: scale, offset (params) and the `average` leaves of
+ * mean_ema / var_ema (state), eps = 1e-5. */
+typedef struct eaz_conv { const float* w; const float* b; } eaz_conv;      /* also hk.Linear */
+typedef struct eaz_bn { const float* scale; const float* offset; const float* mean; const float* var; } eaz_bn;
+typedef struct eaz_convnet_params {
+  int32_t kind;          /* EAZ_CONVNET_* */
+  int32_t height, width, in_channels; /* observation [B,H,W,C] bool (pgx board / MinAtar frame) */
+  int32_t num_actions;
+  int32_t num_channels;  /* resnet: 64; minatar: 16 (conv channels) */
+  int32_t hidden;        /* minatar: hidden_layers_size 64; resnet: value / UBE head width = num_channels */
+  int32_t num_blocks;    /* resnet: 5 */
+  int32_t resnet_v2;     /* resnet.py:50 */
+  /* --- resnet (resnet.py:70-135, module call order) */
+  eaz_conv stem;                                   /* az_resnet/conv2_d */
+  eaz_bn stem_bn;                                  /* v1 only (:73-75) */
+  eaz_bn block_bn[EAZ_CONVNET_MAX_BLOCKS][2];      /* block_i/batch_norm, batch_norm_1 */
+  eaz_conv block_conv[EAZ_CONVNET_MAX_BLOCKS][2];  /* block_i/conv2_d, conv2_d_1 */
+  eaz_bn final_bn;                                 /* v2 only (:80-82) */
+  /* heads in call order: [0] main policy, [1] exploration policy, [2] value, [3] ube (:84-124) */
+  eaz_conv head_conv[4];                           /* 1x1 conv to 2 / 2 / 1 / 1 channels */
+  eaz_bn head_bn[4];
+  eaz_conv head_fc[4];                             /* Linear(num_actions) / Linear(num_actions) / Linear(num_channels) x2 */
+  eaz_conv head_out[4];                            /* [2], [3] only: Linear(1) */
+  /* --- minatar (minatar.py:55-95): towers [0] = x1 (main policy + value), [1] = x2 (exploration policy + ube) */
+  eaz_conv tower_conv[2];
+  eaz_conv tower_fc[2][2];
+  eaz_conv mhead_fc[4][2];                         /* [0] main policy, [1] value, [2] exploration policy, [3] ube: Linear(hidden), Linear(out) */
+  /* --- hash-count novelty on the float32 observation (hashes.py:23-38,162-229; H*W*C % 4 == 0) */
+  const uint8_t* binary_set;
+  int32_t hash_bits;
+  float max_u;                /* resnet.py:62 / minatar max_ube */
+  float novelty_scale;        /* max_reward_epistemic_variance */
+  float local_unc_scale;      /* minatar.py:50: 1 / (1 - min(discount, 0.9997)^2); unused for resnet */
+} eaz_convnet_params;
+
+/* Scratch for B observations (activations ping-pong), 256-byte aligned. */
+size_t eaz_convnet_workspace_bytes(const eaz_convnet_params* net, int32_t B);
+/* observation: bool [B,H,W,C].  Outputs as eaz_mlp_forward (any may be NULL): main policy logits [B,A], exploration policy logits
+ * [B,A], value [B] (resnet: tanh, :102; minatar: linear, :69), ube [B] (max(novelty, u), resnet.py:126-128; minatar.py:101-104 with
+ * the local-uncertainty scale and the clip), novelty [B]. */
+int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observation, int32_t B, float* exploit_logits,
+                        float* explore_logits, float* value, float* ube, float* novelty, void* workspace, size_t workspace_bytes,
+                        void* stream);
+
+/* ------------------------------------------------------------------------ */
 /* reanalyze target computation (reanalyze.py:86-129) on the summary of a      */
 /* finished search: the epilogue that follows epistemic_gumbel_muzero_policy   */
 /* in reanalyze().                                                             */

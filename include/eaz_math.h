@@ -196,4 +196,13 @@ EAZ_HD float eaz_log(float x) {
   return eaz_fma(fe, 0.693359375f, y);
 }
 
+/* softplus(x) = log(1 + exp(x)) = max(x, 0) + log(1 + exp(-|x|)) (jax.nn.softplus = logaddexp(x, 0); the UBE head of
+ * /root/reference/src/network/minatar.py:91).  Absolute error <= 1e-7-class: the sum 1 + t rounds for tiny t. */
+EAZ_HD float eaz_softplus(float x) {
+  if (x != x) return x;
+  const float ax = x < 0.0f ? -x : x;
+  const float t = eaz_exp(-ax);
+  return eaz_add(eaz_max(x, 0.0f), eaz_log(eaz_add(1.0f, t)));
+}
+
 #endif /* EAZ_MATH_H_ */

@@ -465,6 +465,160 @@ int orc_hash_update(const float* x, int32_t B, int32_t D, int32_t bits, uint8_t*
 }
 
 /* ------------------------------------------------------------------------ */
+/* Convolutional evaluators in inference mode: EpistemicResidualAZNet          */
+/* (network/resnet.py:41-135) and EpistemicMinatarAZNet (network/minatar.py:   */
+/* 11-114).  Contract shared with csrc/convnet.cu: hk.Conv2D (SAME, NHWC/HWIO) */
+/* = acc = 0; for kh, kw, ci ascending: acc = fma(x, w, acc); + b; hk.Linear =  */
+/* the chain over k ascending; hk.BatchNorm (inference) = (x - mean) * (scale * */
+/* 1/sqrt(var + 1e-5)) + offset, every operation rounded separately.           */
+
+static float orc_bn(const eaz_bn* bn, int c, float x) {
+  const float inv = eaz_mul(bn->scale[c], eaz_div(1.0f, eaz_sqrt(eaz_add(bn->var[c], 1e-5f))));
+  return eaz_add(eaz_mul(eaz_sub(x, bn->mean[c]), inv), bn->offset[c]);
+}
+/* one board: in [H,W,Cin] -> out [H,W,Cout]; pre: BatchNorm + relu on the input (the padding stays zero); post: BatchNorm on the output */
+static void orc_conv3x3(const float* in, int H, int W, int Cin, int Cout, const eaz_conv* c, const eaz_bn* pre, const eaz_bn* post,
+                        const float* residual, int relu_out, float* out) {
+  float* x = (float*)malloc(sizeof(float) * (size_t)H * W * Cin);
+  for (int i = 0; i < H * W * Cin; ++i) {
+    float v = in[i];
+    if (pre) v = eaz_max(orc_bn(pre, i % Cin, v), 0.0f);
+    x[i] = v;
+  }
+  for (int y = 0; y < H; ++y)
+    for (int xx = 0; xx < W; ++xx)
+      for (int co = 0; co < Cout; ++co) {
+        float acc = 0.0f;
+        for (int kh = 0; kh < 3; ++kh)
+          for (int kw = 0; kw < 3; ++kw) {
+            const int yy = y + kh - 1, xw = xx + kw - 1;
+            const int inside = yy >= 0 && yy < H && xw >= 0 && xw < W;
+            for (int ci = 0; ci < Cin; ++ci) {
+              const float xv = inside ? x[(yy * W + xw) * Cin + ci] : 0.0f; /* SAME padding: zeros take part in the chain */
+              acc = eaz_fma(xv, c->w[((size_t)(kh * 3 + kw) * Cin + ci) * Cout + co], acc);
+            }
+          }
+        float r = eaz_add(acc, c->b[co]);
+        if (post) r = orc_bn(post, co, r);
+        const size_t o = (size_t)(y * W + xx) * Cout + co;
+        if (residual) r = eaz_add(r, residual[o]);
+        if (relu_out) r = eaz_max(r, 0.0f);
+        out[o] = r;
+      }
+  free(x);
+}
+static void orc_dense(const float* x, int K, int N, const eaz_conv* l, const eaz_bn* pre, const eaz_bn* post, int relu, float* y) {
+  for (int n = 0; n < N; ++n) {
+    float acc = 0.0f;
+    for (int k = 0; k < K; ++k) {
+      float v = x[k];
+      if (pre) v = eaz_max(orc_bn(pre, k, v), 0.0f);
+      acc = eaz_fma(v, l->w[(size_t)k * N + n], acc);
+    }
+    acc = eaz_add(acc, l->b[n]);
+    if (post) acc = orc_bn(post, n, acc);
+    if (relu) acc = eaz_max(acc, 0.0f);
+    y[n] = acc;
+  }
+}
+
+int orc_convnet_forward(const eaz_convnet_params* net, const uint8_t* observation, int32_t B, float* exploit_logits, float* explore_logits,
+                        float* value, float* ube, float* novelty) {
+  const int H = net->height, W = net->width, C0 = net->in_channels, C = net->num_channels, A = net->num_actions, HW = H * W, Hd = net->hidden;
+  const int D = HW * C0;
+  if (D % 4 != 0 || net->hash_bits <= 0 || net->hash_bits > 32) return EAZ_ERR_INVALID_ARG; /* hashes.py:154,210 */
+  int fail = 0;
+#pragma omp parallel for schedule(dynamic, 4)
+  for (int b = 0; b < B; ++b) {
+    float* x0 = (float*)malloc(sizeof(float) * (size_t)D);
+    float* bufs[3];
+    for (int i = 0; i < 3; ++i) bufs[i] = (float*)malloc(sizeof(float) * (size_t)HW * C);
+    float* hc = (float*)malloc(sizeof(float) * (size_t)HW * 2);
+    float* hf = (float*)malloc(sizeof(float) * (size_t)(C > Hd ? C : Hd) * 2);
+    float* lg = (float*)malloc(sizeof(float) * (size_t)A);
+    for (int i = 0; i < D; ++i) x0[i] = observation[(size_t)b * D + i] ? 1.0f : 0.0f; /* x.astype(float32) */
+    float v_raw = 0.0f, u_raw = 0.0f;
+    if (net->kind == EAZ_CONVNET_RESNET) {
+      const int v2 = net->resnet_v2 != 0;
+      orc_conv3x3(x0, H, W, C0, C, &net->stem, NULL, v2 ? NULL : &net->stem_bn, NULL, !v2, bufs[0]); /* :70-75 */
+      int cur = 0;
+      for (int i = 0; i < net->num_blocks; ++i) {
+        const int t = (cur + 1) % 3, o = (cur + 2) % 3;
+        if (v2) { /* BlockV2 :28-43 */
+          orc_conv3x3(bufs[cur], H, W, C, C, &net->block_conv[i][0], &net->block_bn[i][0], NULL, NULL, 0, bufs[t]);
+          orc_conv3x3(bufs[t], H, W, C, C, &net->block_conv[i][1], &net->block_bn[i][1], NULL, bufs[cur], 0, bufs[o]);
+        } else { /* BlockV1 :11-24 */
+          orc_conv3x3(bufs[cur], H, W, C, C, &net->block_conv[i][0], NULL, &net->block_bn[i][0], NULL, 1, bufs[t]);
+          orc_conv3x3(bufs[t], H, W, C, C, &net->block_conv[i][1], NULL, &net->block_bn[i][1], bufs[cur], 1, bufs[o]);
+        }
+        cur = o;
+      }
+      for (int h = 0; h < 4; ++h) { /* :84-124 */
+        const int k = h < 2 ? 2 : 1;
+        for (int p = 0; p < HW; ++p) orc_dense(bufs[cur] + (size_t)p * C, C, k, &net->head_conv[h], v2 ? &net->final_bn : NULL, &net->head_bn[h], 1, hc + p * k);
+        if (h < 2) {
+          orc_dense(hc, HW * k, A, &net->head_fc[h], NULL, NULL, 0, lg);
+          float* dst = h == 0 ? exploit_logits : explore_logits;
+          if (dst) memcpy(dst + (size_t)b * A, lg, sizeof(float) * (size_t)A);
+        } else {
+          float o1;
+          orc_dense(hc, HW * k, C, &net->head_fc[h], NULL, NULL, 1, hf);
+          orc_dense(hf, C, 1, &net->head_out[h], NULL, NULL, 0, &o1);
+          if (h == 2) v_raw = o1; else u_raw = o1;
+        }
+      }
+    } else { /* minatar.py:55-95 */
+      float* tower[2] = {hf, hf + Hd};
+      float* f1 = (float*)malloc(sizeof(float) * (size_t)Hd);
+      float* hh = (float*)malloc(sizeof(float) * (size_t)Hd);
+      for (int tw = 0; tw < 2; ++tw) {
+        orc_conv3x3(x0, H, W, C0, C, &net->tower_conv[tw], NULL, NULL, NULL, 1, bufs[0]);
+        orc_dense(bufs[0], HW * C, Hd, &net->tower_fc[tw][0], NULL, NULL, 1, f1);
+        orc_dense(f1, Hd, Hd, &net->tower_fc[tw][1], NULL, NULL, 1, tower[tw]);
+      }
+      for (int h = 0; h < 4; ++h) { /* [0] main policy, [1] value, [2] exploration policy, [3] ube */
+        const int policy = h == 0 || h == 2;
+        orc_dense(tower[h >> 1], Hd, Hd, &net->mhead_fc[h][0], NULL, NULL, 1, hh);
+        if (policy) {
+          orc_dense(hh, Hd, A, &net->mhead_fc[h][1], NULL, NULL, 0, lg);
+          float* dst = h == 0 ? exploit_logits : explore_logits;
+          if (dst) memcpy(dst + (size_t)b * A, lg, sizeof(float) * (size_t)A);
+        } else {
+          float o1;
+          orc_dense(hh, Hd, 1, &net->mhead_fc[h][1], NULL, NULL, 0, &o1);
+          if (h == 1) v_raw = o1; else u_raw = o1;
+        }
+      }
+      free(f1);
+      free(hh);
+    }
+    const uint32_t idx = orc_xxhash_row((const uint32_t*)x0, D, net->hash_bits);
+    const int seen = net->binary_set ? ((net->binary_set[idx >> 3] >> (idx & 7u)) & 1) : 0;
+    const float nov = eaz_mul(seen ? 0.0f : 1.0f, net->novelty_scale);
+    float v, u;
+    if (net->kind == EAZ_CONVNET_RESNET) {
+      v = eaz_tanh(v_raw);                                  /* resnet.py:102 */
+      u = eaz_mul(0.5f, eaz_add(eaz_tanh(u_raw), 1.0f));    /* :114 */
+      u = eaz_max(nov, u);                                  /* :126-128 */
+    } else {
+      v = v_raw;                                            /* minatar.py:69-70 */
+      u = eaz_softplus(u_raw);                              /* :91 */
+      u = eaz_max(eaz_mul(nov, net->local_unc_scale), u);   /* :101-103 */
+      u = eaz_min(eaz_max(u, 0.0f), net->max_u);            /* :104 */
+    }
+    if (value) value[b] = v;
+    if (ube) ube[b] = u;
+    if (novelty) novelty[b] = nov;
+    free(x0);
+    for (int i = 0; i < 3; ++i) free(bufs[i]);
+    free(hc);
+    free(hf);
+    free(lg);
+  }
+  return fail;
+}
+
+/* ------------------------------------------------------------------------ */
 /* EpistemicFullyConnectedAZNet.__call__ (is_training=False),                  */
 /* network/fully_connected.py:41-101                                          */
 

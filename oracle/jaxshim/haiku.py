@@ -133,6 +133,66 @@ class Linear(Module):
         return asarr(_np.dot(x, _np.asarray(w)) + _np.asarray(b))
 
 
+class Conv2D(Module):
+    """hk.Conv2D(output_channels, kernel_shape): NHWC input, HWIO weights, stride 1, SAME zero padding, with bias."""
+
+    def __init__(self, output_channels, kernel_shape, name=None):
+        super().__init__(name=name or "conv2_d")
+        self.output_channels, self.k = output_channels, int(kernel_shape)
+
+    def __call__(self, x):
+        x = _np.asarray(x, _np.float32)
+        B, H, W, Ci = x.shape
+        k, Co = self.k, self.output_channels
+        fan_in = k * k * Ci
+        w = _np.asarray(get_parameter("w", [k, k, Ci, Co], init=initializers.TruncatedNormal(1.0 / _np.sqrt(fan_in))))
+        b = _np.asarray(get_parameter("b", [Co], init=initializers.Constant(0.0)))
+        p = k // 2
+        xp = _np.pad(x, ((0, 0), (p, p), (p, p), (0, 0)))
+        y = _np.zeros((B, H, W, Co), _np.float32)
+        for kh in range(k):
+            for kw in range(k):
+                y += _np.tensordot(xp[:, kh:kh + H, kw:kw + W, :], w[kh, kw], axes=([3], [0])).astype(_np.float32)
+        return asarr(y + b)
+
+
+class ExponentialMovingAverage(Module):
+    def __init__(self, decay, name=None):
+        super().__init__(name=name or "exponential_moving_average")
+        self.decay = decay
+
+    def average(self, shape):
+        return get_state("average", shape, dtype=_np.dtype(_np.float32), init=initializers.Constant(0.0))
+
+
+class BatchNorm(Module):
+    """hk.BatchNorm(create_scale, create_offset, decay_rate) -- inference only (is_training=False, test_local_stats=False):
+    (x - mean_ema.average) * (scale * rsqrt(var_ema.average + eps)) + offset, eps = 1e-5, statistics over all but the channel axis."""
+
+    def __init__(self, create_scale, create_offset, decay_rate, eps=1e-5, name=None):
+        super().__init__(name=name or "batch_norm")
+        self.eps = eps
+        fr = _frame()
+        fr.scope.append(self.module_name)
+        try:  # haiku creates the two moving averages as children named ~/mean_ema, ~/var_ema
+            self.mean_ema = ExponentialMovingAverage(decay_rate, name="~/mean_ema")
+            self.var_ema = ExponentialMovingAverage(decay_rate, name="~/var_ema")
+        finally:
+            fr.scope.pop()
+
+    def __call__(self, x, is_training, test_local_stats=False):
+        assert not is_training and not test_local_stats, "haiku shim: BatchNorm is inference-only"
+        x = _np.asarray(x, _np.float32)
+        c = x.shape[-1]
+        shape = [1] * (x.ndim - 1) + [c]
+        scale = _np.asarray(get_parameter("scale", shape, init=initializers.Constant(1.0)))
+        offset = _np.asarray(get_parameter("offset", shape, init=initializers.Constant(0.0)))
+        mean = _np.asarray(self.mean_ema.average(shape))
+        var = _np.asarray(self.var_ema.average(shape))
+        inv = (scale * (_np.float32(1.0) / _np.sqrt(var + _np.float32(self.eps)))).astype(_np.float32)
+        return asarr(((x - mean) * inv + offset).astype(_np.float32))
+
+
 class Flatten(Module):
     def __init__(self, preserve_dims=1, name=None):
         super().__init__(name=name or "flatten")

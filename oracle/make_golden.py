@@ -356,7 +356,74 @@ def gen_reanalyze():
     print("reanalyze.npz", len(out))
 
 
+# ----------------------------------------------------------------------------- convolutional evaluators (resnet.py / minatar.py)
+def _randomise(tree, rng, positive=()):
+    """Fill every leaf of a haiku pytree with seeded values (weights ~ their init scale, BatchNorm statistics non-trivial)."""
+    out = {}
+    for mod, leaves in tree.items():
+        out[mod] = {}
+        for name, v0 in leaves.items():
+            v = np.asarray(v0)
+            if v.dtype == np.uint8 or name in ("hidden", "counter"):
+                out[mod][name] = v0
+            elif any(mod.endswith(p) for p in positive) and name == "average":  # variances
+                out[mod][name] = jnp.array(rng.uniform(0.3, 2.0, v.shape).astype(np.float32))
+            elif name == "scale":
+                out[mod][name] = jnp.array(rng.uniform(0.5, 1.5, v.shape).astype(np.float32))
+            elif name in ("offset", "b", "average"):
+                out[mod][name] = jnp.array((rng.standard_normal(v.shape) * 0.2).astype(np.float32))
+            else:  # conv / linear weights: haiku's TruncatedNormal(1 / sqrt(fan_in))
+                fan_in = int(np.prod(v.shape[:-1]))
+                out[mod][name] = jnp.array((rng.standard_normal(v.shape).clip(-2, 2) / np.sqrt(fan_in)).astype(np.float32))
+    return out
+
+
+def gen_convnet():
+    from network.resnet import EpistemicResidualAZNet
+    from network.minatar import EpistemicMinatarAZNet
+
+    rng = np.random.default_rng(7)
+    out = {}
+    cases = [("resnet_v2", EpistemicResidualAZNet, dict(num_actions=65, resnet_v2=True), (8, 8, 2)),          # an othello-sized board
+             ("resnet_v1", EpistemicResidualAZNet, dict(num_actions=10, resnet_v2=False, num_blocks=2), (6, 6, 4)),
+             ("minatar", EpistemicMinatarAZNet, dict(num_actions=6, discount=0.99), (10, 10, 4))]              # MinAtar frame, 4 channels
+    for tag, cls, kw, (H, W, Cc) in cases:
+        def fwd(x, update_hash=False):
+            net = cls(hash_class=XXHash, hash_args=dict(bits_per_hash=24), **kw)
+            return net(x, is_training=False, test_local_stats=False, update_hash=update_hash)
+
+        f = hk.without_apply_rng(hk.transform_with_state(fwd))
+        B = 6
+        obs = rng.random((B, H, W, Cc)) < 0.3
+        params, state = f.init(None, jnp.array(obs))
+        params = _randomise(params, rng)
+        state = _randomise(state, rng, positive=("var_ema",))
+        _, state = f.apply(params, state, jnp.array(obs[: B // 2]), update_hash=True)  # half of the batch becomes "seen"
+        outs, _ = f.apply(params, state, jnp.array(obs))
+        out[f"{tag}_obs"] = obs.astype(np.uint8)
+        for name, v in zip(("exploit", "explore", "value", "ube", "novelty"), outs):
+            out[f"{tag}_{name}"] = np_(v, np.float32)
+        for mod, leaves in params.items():
+            for name, v in leaves.items():
+                out[f"{tag}_P|{mod}|{name}"] = np_(v, np.float32)
+        for mod, leaves in state.items():
+            for name, v in leaves.items():
+                if name == "binary_set":
+                    bs = np_(v)
+                    out[f"{tag}_set_idx"] = np.flatnonzero(bs).astype(np.int64)
+                    out[f"{tag}_set_val"] = bs[out[f"{tag}_set_idx"]]
+                    out[f"{tag}_set_mod"] = np.array(mod)
+                elif name == "average":
+                    out[f"{tag}_S|{mod}|{name}"] = np_(v, np.float32)
+    np.savez_compressed(os.path.join(OUT, "convnet.npz"), **out)
+    print("convnet.npz", len(out))
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "convnet":
+        gen_convnet()
+        sys.exit(0)
+    gen_convnet()
     gen_reanalyze()
     gen_deepsea()
     gen_hash()

@@ -379,3 +379,24 @@ def softmax(x) -> np.ndarray:
     p = np.zeros_like(x)
     lib().orc_softmax_probe(_ptr(x), x.size, _ptr(p))
     return p
+
+
+# --------------------------------------------------------------------------- convolutional evaluators (resnet.py / minatar.py)
+def convnet_forward(desc: dict, observation) -> dict:
+    """desc: _abi.convnet_description(...) with numpy leaves; observation bool [B,H,W,C]."""
+    keep = []
+
+    def ptr(a):
+        a = np.ascontiguousarray(a, dtype=np.uint8 if np.asarray(a).dtype == np.uint8 else np.float32)
+        keep.append(a)
+        return a.ctypes.data_as(C.c_void_p)
+
+    s = _abi.fill_convnet_params(desc, ptr)
+    obs = np.ascontiguousarray(observation, np.uint8).reshape(len(observation), -1)
+    B, A = obs.shape[0], desc["num_actions"]
+    out = dict(exploit_logits=np.zeros((B, A), np.float32), explore_logits=np.zeros((B, A), np.float32), value=np.zeros(B, np.float32),
+               ube=np.zeros(B, np.float32), novelty=np.zeros(B, np.float32))
+    _chk(lib().orc_convnet_forward(C.byref(s), _ptr(obs), B, _ptr(out["exploit_logits"]), _ptr(out["explore_logits"]), _ptr(out["value"]),
+                                   _ptr(out["ube"]), _ptr(out["novelty"])), "convnet_forward")
+    return out
+

@@ -130,3 +130,61 @@ def uncompact(env, emb):
     st["solved"][:] = (emb[:, 35] >> 2) & 1
     st["memory"][:] = emb[:, 40:40 + env.word_size]
     return st
+
+
+# --------------------------------------------------------------------------- convolutional evaluators
+CONVNET_CASES = {"resnet_v2": dict(kind=_abi.CONVNET_RESNET, num_actions=65, resnet_v2=True, num_blocks=5),
+                 "resnet_v1": dict(kind=_abi.CONVNET_RESNET, num_actions=10, resnet_v2=False, num_blocks=2),
+                 "minatar": dict(kind=_abi.CONVNET_MINATAR, num_actions=6, discount=0.99)}
+
+
+def load_convnet_golden(g, tag):
+    """tests/golden/convnet.npz -> (description for _abi.fill_convnet_params, observation, expected outputs)."""
+    params, state = {}, {}
+    for key in g.files:
+        if key.startswith(f"{tag}_P|") or key.startswith(f"{tag}_S|"):
+            _, mod, name = key.split("|")
+            (params if key.startswith(f"{tag}_P|") else state).setdefault(mod, {})[name] = g[key]
+    bset = np.zeros(1 << 21, np.uint8)
+    bset[g[f"{tag}_set_idx"]] = g[f"{tag}_set_val"]
+    state[str(g[f"{tag}_set_mod"])] = {"binary_set": bset}
+    obs = g[f"{tag}_obs"]
+    _, H, W, Cc = obs.shape
+    kw = dict(CONVNET_CASES[tag])
+    desc = _abi.convnet_description(params, state, kw.pop("kind"), H, W, Cc, kw.pop("num_actions"), **kw)
+    exp = {k: g[f"{tag}_{k}"] for k in ("exploit", "explore", "value", "ube", "novelty")}
+    return desc, obs, exp
+
+
+def random_convnet(kind, H, W, Cc, A, seed=0, num_channels=None, hidden=64, num_blocks=5, resnet_v2=True, fill=0.5):
+    """A seeded random network description (numpy leaves) without going through haiku pytrees."""
+    rng = np.random.default_rng(seed)
+    C_ = num_channels or (64 if kind == _abi.CONVNET_RESNET else 16)
+
+    def cv(*shape):
+        fan_in = int(np.prod(shape[:-1]))
+        return dict(w=(rng.standard_normal(shape).clip(-2, 2) / np.sqrt(fan_in)).astype(np.float32), b=(rng.standard_normal(shape[-1]) * 0.2).astype(np.float32))
+
+    def bn(c):
+        return dict(scale=rng.uniform(0.5, 1.5, c).astype(np.float32), offset=(rng.standard_normal(c) * 0.2).astype(np.float32),
+                    mean=(rng.standard_normal(c) * 0.2).astype(np.float32), var=rng.uniform(0.3, 2.0, c).astype(np.float32))
+
+    bset = ((rng.random(1 << 21) < fill) * rng.integers(1, 256, 1 << 21)).astype(np.uint8)
+    d = dict(kind=kind, height=H, width=W, in_channels=Cc, num_actions=A, num_channels=C_, hidden=C_ if kind == _abi.CONVNET_RESNET else hidden,
+             num_blocks=num_blocks if kind == _abi.CONVNET_RESNET else 0, resnet_v2=int(resnet_v2), binary_set=bset, hash_bits=24, max_u=1.0,
+             novelty_scale=1.0, local_unc_scale=1.0 / (1 - 0.99 ** 2))
+    if kind == _abi.CONVNET_RESNET:
+        d["stem"] = cv(3, 3, Cc, C_)
+        d["stem_bn"], d["final_bn"] = bn(C_), bn(C_)
+        d["blocks"] = [dict(bn=[bn(C_), bn(C_)], conv=[cv(3, 3, C_, C_), cv(3, 3, C_, C_)]) for _ in range(num_blocks)]
+        d["heads"] = []
+        for h in range(4):
+            k = 2 if h < 2 else 1
+            hd = dict(conv=cv(C_, k), bn=bn(k), fc=cv(H * W * k, A if h < 2 else C_))
+            if h >= 2:
+                hd["out"] = cv(C_, 1)
+            d["heads"].append(hd)
+    else:
+        d["towers"] = [dict(conv=cv(3, 3, Cc, C_), fc=[cv(H * W * C_, hidden), cv(hidden, hidden)]) for _ in range(2)]
+        d["mheads"] = [[cv(hidden, hidden), cv(hidden, A if h in (0, 2) else 1)] for h in range(4)]
+    return d

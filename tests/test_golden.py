@@ -9,6 +9,7 @@ import pytest
 
 from e_alphazero_b200 import _abi
 from oracle import oracle as O
+from tests import helpers as H
 
 RTOL = 1e-5
 ATOL = 2e-6
@@ -311,3 +312,19 @@ try:
         assert all((again[k] == out[k]).all() for k in ("action", "children_index", "node_visits"))
 except ImportError:  # pragma: no cover
     pass
+
+
+@pytest.mark.parametrize("tag", ["resnet_v2", "resnet_v1", "minatar"])
+def test_convnet_oracle_matches_reference_modules(golden_dir, tag):
+    """EpistemicResidualAZNet (v2 as configured by the reference, and v1) / EpistemicMinatarAZNet: the reference's own modules executed
+    on the numpy stand-in (oracle/make_golden.py gen_convnet) vs the oracle's fixed-order fp32 restatement."""
+    g = np.load(os.path.join(golden_dir, "convnet.npz"))
+    desc, obs, exp = H.load_convnet_golden(g, tag)
+    got = O.convnet_forward(desc, obs)
+    np.testing.assert_allclose(got["exploit_logits"], exp["exploit"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(got["explore_logits"], exp["explore"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(got["value"], exp["value"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got["ube"], exp["ube"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_array_equal(got["novelty"], exp["novelty"])
+    assert 0 < exp["novelty"].sum() < len(exp["novelty"])  # both seen and unseen observations
+

@@ -927,3 +927,59 @@ def test_search_many_simulations(ops, kind, kw, B, n):
     exp, got = run_both(ops, env, net, root, dict(num_simulations=n, discount=0.97))
     assert_tree_equal(exp, got)
     assert (got["node_visits"][:, 0] == n + 1).all()
+
+
+# ----------------------------------------------------------------------------- convolutional evaluators
+CONVNET_SHAPES = [
+    ("resnet", dict(H=8, W=8, Cc=2, A=65), 37),                                   # othello-sized board, the reference's 64 channels x 5 blocks
+    ("resnet", dict(H=19, W=19, Cc=16, A=362, num_blocks=2), 5),                   # go-sized board: 113 KB tile per CTA
+    ("resnet", dict(H=6, W=7, Cc=2, A=7, resnet_v2=False, num_blocks=3), 130),     # connect-four-sized, BlockV1
+    ("resnet", dict(H=3, W=3, Cc=4, A=9, num_channels=32, num_blocks=1), 300),
+    ("minatar", dict(H=10, W=10, Cc=4, A=6), 129),
+    ("minatar", dict(H=10, W=10, Cc=10, A=3, hidden=32), 17),
+]
+
+
+@pytest.mark.parametrize("kind,kw,B", CONVNET_SHAPES)
+def test_convnet_bit_exact(ops, kind, kw, B):
+    """eaz_convnet_forward (csrc/convnet.cu) vs the oracle's fixed-order fp32 restatement of resnet.py / minatar.py: every output bit."""
+    import torch
+
+    kw = dict(kw)
+    k = _abi.CONVNET_RESNET if kind == "resnet" else _abi.CONVNET_MINATAR
+    Hh, W, Cc, A = kw.pop("H"), kw.pop("W"), kw.pop("Cc"), kw.pop("A")
+    desc = H.random_convnet(k, Hh, W, Cc, A, seed=B, **kw)
+    rng = np.random.default_rng(B + 1)
+    obs = (rng.random((B, Hh, W, Cc)) < 0.35).astype(np.uint8)
+    obs[B // 2:] = obs[: B - B // 2]  # repeated observations hash alike
+    exp = O.convnet_forward(desc, obs)
+    net = ops.ConvNetParams(desc)
+    got = net.forward(torch.as_tensor(obs).cuda())
+    for name in ("exploit_logits", "explore_logits", "value", "ube", "novelty"):
+        H.assert_same_bits(host(got[name]), exp[name], f"{kind} {name}")
+    assert 0 < exp["novelty"].sum() < B
+
+
+@pytest.mark.parametrize("tag", ["resnet_v2", "resnet_v1", "minatar"])
+def test_convnet_golden(ops, golden_dir, tag):
+    """... and against the reference's own modules (golden file generated by executing resnet.py / minatar.py), 1e-5."""
+    import os
+
+    import torch
+
+    g = np.load(os.path.join(golden_dir, "convnet.npz"))
+    desc, obs, exp = H.load_convnet_golden(g, tag)
+    got = {k: host(v) for k, v in ops.ConvNetParams(desc).forward(torch.as_tensor(obs).cuda()).items()}
+    np.testing.assert_allclose(got["exploit_logits"], exp["exploit"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(got["explore_logits"], exp["explore"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(got["value"], exp["value"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(got["ube"], exp["ube"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_array_equal(got["novelty"], exp["novelty"])
+
+
+def test_convnet_rejects_bad_arguments(ops):
+    desc = H.random_convnet(_abi.CONVNET_RESNET, 19, 19, 17, 362, num_blocks=1)  # 19 * 19 * 17 is not a multiple of 4 (hashes.py:210)
+    import torch
+
+    with pytest.raises(ops.EazError, match="multiple of 4"):
+        ops.ConvNetParams(desc).forward(torch.zeros((2, 19, 19, 17), dtype=torch.uint8, device="cuda"))
