@@ -25,6 +25,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--quick", action="store_true")
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--no-cpu", action="store_true")
+ap.add_argument("--streams", type=int, default=3, help="EAZ_FLAG_STREAMS sub-batches (measured best for Subleq: 3)")
 args = ap.parse_args()
 world, rank, local = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
@@ -84,7 +85,7 @@ for B in Bs:
         if (n + 1) * Bl * ws >= 2 ** 31:
             continue
         try:
-            r = ReanalyzeRunner(env, net, Bl, n, gamma, reanalyze_beta=0.0, exploration_beta=0.0, mlp_mode=_abi.MLP_TENSOR, device=dev, seed=rank, use_graph=True)
+            r = ReanalyzeRunner(env, net, Bl, n, gamma, reanalyze_beta=0.0, exploration_beta=0.0, mlp_mode=_abi.MLP_TENSOR, device=dev, seed=rank, use_graph=True, streams=args.streams)
             for _ in range(2):
                 r(first, second)
             torch.cuda.synchronize()
