@@ -134,6 +134,7 @@ class EazConvnetParams(C.Structure):
         ("head_conv", EazConv * 4), ("head_bn", EazBn * 4), ("head_fc", EazConv * 4), ("head_out", EazConv * 4),
         ("tower_conv", EazConv * 2), ("tower_fc", (EazConv * 2) * 2), ("mhead_fc", (EazConv * 2) * 4),
         ("binary_set", _p), ("hash_bits", C.c_int32), ("max_u", C.c_float), ("novelty_scale", C.c_float), ("local_unc_scale", C.c_float),
+        ("mlp_mode", C.c_int32),
     ]
 
 
@@ -146,6 +147,7 @@ def fill_convnet_params(desc: dict, ptr) -> EazConvnetParams:
     for k in ("max_u", "novelty_scale", "local_unc_scale"):
         setattr(s, k, float(desc[k]))
     s.binary_set = ptr(desc["binary_set"])
+    s.mlp_mode = int(desc.get("mlp_mode", MLP_EXACT))
 
     def conv(dst, d):
         dst.w, dst.b = ptr(d["w"]), ptr(d["b"])

@@ -26,7 +26,7 @@ EXPORTS = [
     "eaz_mlp_forward", "eaz_mlp_forward_states",
     "eaz_search_workspace_bytes", "eaz_search_gumbel", "eaz_search_gumbel_profiled", "eaz_search_num_launches", "eaz_search_numeric_status",
     "eaz_reanalyze_targets",
-    "eaz_convnet_workspace_bytes", "eaz_convnet_forward",
+    "eaz_convnet_workspace_bytes", "eaz_convnet_forward", "eaz_convnet_numeric_status",
 ]
 
 

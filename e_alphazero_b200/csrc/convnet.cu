@@ -15,9 +15,11 @@
 //                    convolutions), per-output BatchNorm, ReLU: serves hk.Linear AND the 1x1 convolutions (rows = B * H * W)
 //   convnet_finish_kernel   tanh / softplus, the hash-count novelty of the float32 observation (XXHash, hashes.py:162-229) and
 //                    max(novelty, u) (resnet.py:126-128, minatar.py:101-104)
-#include "common.cuh"
+#include "mlp.cuh"
+#include "umma.cuh"
 
 namespace eaz {
+using namespace umma;
 
 struct BnDev {
   const float *scale, *offset, *mean, *var;  // scale == nullptr: no BatchNorm
@@ -29,11 +31,24 @@ __device__ __forceinline__ float bn_apply(const BnDev& bn, int c, float x) {  //
   return __fadd_rn(__fmul_rn(__fsub_rn(x, bn.mean[c]), bn_inv(bn, c)), bn.offset[c]);
 }
 
+// ---- TENSOR mode operand format: per pixel [hi 64 halves | lo 64 halves] of relu(bn_next(x)) * 16 (the scaled 3xFP16 split of mlp.cuh)
+constexpr int kAct16Bytes = 256;
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
+__device__ __forceinline__ void act16_split(const BnDev& bn, int c, float x, __half& hi, __half& lo, uint32_t* num_flags) {
+  float v = __fmul_rn(fmaxf(bn_apply(bn, c, x), 0.0f), kActScale);
+  if (!(v <= 65504.0f)) {  // range guard: clamped AND reported (eaz_convnet_numeric_status)
+    atomicOr(num_flags, kNumActSaturated);
+    v = 65504.0f;
+  }
+  split_f16(v, hi, lo);
+}
+
 // ------------------------------------------------------------------------------------------------ 3x3 convolution, SAME padding
 // in: fp32 [B,H,W,Cin] or (obs != nullptr) bool [B,H,W,Cin]; w: [3,3,Cin,Cout]; out: fp32 [B,H,W,Cout]; Cout % 4 == 0, Cout / 4 | 256
 __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const uint8_t* __restrict__ obs, int H, int W, int Cin, int Cout,
                                                       const float* __restrict__ w, const float* __restrict__ bias, BnDev pre, BnDev post,
-                                                      const float* __restrict__ residual, int relu_out, float* __restrict__ out) {
+                                                      const float* __restrict__ residual, int relu_out, float* __restrict__ out,
+                                                      uint8_t* __restrict__ act16_out, BnDev next_bn, uint32_t* num_flags) {
   extern __shared__ __align__(16) float s_in[];  // [(H + 2) * (W + 2)][Cin], zero halo
   const int b = blockIdx.x, HW = H * W, W2 = W + 2;
   const size_t base = (size_t)b * HW * Cin;
@@ -93,8 +108,223 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
       }
       if (relu_out) r = make_float4(fmaxf(r.x, 0.0f), fmaxf(r.y, 0.0f), fmaxf(r.z, 0.0f), fmaxf(r.w, 0.0f));
       *reinterpret_cast<float4*>(out + o) = r;
+      if (act16_out) {  // TENSOR mode: the next convolution's A operand, pre-activated and split (conv_tensor_kernel below)
+        const float rr[4] = {r.x, r.y, r.z, r.w};
+        __half hi[4], lo[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) act16_split(next_bn, 4 * cg + q, rr[q], hi[q], lo[q], num_flags);
+        uint8_t* a16 = act16_out + ((size_t)b * HW + p) * kAct16Bytes + (size_t)(4 * cg) * 2;
+        *reinterpret_cast<uint2*>(a16) = make_uint2(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]));
+        *reinterpret_cast<uint2*>(a16 + kAct16Bytes / 2) = make_uint2(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]));
+      }
     }
   }
+}
+
+// ------------------------------------------------------------------------------------------------ 3x3 convolution 64 -> 64 on tcgen05
+// Implicit GEMM: one CTA = 128 consecutive output pixels (M) x 64 output channels (N), K = 9 taps x 64 input channels = 18 chunks of
+// 32.  The A operand of chunk (tap, ci-half) is a pure GATHER of the shifted pixels' pre-activated fp16 hi / lo rows (written once by
+// the producing layer's epilogue; rows outside the board come from a zero page), copied into the UMMA K-major core-matrix layout by 8
+// producer warps exactly as mlp_gather.cu copies its layer-1 rows; the weight chunk images (tile_weights.cu, [hi 64x32 | lo 64x32]) arrive
+// by 1-D bulk async copies; one elected lane issues tcgen05.mma kind::f16 M=128 N=64 K=16, three split products per K-step, fp32
+// accumulators in 64 TMEM columns.  Epilogue (the same 8 warps, straight out of TMEM): x unscale + bias, + residual, fp32 store, and the
+// NEXT layer's operand: relu(bn_next(.)) x 16, clamp + flag, hi / lo split.  99 KB of shared memory: two CTAs per SM.
+namespace ct {
+constexpr int kTM = 128, kC = 64, kCK = 32, kChunks = 9 * kC / kCK, kStages = 4;
+constexpr int kAHalf = kTM * kCK * 2, kAStage = 2 * kAHalf;  // 8 KB hi + 8 KB lo
+constexpr int kBHalf = kC * kCK * 2, kBStage = 2 * kBHalf;    // 4 KB hi + 4 KB lo
+constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;             // 512 B
+struct Smem {
+  uint64_t full_a[kStages], full_b[kStages], empty[kStages], acc_done;
+  uint32_t tmem_base;
+  alignas(16) float bias[kC];
+};
+constexpr size_t kSmemBytes = (size_t)kStages * (kAStage + kBStage) + sizeof(Smem) + 1024;
+}  // namespace ct
+
+struct ConvTensorArgs {
+  const uint8_t* act16_in;  // [P][hi 64 halves | lo 64 halves]
+  const uint8_t* zero_page; // >= 256 zero bytes
+  const uint8_t* wimg;      // 18 chunk images
+  const float* wscale;      // the power-of-two scale the image carries
+  const float* bias;        // [64]
+  const float* residual;    // fp32 [P][64] or nullptr
+  float* out_raw;           // fp32 [P][64] or nullptr
+  uint8_t* act16_out;       // or nullptr
+  BnDev next_bn;            // pre-activation of the consumer of act16_out
+  uint32_t* num_flags;
+  int P, H, W;              // P = B * H * W pixels
+};
+
+__global__ void __launch_bounds__(320, 2) conv_tensor_kernel(const ConvTensorArgs a) {
+  using namespace ct;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + kStages * kAStage;
+  Smem* sh = reinterpret_cast<Smem*>(sB + kStages * kBStage);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P0 = blockIdx.x * kTM, HW = a.H * a.W;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&sh->full_a[s], 8);  // one elected arrive per producer warp
+      mbar_init(&sh->full_b[s], 1);
+      mbar_init(&sh->empty[s], 1);
+    }
+    mbar_init(&sh->acc_done, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < kC) sh->bias[threadIdx.x] = __ldg(a.bias + threadIdx.x);
+  if (warp == 8) {
+    tmem_alloc(&sh->tmem_base, kC);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sh->tmem_base;
+  auto issue_b = [&](int c) {
+    const int s = c % kStages;
+    mbar_arrive_expect_tx(&sh->full_b[s], (uint32_t)kBStage);
+    bulk_g2s(sB + s * kBStage, a.wimg + (size_t)c * kBStage, kBStage, &sh->full_b[s]);
+  };
+
+  if (warp == 9) {
+    // ================= weight-copy warp =================
+    if (lane == 0) {
+      for (int c = 0; c < kChunks; ++c) {
+        if (c >= kStages) mbar_wait(&sh->empty[c % kStages], ((c / kStages) & 1) ^ 1);
+        issue_b(c);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ================= MMA-issue warp: warp-uniform loop, one elected lane issues =================
+    const uint32_t desc_hi = (uint32_t)(kSBO >> 4) | (1u << 14);  // SBO [32,46) + version=1 [46,48)
+    const uint32_t lbo_bits = (uint32_t)(kCoreBytes >> 4) << 16;  // LBO [16,30)
+    auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
+    const uint32_t idesc = idesc_f16(kTM, kC);
+    const uint32_t a_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | lbo_bits, b_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | lbo_bits;
+#pragma unroll 1
+    for (int c = 0; c < kChunks; ++c) {
+      const int s = c % kStages, ph = (c / kStages) & 1;
+      mbar_wait(&sh->full_b[s], ph);
+      mbar_wait(&sh->full_a[s], ph);
+      tc_fence_after();
+      const uint32_t al = a_base + (uint32_t)((s * kAStage) >> 4), bl = b_base + (uint32_t)((s * kBStage) >> 4);
+      if (elect_one()) {
+#pragma unroll
+        for (int j = 0; j < kCK / 16; ++j) {
+          const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
+          mma_f16(tmem, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
+          mma_f16(tmem, mk(al + o), mk(bl + (kBHalf >> 4) + o), idesc, 1);
+          mma_f16(tmem, mk(al + (kAHalf >> 4) + o), mk(bl + o), idesc, 1);
+        }
+        mma_commit(&sh->empty[s]);
+        if (c == kChunks - 1) mma_commit(&sh->acc_done);
+      }
+      __syncwarp();
+    }
+  } else {
+    // ================= workers: the shifted-pixel gather, then the epilogue out of TMEM =================
+    const int part = warp >> 2, wq = warp & 3;  // hi / lo halves; rows [32 wq, 32 wq + 32)
+    const int piece = lane & 3;
+    int Pj[4], yj[4], xj[4];
+    uint32_t doff[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int rj = 32 * wq + 8 * j + (lane >> 2);
+      Pj[j] = P0 + rj;
+      const int p = Pj[j] < a.P ? Pj[j] % HW : -(1 << 20);  // dead rows: every tap falls outside the board
+      yj[j] = p >= 0 ? p / a.W : -(1 << 20);
+      xj[j] = p >= 0 ? p % a.W : 0;
+      doff[j] = (uint32_t)(part * kAHalf + tile_offset_h32(rj, piece * 8));
+    }
+    uint4 v[3][4];  // chunks in flight: two ahead of the one being stored
+    auto load_a = [&](int c, uint4 (&x)[4]) {
+      const int tap = c >> 1, kh = tap / 3 - 1, kw = tap % 3 - 1, ci0 = (c & 1) * kCK;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int yy = yj[j] + kh, xx = xj[j] + kw;
+        const bool in = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;  // SAME padding: zeros outside the board
+        const uint8_t* src = in ? a.act16_in + (size_t)(Pj[j] + kh * a.W + kw) * kAct16Bytes + part * (kAct16Bytes / 2) + ci0 * 2 + piece * 16
+                                : a.zero_page + piece * 16;
+        x[j] = __ldg(reinterpret_cast<const uint4*>(src));
+      }
+    };
+    auto store_a = [&](int c, const uint4 (&x)[4]) {
+      const int s = c % kStages;
+      if (c >= kStages) mbar_wait_warp(&sh->empty[s], ((c / kStages) & 1) ^ 1);  // the MMAs of chunk c - kStages have completed
+      uint8_t* dst = sA + s * kAStage;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + doff[j]) = x[j];
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->full_a[s]);
+    };
+    load_a(0, v[0]);
+    load_a(1, v[1]);
+#pragma unroll
+    for (int c = 0; c < kChunks; ++c) {
+      if (c + 2 < kChunks) load_a(c + 2, v[(c + 2) % 3]);
+      store_a(c, v[c % 3]);
+    }
+
+    // ---- epilogue: this thread's row (TMEM lane), 32 of the 64 channels
+    const int row = 32 * wq + lane, Pr = P0 + row;
+    const bool live = Pr < a.P;
+    const int cbase = part * (kC / 2);
+    const float unscale = 1.0f / (kActScale * __ldg(a.wscale));  // exact: powers of two
+    mbar_wait_warp(&sh->acc_done, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)cbase;
+    uint32_t ra[16], rb[16];
+    tmem_ld16(taddr, ra);
+    tmem_ld16(taddr + 16, rb);
+    tmem_ld_wait();
+    if (live) {
+      float val[32];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        val[i] = __fmaf_rn(__uint_as_float(ra[i]), unscale, sh->bias[cbase + i]);
+        val[16 + i] = __fmaf_rn(__uint_as_float(rb[i]), unscale, sh->bias[cbase + 16 + i]);
+      }
+      const size_t o = (size_t)Pr * kC + cbase;
+      if (a.residual) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 r4 = *reinterpret_cast<const float4*>(a.residual + o + 4 * q);
+          val[4 * q] = __fadd_rn(val[4 * q], r4.x); val[4 * q + 1] = __fadd_rn(val[4 * q + 1], r4.y);
+          val[4 * q + 2] = __fadd_rn(val[4 * q + 2], r4.z); val[4 * q + 3] = __fadd_rn(val[4 * q + 3], r4.w);
+        }
+      }
+      if (a.out_raw) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(a.out_raw + o + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+      }
+      if (a.act16_out) {
+        uint8_t* a16 = a.act16_out + (size_t)Pr * kAct16Bytes + (size_t)cbase * 2;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {  // 8 channels = 16 bytes of hi and of lo per store
+          uint32_t h[4], l[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            __half h0, l0, h1, l1;
+            act16_split(a.next_bn, cbase + 8 * q + 2 * e, val[8 * q + 2 * e], h0, l0, a.num_flags);
+            act16_split(a.next_bn, cbase + 8 * q + 2 * e + 1, val[8 * q + 2 * e + 1], h1, l1, a.num_flags);
+            h[e] = pack_h2(h0, h1);
+            l[e] = pack_h2(l0, l1);
+          }
+          *reinterpret_cast<uint4*>(a16 + 16 * q) = make_uint4(h[0], h[1], h[2], h[3]);
+          *reinterpret_cast<uint4*>(a16 + kAct16Bytes / 2 + 16 * q) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 8) tmem_dealloc(tmem, ct::kC);
 }
 
 // ------------------------------------------------------------------------------------------------ rows x K @ K x N
@@ -162,12 +392,13 @@ static BnDev bn_of(const eaz_bn& b) { return BnDev{b.scale, b.offset, b.mean, b.
 static const BnDev kNoBn{nullptr, nullptr, nullptr, nullptr};
 
 static int launch_conv3x3(const float* in, const uint8_t* obs, int B, int H, int W, int Cin, int Cout, const eaz_conv& c, BnDev pre, BnDev post,
-                          const float* residual, int relu_out, float* out, cudaStream_t st) {
+                          const float* residual, int relu_out, float* out, cudaStream_t st, uint8_t* act16_out = nullptr, BnDev next_bn = BnDev{},
+                          uint32_t* num_flags = nullptr) {
   const size_t smem = (size_t)(H + 2) * (W + 2) * Cin * sizeof(float);
   if (smem > 48 * 1024)
     if (cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e != cudaSuccess)
       return cuda_fail(e, "conv3x3_kernel shared memory");
-  conv3x3_kernel<<<B, 256, smem, st>>>(in, obs, H, W, Cin, Cout, c.w, c.b, pre, post, residual, relu_out, out);
+  conv3x3_kernel<<<B, 256, smem, st>>>(in, obs, H, W, Cin, Cout, c.w, c.b, pre, post, residual, relu_out, out, act16_out, next_bn, num_flags);
   EAZ_CHECK_LAUNCH("conv3x3_kernel");
   return 0;
 }
@@ -195,6 +426,11 @@ static int check_convnet(const eaz_convnet_params* n) {
                 n->height * n->width * n->in_channels);
   EAZ_CHECK_ARG(n->hash_bits > 0 && n->hash_bits <= 32, "bits_per_hash %d outside (0, 32] (hashes.py:154)", n->hash_bits);
   if (n->kind == EAZ_CONVNET_RESNET) EAZ_CHECK_ARG(n->num_blocks >= 0 && n->num_blocks <= EAZ_CONVNET_MAX_BLOCKS, "convnet: num_blocks outside [0, 8]");
+  EAZ_CHECK_ARG(n->mlp_mode == EAZ_MLP_EXACT || n->mlp_mode == EAZ_MLP_TENSOR, "convnet: unknown mlp_mode %d", n->mlp_mode);
+  if (n->mlp_mode == EAZ_MLP_TENSOR && !(n->kind == EAZ_CONVNET_RESNET && n->resnet_v2 && n->num_channels == 64)) {
+    set_error("convnet: mlp_mode TENSOR covers EpistemicResidualAZNet v2 with 64 channels (the reference configuration); use EXACT for this network");
+    return EAZ_ERR_UNSUPPORTED;
+  }
   const size_t tile = (size_t)(n->height + 2) * (n->width + 2) * (size_t)max(n->in_channels, n->num_channels) * sizeof(float);
   if (tile > 200 * 1024) {
     set_error("convnet: a %dx%d board with %d channels does not fit the one-board-per-CTA convolution", n->height, n->width, max(n->in_channels, n->num_channels));
@@ -205,14 +441,42 @@ static int check_convnet(const eaz_convnet_params* n) {
 
 struct ConvnetLayout {
   size_t act, small, total;  // three activation buffers of `act` floats, then `small` floats of head scratch (bump-allocated)
+  // TENSOR mode, behind them (byte offsets from the workspace base): two act16 buffers, the weight images, zero page + status blocks
+  size_t act16_off, act16_bytes, wimg_off, wimg_bytes, zero_off, status_off;
 };
+constexpr size_t kConvImgBytes = (size_t)ct::kChunks * ct::kBStage;  // 147 456 B per 64 -> 64 convolution
+static bool convnet_tensor(const eaz_convnet_params* n) { return n->mlp_mode == EAZ_MLP_TENSOR; }
 static ConvnetLayout convnet_layout(const eaz_convnet_params* n, int B) {
-  ConvnetLayout L;
+  ConvnetLayout L{};
   const size_t HW = (size_t)n->height * n->width, wide = (size_t)max(n->num_channels, n->hidden);
   L.act = ((size_t)B * HW * n->num_channels + 63) & ~(size_t)63;
   L.small = (size_t)B * (4 * HW * 2 + 10 * wide + 16) + 64 * 24;
   L.total = (3 * L.act + L.small) * sizeof(float);
+  if (convnet_tensor(n)) {
+    L.total = (L.total + 255) & ~(size_t)255;
+    L.act16_off = L.total;
+    L.act16_bytes = ((size_t)B * HW * kAct16Bytes + 255) & ~(size_t)255;
+    L.wimg_off = L.act16_off + 2 * L.act16_bytes;
+    L.wimg_bytes = (size_t)2 * EAZ_CONVNET_MAX_BLOCKS * kConvImgBytes;
+    L.zero_off = L.wimg_off + L.wimg_bytes;
+    L.status_off = L.zero_off + 256;
+    L.total = L.status_off + 2 * sizeof(NumStatus);
+  }
   return L;
+}
+
+static int launch_conv_tensor(const ConvTensorArgs& a, cudaStream_t st) {
+  static bool attr_set[32] = {false};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 32 && !attr_set[dev]) {
+    if (cudaError_t e = cudaFuncSetAttribute(conv_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::kSmemBytes); e != cudaSuccess)
+      return cuda_fail(e, "conv_tensor_kernel shared memory");
+    attr_set[dev] = true;
+  }
+  conv_tensor_kernel<<<ceil_div(a.P, ct::kTM), 320, ct::kSmemBytes, st>>>(a);
+  EAZ_CHECK_LAUNCH("conv_tensor_kernel");
+  return 0;
 }
 
 }  // namespace eaz
@@ -251,9 +515,47 @@ int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observatio
   if (net->kind == EAZ_CONVNET_RESNET) {
     // ---- trunk (resnet.py:69-82)
     const bool v2 = net->resnet_v2 != 0;
+    int cur = 0;
+    if (convnet_tensor(net) && net->num_blocks > 0) {
+      // ---- TENSOR mode: the 2 x num_blocks 64 -> 64 convolutions as tcgen05 implicit GEMMs (conv_tensor_kernel)
+      uint8_t* wsb = (uint8_t*)workspace;
+      uint8_t* a16[2] = {wsb + L.act16_off, wsb + L.act16_off + L.act16_bytes};
+      uint8_t* zero = wsb + L.zero_off;
+      NumStatus* ns = reinterpret_cast<NumStatus*>(wsb + L.status_off);
+      if (cudaError_t e = cudaMemsetAsync(zero, 0, 256, st); e != cudaSuccess) return cuda_fail(e, "convnet zero page");
+      const int nconv = 2 * net->num_blocks;
+      for (int g = 0; g * 12 < nconv; ++g) {  // per-tensor power-of-two scales from max |w| (tile_weights.cu), 12 tensors per status block
+        const float* wl[12];
+        int nl[12];
+        const int cnt = min(12, nconv - 12 * g);
+        for (int m = 0; m < cnt; ++m) {
+          wl[m] = net->block_conv[(12 * g + m) >> 1][(12 * g + m) & 1].w;
+          nl[m] = 9 * C * C;
+        }
+        if (int rc = launch_weight_scales_list(wl, nl, cnt, ns + g, st)) return rc;
+      }
+      auto scale_of = [&](int k) { return &ns[k / 12].wscale[(k % 12) / 3][(k % 12) % 3]; };
+      for (int k = 0; k < nconv; ++k)
+        if (int rc = launch_tile_weights_f16(net->block_conv[k >> 1][k & 1].w, 9 * C, C, 9 * C, C, scale_of(k), wsb + L.wimg_off + (size_t)k * kConvImgBytes, st))
+          return rc;
+      uint32_t* flags = &ns[0].flags;
+      // stem (fp32: K = 9 x in_channels is tiny) -> raw x_0 and the first block's operand relu(bn_0,0(x_0))
+      if (int rc = launch_conv3x3(nullptr, observation, B, H, W, C0, C, net->stem, kNoBn, kNoBn, nullptr, 0, buf[0], st, a16[0], bn_of(net->block_bn[0][0]), flags))
+        return rc;
+      for (int i = 0; i < net->num_blocks; ++i) {  // BlockV2: x_{i+1} = conv2(relu(bn2(conv1(relu(bn1(x_i)))))) + x_i
+        const int o = cur ^ 1;
+        ConvTensorArgs c1{a16[0], zero, wsb + L.wimg_off + (size_t)(2 * i) * kConvImgBytes, scale_of(2 * i), net->block_conv[i][0].b, nullptr, nullptr,
+                          a16[1], bn_of(net->block_bn[i][1]), flags, B * HW, H, W};
+        if (int rc = launch_conv_tensor(c1, st)) return rc;
+        const bool last = i + 1 == net->num_blocks;
+        ConvTensorArgs c2{a16[1], zero, wsb + L.wimg_off + (size_t)(2 * i + 1) * kConvImgBytes, scale_of(2 * i + 1), net->block_conv[i][1].b, buf[cur],
+                          buf[o], last ? nullptr : a16[0], last ? kNoBn : bn_of(net->block_bn[i + 1][0]), flags, B * HW, H, W};
+        if (int rc = launch_conv_tensor(c2, st)) return rc;
+        cur = o;
+      }
+    } else {
     if (int rc = launch_conv3x3(nullptr, observation, B, H, W, C0, C, net->stem, kNoBn, v2 ? kNoBn : bn_of(net->stem_bn), nullptr, v2 ? 0 : 1, buf[0], st))
       return rc;
-    int cur = 0;
     for (int i = 0; i < net->num_blocks; ++i) {
       const int t = (cur + 1) % 3, o = (cur + 2) % 3;
       if (v2) {  // BlockV2 (:28-43): bn -> relu -> conv -> bn -> relu -> conv, + input
@@ -264,6 +566,7 @@ int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observatio
         if (int rc = launch_conv3x3(buf[t], nullptr, B, H, W, C, C, net->block_conv[i][1], kNoBn, bn_of(net->block_bn[i][1]), buf[cur], 1, buf[o], st)) return rc;
       }
       cur = o;
+    }
     }
     // ---- heads (:84-124): 1x1 conv (on relu(bn(x1)) for v2, :80-82) -> bn -> relu -> flatten -> linear [-> relu -> linear]
     const BnDev trunk_bn = v2 ? bn_of(net->final_bn) : kNoBn;
@@ -313,6 +616,29 @@ int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observatio
                                                               net->novelty_scale, net->local_unc_scale, v_raw, u_raw, value, ube, novelty);
   EAZ_CHECK_LAUNCH("convnet_finish_kernel");
   return 0;
+}
+
+int eaz_convnet_numeric_status(const eaz_convnet_params* net, int32_t B, const void* workspace, size_t workspace_bytes, void* stream,
+                               int32_t* flags_out) {
+  if (int rc = check_convnet(net)) return rc;
+  if (flags_out) *flags_out = 0;
+  if (!convnet_tensor(net) || B < 1) return 0;  // the fp32 path has no scaled split
+  const ConvnetLayout L = convnet_layout(net, B);
+  EAZ_CHECK_ARG(workspace && workspace_bytes >= L.total, "convnet numeric status: workspace too small");
+  if (cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream); e != cudaSuccess) return cuda_fail(e, "convnet numeric status sync");
+  uint32_t flags = 0;
+  for (int g = 0; g < 2; ++g) {
+    uint32_t f = 0;
+    const uint8_t* p = (const uint8_t*)workspace + L.status_off + g * sizeof(NumStatus) + offsetof(NumStatus, flags);
+    if (cudaError_t e = cudaMemcpy(&f, p, sizeof(f), cudaMemcpyDeviceToHost); e != cudaSuccess) return cuda_fail(e, "convnet numeric status read");
+    if (g == 0 || 12 * g < 2 * net->num_blocks) flags |= f;
+  }
+  if (flags_out) *flags_out = (int32_t)flags;
+  if (flags == 0) return 0;
+  set_error("tensor-core convolution path out of range:%s%s -- use mlp_mode EXACT for this model",
+            (flags & kNumWeightsNonFinite) ? " a weight tensor holds inf / nan or |w| > 2^20;" : "",
+            (flags & kNumActSaturated) ? " an activation exceeded 4094 (fp16 range of the 16x-scaled split) and was clamped;" : "");
+  return EAZ_ERR_UNSUPPORTED;
 }
 
 }  // extern "C"

@@ -55,6 +55,8 @@ struct NumStatus {
   uint32_t flags;
   uint32_t pad[7];
 };
+int launch_weight_scales_list(const float* const* w, const int* n, int count, NumStatus* ns, cudaStream_t st);                                   // tile_weights.cu
+int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, const float* scale, void* out, cudaStream_t st, int chunk_k = 32);  // tile_weights.cu
 size_t gather_table_bytes(const NetDesc& net);
 int prepare_gather_table(const NetDesc& net, int head, void* buf, uint32_t* num_flags, cudaStream_t st);
 int launch_mlp_gather(const NetDesc& net, const EnvDesc& env, const MlpSource& src, const TensorWeights& tw, int B, int heads_mask,

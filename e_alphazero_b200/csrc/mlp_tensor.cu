@@ -25,7 +25,6 @@
 namespace eaz {
 using namespace umma;
 
-int launch_tile_weights_f16(const float* W, int K, int N, int Kpad, int Npad, const float* scale, void* out, cudaStream_t st, int chunk_k = 32);  // tile_weights.cu
 int launch_weight_scales(const NetDesc& net, int heads_mask, NumStatus* ns, cudaStream_t st);                                                     // tile_weights.cu
 
 constexpr int kTM = 128;                       // rows per CTA

@@ -104,6 +104,21 @@ int launch_weight_scales(const NetDesc& net, int heads_mask, NumStatus* ns, cuda
   return 0;
 }
 
+// the same for an arbitrary list of up to 12 matrices (convnet.cu): slot m -> ns->wscale[m / 3][m % 3]
+int launch_weight_scales_list(const float* const* w, const int* n, int count, NumStatus* ns, cudaStream_t st) {
+  if (cudaError_t e = cudaMemsetAsync(ns, 0, sizeof(NumStatus), st); e != cudaSuccess) return cuda_fail(e, "numeric status memset");
+  WeightList wl{};
+  for (int m = 0; m < 12; ++m) {
+    wl.w[m / 3][m % 3] = m < count ? w[m] : nullptr;
+    wl.n[m / 3][m % 3] = m < count ? n[m] : 0;
+  }
+  weight_max_kernel<<<dim3(16, 12), 256, 0, st>>>(wl, ns);
+  EAZ_CHECK_LAUNCH("weight_max_kernel");
+  weight_scales_kernel<<<1, 32, 0, st>>>(ns);
+  EAZ_CHECK_LAUNCH("weight_scales_kernel");
+  return 0;
+}
+
 int launch_tile_weights(const float* W, int K, int N, int Kpad, int Npad, uint32_t* out, cudaStream_t st, int chunk_k) {
   if (chunk_k == 16) tile_weights_kernel<16><<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, out);
   else tile_weights_kernel<32><<<ceil_div(Kpad * Npad, 256), 256, 0, st>>>(W, K, N, Kpad, Npad, out);

@@ -399,10 +399,19 @@ class ConvNetParams:
         nbytes = load().eaz_convnet_workspace_bytes(C.byref(self.struct), B)
         if nbytes == 0:
             raise EazError("eaz_convnet_workspace_bytes rejected the configuration: " + load().eaz_last_error().decode())
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=obs.device)
+        ws = torch.empty(nbytes + 256, dtype=torch.uint8, device=obs.device)
+        off = (-ws.data_ptr()) % 256
+        self._last = (ws, C.c_void_p(ws.data_ptr() + off), C.c_size_t(nbytes), B)
         check(load().eaz_convnet_forward(C.byref(self.struct), _ptr(obs), B, _ptr(out["exploit_logits"]), _ptr(out["explore_logits"]), _ptr(out["value"]),
-                                         _ptr(out["ube"]), _ptr(out["novelty"]), _ptr(ws), C.c_size_t(nbytes), _stream()), "eaz_convnet_forward")
+                                         _ptr(out["ube"]), _ptr(out["novelty"]), self._last[1], self._last[2], _stream()), "eaz_convnet_forward")
         return out
+
+    def numeric_status(self) -> int:
+        """eaz_convnet_numeric_status on the workspace of the last forward(): raises EazError if the tensor-core path left its range."""
+        _, ptr, nbytes, B = self._last
+        flags = C.c_int32(0)
+        check(load().eaz_convnet_numeric_status(C.byref(self.struct), B, ptr, nbytes, _stream(), C.byref(flags)), "eaz_convnet_numeric_status")
+        return int(flags.value)
 
 
 # --------------------------------------------------------------------------- search

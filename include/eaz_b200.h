@@ -374,6 +374,9 @@ typedef struct eaz_convnet_params {
   float max_u;                /* resnet.py:62 / minatar max_ube */
   float novelty_scale;        /* max_reward_epistemic_variance */
   float local_unc_scale;      /* minatar.py:50: 1 / (1 - min(discount, 0.9997)^2); unused for resnet */
+  int32_t mlp_mode;           /* EAZ_MLP_EXACT: fp32 in the reference's order, bit-identical to the oracle.  EAZ_MLP_TENSOR (resnet v2 with
+                                 64 channels): the 64 -> 64 convolutions of the residual blocks as tcgen05 implicit GEMMs on the scaled
+                                 3xFP16 split (<= 1e-5 of EXACT relative to the magnitude of the terms); stem and heads stay fp32 */
 } eaz_convnet_params;
 
 /* Scratch for B observations (activations ping-pong), 256-byte aligned. */
@@ -384,6 +387,11 @@ size_t eaz_convnet_workspace_bytes(const eaz_convnet_params* net, int32_t B);
 int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observation, int32_t B, float* exploit_logits,
                         float* explore_logits, float* value, float* ube, float* novelty, void* workspace, size_t workspace_bytes,
                         void* stream);
+/* Range guard of mlp_mode TENSOR, as eaz_search_numeric_status: SYNCHRONISES `stream`, reads the sticky flags the last
+ * eaz_convnet_forward on this workspace left (bit 0: a weight tensor non-finite / > 2^20, bit 1: an activation above 4094 was clamped)
+ * and returns EAZ_ERR_UNSUPPORTED with a message if any is set. */
+int eaz_convnet_numeric_status(const eaz_convnet_params* net, int32_t B, const void* workspace, size_t workspace_bytes, void* stream,
+                               int32_t* flags_out);
 
 /* ------------------------------------------------------------------------ */
 /* reanalyze target computation (reanalyze.py:86-129) on the summary of a      */

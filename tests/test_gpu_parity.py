@@ -983,3 +983,38 @@ def test_convnet_rejects_bad_arguments(ops):
 
     with pytest.raises(ops.EazError, match="multiple of 4"):
         ops.ConvNetParams(desc).forward(torch.zeros((2, 19, 19, 17), dtype=torch.uint8, device="cuda"))
+
+
+@pytest.mark.parametrize("Hh,W,Cc,A,B,blocks", [(8, 8, 2, 65, 70, 5), (19, 19, 16, 362, 3, 2), (6, 7, 2, 7, 257, 1), (3, 3, 4, 9, 500, 5)])
+def test_convnet_tensor_mode(ops, Hh, W, Cc, A, B, blocks):
+    """mlp_mode TENSOR: the residual blocks' 64 -> 64 convolutions as tcgen05 implicit GEMMs on the scaled 3xFP16 split
+    (conv_tensor_kernel) against the fp32 oracle.  Bound: 1e-5 of the magnitude of the terms -- here the largest |logit| / 1 for the
+    tanh-squashed heads -- after up to 10 chained convolutions; the hash novelty stays exact; the range status stays clean."""
+    import torch
+
+    desc = H.random_convnet(_abi.CONVNET_RESNET, Hh, W, Cc, A, seed=B, num_blocks=blocks)
+    rng = np.random.default_rng(B + 1)
+    obs = (rng.random((B, Hh, W, Cc)) < 0.35).astype(np.uint8)
+    exp = O.convnet_forward(desc, obs)
+    net = ops.ConvNetParams(dict(desc, mlp_mode=_abi.MLP_TENSOR))
+    got = {k: host(v) for k, v in net.forward(torch.as_tensor(obs).cuda()).items()}
+    assert net.numeric_status() == 0
+    for k in ("exploit_logits", "explore_logits"):
+        scale = max(1.0, float(np.abs(exp[k]).max()))
+        err = float(np.abs(got[k] - exp[k]).max())
+        assert err <= 1e-5 * scale, (k, err, scale)
+    np.testing.assert_allclose(got["value"], exp["value"], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(got["ube"], exp["ube"], rtol=0, atol=1e-5)
+    H.assert_same_bits(got["novelty"], exp["novelty"], "novelty")
+    # a BatchNorm that blows the activations past 4094 is clamped AND reported
+    big = dict(desc, mlp_mode=_abi.MLP_TENSOR)
+    big["blocks"] = [dict(b) for b in desc["blocks"]]
+    big["blocks"][0] = dict(bn=[dict(desc["blocks"][0]["bn"][0], offset=np.full(64, 9000.0, np.float32)), desc["blocks"][0]["bn"][1]], conv=desc["blocks"][0]["conv"])
+    bad = ops.ConvNetParams(big)
+    bad.forward(torch.as_tensor(obs).cuda())
+    with pytest.raises(ops.EazError, match="activation"):
+        bad.numeric_status()
+    # networks outside the tensor path are refused, not silently run in fp32
+    with pytest.raises(ops.EazError, match="TENSOR"):
+        ops.ConvNetParams(dict(H.random_convnet(_abi.CONVNET_MINATAR, 10, 10, 4, 6), mlp_mode=_abi.MLP_TENSOR)).forward(torch.zeros((2, 10, 10, 4), dtype=torch.uint8, device="cuda"))
+
