@@ -122,29 +122,38 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------ 3x3 convolution 64 -> 64 on tcgen05
-// Implicit GEMM: one CTA = 128 consecutive output pixels (M) x 64 output channels (N), K = 9 taps x 64 input channels = 18 chunks of
-// 32.  The A operand of chunk (tap, ci-half) is a pure GATHER of the shifted pixels' pre-activated fp16 hi / lo rows (written once by
-// the producing layer's epilogue; rows outside the board come from a zero page), copied into the UMMA K-major core-matrix layout by 8
-// producer warps exactly as mlp_gather.cu copies its layer-1 rows; the weight chunk images (tile_weights.cu, [hi 64x32 | lo 64x32]) arrive
-// by 1-D bulk async copies; one elected lane issues tcgen05.mma kind::f16 M=128 N=64 K=16, three split products per K-step, fp32
-// accumulators in 64 TMEM columns.  Epilogue (the same 8 warps, straight out of TMEM): x unscale + bias, + residual, fp32 store, and the
-// NEXT layer's operand: relu(bn_next(.)) x 16, clamp + flag, hi / lo split.  99 KB of shared memory: two CTAs per SM.
+// Implicit GEMM: one CTA = 256 consecutive output pixels (two M = 128 groups sharing every weight chunk) x 64 output channels (N),
+// K = 9 taps x 64 input channels = 18 chunks of 32.
+//   * the pre-activated fp16 hi / lo rows of the CTA's pixels PLUS a halo of W + 1 pixels on either side (everything a valid tap can
+//     touch; written once by the producing layer's epilogue) are staged in shared memory ONCE by 256-byte bulk async copies (row stride
+//     272 B: conflict-free for thread-per-row 16-byte reads) -- the first version gathered every tap from L2 (9 x re-read, 0.9 GB per
+//     layer at 4096 boards: 242 us per layer);
+//   * 8 producer warps (thread = row = TMEM lane) copy the shifted pixel's 64 B hi + 64 B lo of the chunk from the staged tile straight
+//     into TENSOR MEMORY (tcgen05.st; zeros for taps outside the board): the A operand never crosses the shared-memory port twice,
+//     2-stage ring of 32 columns per group;
+//   * weight chunk images (tile_weights.cu: [hi 64x32 | lo 64x32], 8 KB) by 1-D bulk async copies through a 4-stage ring, each used by
+//     both groups; one elected lane issues tcgen05.mma kind::f16 M=128 N=64 K=16 with A from TMEM, three split products per K-step,
+//     fp32 accumulators in 2 x 64 TMEM columns;
+//   * epilogue (the same 8 warps, out of TMEM): x unscale + bias, + residual, fp32 store, and the NEXT layer's operand:
+//     relu(bn_next(.)) x 16, clamp + flag, hi / lo split.
 namespace ct {
-constexpr int kTM = 128, kC = 64, kCK = 32, kChunks = 9 * kC / kCK, kStages = 4;
-constexpr int kAHalf = kTM * kCK * 2, kAStage = 2 * kAHalf;  // 8 KB hi + 8 KB lo
-constexpr int kBHalf = kC * kCK * 2, kBStage = 2 * kBHalf;    // 4 KB hi + 4 KB lo
-constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;             // 512 B
+constexpr int kTM = 128, kGroups = 2, kPix = kTM * kGroups, kC = 64, kCK = 32, kChunks = 9 * kC / kCK;
+constexpr int kStagesA = 2, kStagesB = 4;
+constexpr int kBHalf = kC * kCK * 2, kBStage = 2 * kBHalf;  // 4 KB hi + 4 KB lo
+constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;           // 512 B
+constexpr int kRowStride = 272;                              // staged pixel row: [hi 128 B | lo 128 B] + 16 B
+constexpr int kTmemCols = 256, kTmemA = kGroups * kC;        // D: group g at 64 g; A: stage s, group g at kTmemA + (2 s + g) * 32: [hi 16 | lo 16]
 struct Smem {
-  uint64_t full_a[kStages], full_b[kStages], empty[kStages], acc_done;
+  uint64_t full_a[kStagesA], empty_a[kStagesA], full_b[kStagesB], empty_b[kStagesB], acc_done, staged;
   uint32_t tmem_base;
   alignas(16) float bias[kC];
 };
-constexpr size_t kSmemBytes = (size_t)kStages * (kAStage + kBStage) + sizeof(Smem) + 1024;
+__host__ __device__ inline int staged_pixels(int W) { return kPix + 2 * (W + 1); }
+__host__ __device__ inline size_t smem_bytes(int W) { return 1024 + (size_t)kStagesB * kBStage + (size_t)staged_pixels(W) * kRowStride + sizeof(Smem) + 16; }
 }  // namespace ct
 
 struct ConvTensorArgs {
   const uint8_t* act16_in;  // [P][hi 64 halves | lo 64 halves]
-  const uint8_t* zero_page; // >= 256 zero bytes
   const uint8_t* wimg;      // 18 chunk images
   const float* wscale;      // the power-of-two scale the image carries
   const float* bias;        // [64]
@@ -160,171 +169,181 @@ __global__ void __launch_bounds__(320, 2) conv_tensor_kernel(const ConvTensorArg
   using namespace ct;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + kStages * kAStage;
-  Smem* sh = reinterpret_cast<Smem*>(sB + kStages * kBStage);
+  uint8_t* sB = smem;
+  uint8_t* sX = smem + kStagesB * kBStage;  // staged pixels [first, first + n_staged), kRowStride bytes each
+  const int nst = staged_pixels(a.W);
+  Smem* sh = reinterpret_cast<Smem*>(sX + (size_t)nst * kRowStride);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P0 = blockIdx.x * kTM, HW = a.H * a.W;
+  const int P0 = blockIdx.x * kPix, HW = a.H * a.W;
+  const int first = P0 - (a.W + 1);  // global pixel index of staged row 0
+  const int lo_pix = max(first, 0), hi_pix = min(first + nst, a.P);  // the rows that exist
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kStagesA; ++s) {
       mbar_init(&sh->full_a[s], 8);  // one elected arrive per producer warp
+      mbar_init(&sh->empty_a[s], 1);
+    }
+    for (int s = 0; s < kStagesB; ++s) {
       mbar_init(&sh->full_b[s], 1);
-      mbar_init(&sh->empty[s], 1);
+      mbar_init(&sh->empty_b[s], 1);
     }
     mbar_init(&sh->acc_done, 1);
+    mbar_init(&sh->staged, 1);
     fence_mbar_init();
   }
   if (threadIdx.x < kC) sh->bias[threadIdx.x] = __ldg(a.bias + threadIdx.x);
   if (warp == 8) {
-    tmem_alloc(&sh->tmem_base, kC);
+    tmem_alloc(&sh->tmem_base, kTmemCols);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = sh->tmem_base;
-  auto issue_b = [&](int c) {
-    const int s = c % kStages;
-    mbar_arrive_expect_tx(&sh->full_b[s], (uint32_t)kBStage);
-    bulk_g2s(sB + s * kBStage, a.wimg + (size_t)c * kBStage, kBStage, &sh->full_b[s]);
-  };
 
   if (warp == 9) {
-    // ================= weight-copy warp =================
+    // ================= copy warp: the staged pixel rows (once), then the weight chunk ring =================
+    if (lane == 0) mbar_arrive_expect_tx(&sh->staged, (uint32_t)(hi_pix - lo_pix) * kAct16Bytes);
+    __syncwarp();
+    for (int p = lo_pix + lane; p < hi_pix; p += 32)
+      bulk_g2s(sX + (size_t)(p - first) * kRowStride, a.act16_in + (size_t)p * kAct16Bytes, kAct16Bytes, &sh->staged);
     if (lane == 0) {
       for (int c = 0; c < kChunks; ++c) {
-        if (c >= kStages) mbar_wait(&sh->empty[c % kStages], ((c / kStages) & 1) ^ 1);
-        issue_b(c);
+        const int s = c % kStagesB;
+        if (c >= kStagesB) mbar_wait(&sh->empty_b[s], ((c / kStagesB) & 1) ^ 1);
+        mbar_arrive_expect_tx(&sh->full_b[s], (uint32_t)kBStage);
+        bulk_g2s(sB + s * kBStage, a.wimg + (size_t)c * kBStage, kBStage, &sh->full_b[s]);
       }
     }
     __syncwarp();
   } else if (warp == 8) {
-    // ================= MMA-issue warp: warp-uniform loop, one elected lane issues =================
+    // ================= MMA-issue warp: warp-uniform loop, one elected lane issues (A from tensor memory) =================
     const uint32_t desc_hi = (uint32_t)(kSBO >> 4) | (1u << 14);  // SBO [32,46) + version=1 [46,48)
     const uint32_t lbo_bits = (uint32_t)(kCoreBytes >> 4) << 16;  // LBO [16,30)
     auto mk = [&](uint32_t lo) { return ((uint64_t)desc_hi << 32) | (uint64_t)lo; };
     const uint32_t idesc = idesc_f16(kTM, kC);
-    const uint32_t a_base = ((smem_u32(sA) & 0x3FFFFu) >> 4) | lbo_bits, b_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | lbo_bits;
+    const uint32_t b_base = ((smem_u32(sB) & 0x3FFFFu) >> 4) | lbo_bits;
 #pragma unroll 1
     for (int c = 0; c < kChunks; ++c) {
-      const int s = c % kStages, ph = (c / kStages) & 1;
-      mbar_wait(&sh->full_b[s], ph);
-      mbar_wait(&sh->full_a[s], ph);
+      const int sa = c % kStagesA, sb = c % kStagesB;
+      mbar_wait(&sh->full_b[sb], (c / kStagesB) & 1);
+      mbar_wait(&sh->full_a[sa], (c / kStagesA) & 1);
       tc_fence_after();
-      const uint32_t al = a_base + (uint32_t)((s * kAStage) >> 4), bl = b_base + (uint32_t)((s * kBStage) >> 4);
+      const uint32_t bl = b_base + (uint32_t)((sb * kBStage) >> 4);
       if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < kCK / 16; ++j) {
-          const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
-          mma_f16(tmem, mk(al + o), mk(bl + o), idesc, (c | j) != 0);
-          mma_f16(tmem, mk(al + o), mk(bl + (kBHalf >> 4) + o), idesc, 1);
-          mma_f16(tmem, mk(al + (kAHalf >> 4) + o), mk(bl + o), idesc, 1);
+        for (int g = 0; g < kGroups; ++g) {
+          const uint32_t d = tmem + (uint32_t)(g * kC);
+          const uint32_t a_hi = tmem + (uint32_t)(kTmemA + (2 * sa + g) * 32), a_lo = a_hi + 16;
+#pragma unroll
+          for (int j = 0; j < kCK / 16; ++j) {
+            const uint32_t o = (uint32_t)(j * kKStepBytes) >> 4;
+            mma_f16_ts(d, a_hi + 8 * j, mk(bl + o), idesc, (c | j) != 0);
+            mma_f16_ts(d, a_hi + 8 * j, mk(bl + (kBHalf >> 4) + o), idesc, 1);
+            mma_f16_ts(d, a_lo + 8 * j, mk(bl + o), idesc, 1);
+          }
         }
-        mma_commit(&sh->empty[s]);
+        mma_commit(&sh->empty_a[sa]);
+        mma_commit(&sh->empty_b[sb]);
         if (c == kChunks - 1) mma_commit(&sh->acc_done);
       }
       __syncwarp();
     }
   } else {
-    // ================= workers: the shifted-pixel gather, then the epilogue out of TMEM =================
-    const int part = warp >> 2, wq = warp & 3;  // hi / lo halves; rows [32 wq, 32 wq + 32)
-    const int piece = lane & 3;
-    int Pj[4], yj[4], xj[4];
-    uint32_t doff[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int rj = 32 * wq + 8 * j + (lane >> 2);
-      Pj[j] = P0 + rj;
-      const int p = Pj[j] < a.P ? Pj[j] % HW : -(1 << 20);  // dead rows: every tap falls outside the board
-      yj[j] = p >= 0 ? p / a.W : -(1 << 20);
-      xj[j] = p >= 0 ? p % a.W : 0;
-      doff[j] = (uint32_t)(part * kAHalf + tile_offset_h32(rj, piece * 8));
-    }
-    uint4 v[3][4];  // chunks in flight: two ahead of the one being stored
-    auto load_a = [&](int c, uint4 (&x)[4]) {
-      const int tap = c >> 1, kh = tap / 3 - 1, kw = tap % 3 - 1, ci0 = (c & 1) * kCK;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int yy = yj[j] + kh, xx = xj[j] + kw;
-        const bool in = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;  // SAME padding: zeros outside the board
-        const uint8_t* src = in ? a.act16_in + (size_t)(Pj[j] + kh * a.W + kw) * kAct16Bytes + part * (kAct16Bytes / 2) + ci0 * 2 + piece * 16
-                                : a.zero_page + piece * 16;
-        x[j] = __ldg(reinterpret_cast<const uint4*>(src));
-      }
-    };
-    auto store_a = [&](int c, const uint4 (&x)[4]) {
-      const int s = c % kStages;
-      if (c >= kStages) mbar_wait_warp(&sh->empty[s], ((c / kStages) & 1) ^ 1);  // the MMAs of chunk c - kStages have completed
-      uint8_t* dst = sA + s * kAStage;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) *reinterpret_cast<uint4*>(dst + doff[j]) = x[j];
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->full_a[s]);
-    };
-    load_a(0, v[0]);
-    load_a(1, v[1]);
-#pragma unroll
+    // ================= workers: thread = output pixel = TMEM lane; warps 0-3 group 0, warps 4-7 group 1 =================
+    const int g = warp >> 2, wq = warp & 3;
+    const int row = 32 * wq + lane, Pr = P0 + g * kTM + row;
+    const bool live = Pr < a.P;
+    const int p = live ? Pr % HW : 0;
+    const int y = live ? p / a.W : -(1 << 20), x = p % a.W;  // dead rows: every tap falls outside the board
+    const uint8_t* const xrow = sX + (size_t)(Pr - first) * kRowStride;  // this pixel's own staged row
+    const uint32_t tlane = tmem + ((uint32_t)(32 * wq) << 16);
+    mbar_wait_warp(&sh->staged, 0);
+#pragma unroll 1
     for (int c = 0; c < kChunks; ++c) {
-      if (c + 2 < kChunks) load_a(c + 2, v[(c + 2) % 3]);
-      store_a(c, v[c % 3]);
+      const int sa = c % kStagesA;
+      const int tap = c >> 1, kh = tap / 3 - 1, kw = tap % 3 - 1, ci0 = (c & 1) * kCK;
+      const int yy = y + kh, xx = x + kw;
+      const bool in = yy >= 0 && yy < a.H && xx >= 0 && xx < a.W;  // SAME padding: zeros outside the board
+      uint4 h[4], l[4];
+      if (in) {
+        const uint4* src = reinterpret_cast<const uint4*>(xrow + (kh * a.W + kw) * kRowStride + ci0 * 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          h[q] = src[q];
+          l[q] = src[(kAct16Bytes / 2) / 16 + q];
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[q] = l[q] = make_uint4(0u, 0u, 0u, 0u);
+      }
+      if (c >= kStagesA) mbar_wait_warp(&sh->empty_a[sa], ((c / kStagesA) & 1) ^ 1);  // the MMAs of chunk c - 2 have read this stage
+      tc_fence_after();
+      const uint32_t ta = tlane + (uint32_t)(kTmemA + (2 * sa + g) * 32);
+      tmem_st8(ta, h[0], h[1]);
+      tmem_st8(ta + 8, h[2], h[3]);
+      tmem_st8(ta + 16, l[0], l[1]);
+      tmem_st8(ta + 24, l[2], l[3]);
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->full_a[sa]);
     }
 
-    // ---- epilogue: this thread's row (TMEM lane), 32 of the 64 channels
-    const int row = 32 * wq + lane, Pr = P0 + row;
-    const bool live = Pr < a.P;
-    const int cbase = part * (kC / 2);
+    // ---- epilogue: this thread's pixel, 64 channels in two halves of 32
     const float unscale = 1.0f / (kActScale * __ldg(a.wscale));  // exact: powers of two
     mbar_wait_warp(&sh->acc_done, 0);
     tc_fence_after();
-    const uint32_t taddr = tmem + ((uint32_t)(32 * wq) << 16) + (uint32_t)cbase;
-    uint32_t ra[16], rb[16];
-    tmem_ld16(taddr, ra);
-    tmem_ld16(taddr + 16, rb);
-    tmem_ld_wait();
-    if (live) {
-      float val[32];
+#pragma unroll 1
+    for (int half = 0; half < 2; ++half) {
+      const int cbase = half * 32;
+      uint32_t ra[16], rb[16];
+      tmem_ld16(tlane + (uint32_t)(g * kC + cbase), ra);
+      tmem_ld16(tlane + (uint32_t)(g * kC + cbase + 16), rb);
+      tmem_ld_wait();
+      if (live) {
+        float val[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        val[i] = __fmaf_rn(__uint_as_float(ra[i]), unscale, sh->bias[cbase + i]);
-        val[16 + i] = __fmaf_rn(__uint_as_float(rb[i]), unscale, sh->bias[cbase + 16 + i]);
-      }
-      const size_t o = (size_t)Pr * kC + cbase;
-      if (a.residual) {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 r4 = *reinterpret_cast<const float4*>(a.residual + o + 4 * q);
-          val[4 * q] = __fadd_rn(val[4 * q], r4.x); val[4 * q + 1] = __fadd_rn(val[4 * q + 1], r4.y);
-          val[4 * q + 2] = __fadd_rn(val[4 * q + 2], r4.z); val[4 * q + 3] = __fadd_rn(val[4 * q + 3], r4.w);
+        for (int i = 0; i < 16; ++i) {
+          val[i] = __fmaf_rn(__uint_as_float(ra[i]), unscale, sh->bias[cbase + i]);
+          val[16 + i] = __fmaf_rn(__uint_as_float(rb[i]), unscale, sh->bias[cbase + 16 + i]);
         }
-      }
-      if (a.out_raw) {
+        const size_t o = (size_t)Pr * kC + cbase;
+        if (a.residual) {
 #pragma unroll
-        for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(a.out_raw + o + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
-      }
-      if (a.act16_out) {
-        uint8_t* a16 = a.act16_out + (size_t)Pr * kAct16Bytes + (size_t)cbase * 2;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {  // 8 channels = 16 bytes of hi and of lo per store
-          uint32_t h[4], l[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            __half h0, l0, h1, l1;
-            act16_split(a.next_bn, cbase + 8 * q + 2 * e, val[8 * q + 2 * e], h0, l0, a.num_flags);
-            act16_split(a.next_bn, cbase + 8 * q + 2 * e + 1, val[8 * q + 2 * e + 1], h1, l1, a.num_flags);
-            h[e] = pack_h2(h0, h1);
-            l[e] = pack_h2(l0, l1);
+          for (int q = 0; q < 8; ++q) {
+            const float4 r4 = *reinterpret_cast<const float4*>(a.residual + o + 4 * q);
+            val[4 * q] = __fadd_rn(val[4 * q], r4.x); val[4 * q + 1] = __fadd_rn(val[4 * q + 1], r4.y);
+            val[4 * q + 2] = __fadd_rn(val[4 * q + 2], r4.z); val[4 * q + 3] = __fadd_rn(val[4 * q + 3], r4.w);
           }
-          *reinterpret_cast<uint4*>(a16 + 16 * q) = make_uint4(h[0], h[1], h[2], h[3]);
-          *reinterpret_cast<uint4*>(a16 + kAct16Bytes / 2 + 16 * q) = make_uint4(l[0], l[1], l[2], l[3]);
+        }
+        if (a.out_raw) {
+#pragma unroll
+          for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(a.out_raw + o + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
+        }
+        if (a.act16_out) {
+          uint8_t* a16 = a.act16_out + (size_t)Pr * kAct16Bytes + (size_t)cbase * 2;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {  // 8 channels = 16 bytes of hi and of lo per store
+            uint32_t hh[4], ll[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              __half h0, l0, h1, l1;
+              act16_split(a.next_bn, cbase + 8 * q + 2 * e, val[8 * q + 2 * e], h0, l0, a.num_flags);
+              act16_split(a.next_bn, cbase + 8 * q + 2 * e + 1, val[8 * q + 2 * e + 1], h1, l1, a.num_flags);
+              hh[e] = pack_h2(h0, h1);
+              ll[e] = pack_h2(l0, l1);
+            }
+            *reinterpret_cast<uint4*>(a16 + 16 * q) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+            *reinterpret_cast<uint4*>(a16 + kAct16Bytes / 2 + 16 * q) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
+          }
         }
       }
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 8) tmem_dealloc(tmem, ct::kC);
+  if (warp == 8) tmem_dealloc(tmem, ct::kTmemCols);
 }
 
 // ------------------------------------------------------------------------------------------------ rows x K @ K x N
@@ -466,15 +485,10 @@ static ConvnetLayout convnet_layout(const eaz_convnet_params* n, int B) {
 }
 
 static int launch_conv_tensor(const ConvTensorArgs& a, cudaStream_t st) {
-  static bool attr_set[32] = {false};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev >= 0 && dev < 32 && !attr_set[dev]) {
-    if (cudaError_t e = cudaFuncSetAttribute(conv_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::kSmemBytes); e != cudaSuccess)
-      return cuda_fail(e, "conv_tensor_kernel shared memory");
-    attr_set[dev] = true;
-  }
-  conv_tensor_kernel<<<ceil_div(a.P, ct::kTM), 320, ct::kSmemBytes, st>>>(a);
+  const size_t smem = ct::smem_bytes(a.W);
+  if (cudaError_t e = cudaFuncSetAttribute(conv_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ct::smem_bytes(32)); e != cudaSuccess)
+    return cuda_fail(e, "conv_tensor_kernel shared memory");
+  conv_tensor_kernel<<<ceil_div(a.P, ct::kPix), 320, smem, st>>>(a);
   EAZ_CHECK_LAUNCH("conv_tensor_kernel");
   return 0;
 }
@@ -520,9 +534,7 @@ int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observatio
       // ---- TENSOR mode: the 2 x num_blocks 64 -> 64 convolutions as tcgen05 implicit GEMMs (conv_tensor_kernel)
       uint8_t* wsb = (uint8_t*)workspace;
       uint8_t* a16[2] = {wsb + L.act16_off, wsb + L.act16_off + L.act16_bytes};
-      uint8_t* zero = wsb + L.zero_off;
       NumStatus* ns = reinterpret_cast<NumStatus*>(wsb + L.status_off);
-      if (cudaError_t e = cudaMemsetAsync(zero, 0, 256, st); e != cudaSuccess) return cuda_fail(e, "convnet zero page");
       const int nconv = 2 * net->num_blocks;
       for (int g = 0; g * 12 < nconv; ++g) {  // per-tensor power-of-two scales from max |w| (tile_weights.cu), 12 tensors per status block
         const float* wl[12];
@@ -544,11 +556,11 @@ int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observatio
         return rc;
       for (int i = 0; i < net->num_blocks; ++i) {  // BlockV2: x_{i+1} = conv2(relu(bn2(conv1(relu(bn1(x_i)))))) + x_i
         const int o = cur ^ 1;
-        ConvTensorArgs c1{a16[0], zero, wsb + L.wimg_off + (size_t)(2 * i) * kConvImgBytes, scale_of(2 * i), net->block_conv[i][0].b, nullptr, nullptr,
+        ConvTensorArgs c1{a16[0], wsb + L.wimg_off + (size_t)(2 * i) * kConvImgBytes, scale_of(2 * i), net->block_conv[i][0].b, nullptr, nullptr,
                           a16[1], bn_of(net->block_bn[i][1]), flags, B * HW, H, W};
         if (int rc = launch_conv_tensor(c1, st)) return rc;
         const bool last = i + 1 == net->num_blocks;
-        ConvTensorArgs c2{a16[1], zero, wsb + L.wimg_off + (size_t)(2 * i + 1) * kConvImgBytes, scale_of(2 * i + 1), net->block_conv[i][1].b, buf[cur],
+        ConvTensorArgs c2{a16[1], wsb + L.wimg_off + (size_t)(2 * i + 1) * kConvImgBytes, scale_of(2 * i + 1), net->block_conv[i][1].b, buf[cur],
                           buf[o], last ? nullptr : a16[0], last ? kNoBn : bn_of(net->block_bn[i + 1][0]), flags, B * HW, H, W};
         if (int rc = launch_conv_tensor(c2, st)) return rc;
         cur = o;
