@@ -33,6 +33,8 @@ __device__ __forceinline__ float bn_apply(const BnDev& bn, int c, float x) {  //
 
 // ---- TENSOR mode operand format: per pixel [hi 64 halves | lo 64 halves] of relu(bn_next(x)) * 16 (the scaled 3xFP16 split of mlp.cuh)
 constexpr int kAct16Bytes = 256;
+constexpr int kAct16Stride = 272;  // bytes between pixels, in global memory as in the staged tile: thread-per-row 16-byte shared-memory reads
+                                   // are conflict-free at this stride, and a CTA's whole input tile is ONE contiguous range (bulk copy)
 __device__ __forceinline__ uint32_t pack_h2(__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); }
 __device__ __forceinline__ void act16_split(const BnDev& bn, int c, float x, __half& hi, __half& lo, uint32_t* num_flags) {
   float v = __fmul_rn(fmaxf(bn_apply(bn, c, x), 0.0f), kActScale);
@@ -51,14 +53,24 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
                                                       uint8_t* __restrict__ act16_out, BnDev next_bn, uint32_t* num_flags) {
   extern __shared__ __align__(16) float s_in[];  // [(H + 2) * (W + 2)][Cin], zero halo
   const int b = blockIdx.x, HW = H * W, W2 = W + 2;
+  float* const s_pre = s_in + (H + 2) * W2 * Cin;  // [3][Cin]: the pre-activation BatchNorm per input channel: inv, mean, offset
   const size_t base = (size_t)b * HW * Cin;
+  if (pre.scale) {
+    for (int c = threadIdx.x; c < Cin; c += blockDim.x) {
+      s_pre[c] = bn_inv(pre, c);
+      s_pre[Cin + c] = pre.mean[c];
+      s_pre[2 * Cin + c] = pre.offset[c];
+    }
+    __syncthreads();
+  }
   for (int i = threadIdx.x; i < (H + 2) * W2 * Cin; i += blockDim.x) {
     const int c = i % Cin, pp = i / Cin, y = pp / W2 - 1, x = pp % W2 - 1;
     float v = 0.0f;
     if (y >= 0 && y < H && x >= 0 && x < W) {
       const size_t g = base + (size_t)(y * W + x) * Cin + c;
       v = obs ? (obs[g] ? 1.0f : 0.0f) : in[g];  // x.astype(float32), resnet.py:69
-      if (pre.scale) v = fmaxf(bn_apply(pre, c, v), 0.0f);  // BlockV2: BatchNorm -> relu -> conv (:36-41); the padding stays zero
+      // BlockV2: BatchNorm -> relu -> conv (:36-41), the operations of bn_apply; the padding stays zero
+      if (pre.scale) v = fmaxf(__fadd_rn(__fmul_rn(__fsub_rn(v, s_pre[Cin + c]), s_pre[c]), s_pre[2 * Cin + c]), 0.0f);
     }
     s_in[i] = v;
   }
@@ -113,7 +125,7 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
         __half hi[4], lo[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) act16_split(next_bn, 4 * cg + q, rr[q], hi[q], lo[q], num_flags);
-        uint8_t* a16 = act16_out + ((size_t)b * HW + p) * kAct16Bytes + (size_t)(4 * cg) * 2;
+        uint8_t* a16 = act16_out + ((size_t)b * HW + p) * kAct16Stride + (size_t)(4 * cg) * 2;
         *reinterpret_cast<uint2*>(a16) = make_uint2(pack_h2(hi[0], hi[1]), pack_h2(hi[2], hi[3]));
         *reinterpret_cast<uint2*>(a16 + kAct16Bytes / 2) = make_uint2(pack_h2(lo[0], lo[1]), pack_h2(lo[2], lo[3]));
       }
@@ -125,8 +137,8 @@ __global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ 
 // Implicit GEMM: one CTA = 256 consecutive output pixels (two M = 128 groups sharing every weight chunk) x 64 output channels (N),
 // K = 9 taps x 64 input channels = 18 chunks of 32.
 //   * the pre-activated fp16 hi / lo rows of the CTA's pixels PLUS a halo of W + 1 pixels on either side (everything a valid tap can
-//     touch; written once by the producing layer's epilogue) are staged in shared memory ONCE by 256-byte bulk async copies (row stride
-//     272 B: conflict-free for thread-per-row 16-byte reads) -- the first version gathered every tap from L2 (9 x re-read, 0.9 GB per
+//     touch; written once by the producing layer's epilogue) are staged in shared memory ONCE by a few large bulk async copies (the
+//     operand buffer keeps the same 272-byte pixel stride that makes thread-per-row 16-byte reads conflict-free) -- the first version gathered every tap from L2 (9 x re-read, 0.9 GB per
 //     layer at 4096 boards: 242 us per layer);
 //   * 8 producer warps (thread = row = TMEM lane) copy the shifted pixel's 64 B hi + 64 B lo of the chunk from the staged tile straight
 //     into TENSOR MEMORY (tcgen05.st; zeros for taps outside the board): the A operand never crosses the shared-memory port twice,
@@ -141,12 +153,13 @@ constexpr int kTM = 128, kGroups = 2, kPix = kTM * kGroups, kC = 64, kCK = 32, k
 constexpr int kStagesA = 2, kStagesB = 4;
 constexpr int kBHalf = kC * kCK * 2, kBStage = 2 * kBHalf;  // 4 KB hi + 4 KB lo
 constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;           // 512 B
-constexpr int kRowStride = 272;                              // staged pixel row: [hi 128 B | lo 128 B] + 16 B
+constexpr int kRowStride = kAct16Stride;                     // staged pixel row: [hi 128 B | lo 128 B] + 16 B
 constexpr int kTmemCols = 256, kTmemA = kGroups * kC;        // D: group g at 64 g; A: stage s, group g at kTmemA + (2 s + g) * 32: [hi 16 | lo 16]
 struct Smem {
   uint64_t full_a[kStagesA], empty_a[kStagesA], full_b[kStagesB], empty_b[kStagesB], acc_done, staged;
   uint32_t tmem_base;
   alignas(16) float bias[kC];
+  alignas(16) float nb_inv[kC], nb_mean[kC], nb_off[kC];  // the consumer's BatchNorm, per channel (same operations as bn_apply)
 };
 __host__ __device__ inline int staged_pixels(int W) { return kPix + 2 * (W + 1); }
 __host__ __device__ inline size_t smem_bytes(int W) { return 1024 + (size_t)kStagesB * kBStage + (size_t)staged_pixels(W) * kRowStride + sizeof(Smem) + 16; }
@@ -191,7 +204,14 @@ __global__ void __launch_bounds__(320, 2) conv_tensor_kernel(const ConvTensorArg
     mbar_init(&sh->staged, 1);
     fence_mbar_init();
   }
-  if (threadIdx.x < kC) sh->bias[threadIdx.x] = __ldg(a.bias + threadIdx.x);
+  if (threadIdx.x < kC) {
+    sh->bias[threadIdx.x] = __ldg(a.bias + threadIdx.x);
+    if (a.act16_out) {
+      sh->nb_inv[threadIdx.x] = bn_inv(a.next_bn, threadIdx.x);
+      sh->nb_mean[threadIdx.x] = a.next_bn.mean[threadIdx.x];
+      sh->nb_off[threadIdx.x] = a.next_bn.offset[threadIdx.x];
+    }
+  }
   if (warp == 8) {
     tmem_alloc(&sh->tmem_base, kTmemCols);
     tmem_relinquish();
@@ -203,10 +223,13 @@ __global__ void __launch_bounds__(320, 2) conv_tensor_kernel(const ConvTensorArg
 
   if (warp == 9) {
     // ================= copy warp: the staged pixel rows (once), then the weight chunk ring =================
-    if (lane == 0) mbar_arrive_expect_tx(&sh->staged, (uint32_t)(hi_pix - lo_pix) * kAct16Bytes);
-    __syncwarp();
-    for (int p = lo_pix + lane; p < hi_pix; p += 32)
-      bulk_g2s(sX + (size_t)(p - first) * kRowStride, a.act16_in + (size_t)p * kAct16Bytes, kAct16Bytes, &sh->staged);
+    if (lane == 0) {
+      // the staged rows are one contiguous range of the (272-byte strided) operand buffer: a few large bulk copies
+      const uint32_t total = (uint32_t)(hi_pix - lo_pix) * kRowStride;
+      mbar_arrive_expect_tx(&sh->staged, total);
+      for (uint32_t off = 0; off < total; off += 32768u)
+        bulk_g2s(sX + (size_t)(lo_pix - first) * kRowStride + off, a.act16_in + (size_t)lo_pix * kAct16Stride + off, min(32768u, total - off), &sh->staged);
+    }
     if (lane == 0) {
       for (int c = 0; c < kChunks; ++c) {
         const int s = c % kStagesB;
@@ -322,17 +345,26 @@ __global__ void __launch_bounds__(320, 2) conv_tensor_kernel(const ConvTensorArg
           for (int q = 0; q < 8; ++q) *reinterpret_cast<float4*>(a.out_raw + o + 4 * q) = make_float4(val[4 * q], val[4 * q + 1], val[4 * q + 2], val[4 * q + 3]);
         }
         if (a.act16_out) {
-          uint8_t* a16 = a.act16_out + (size_t)Pr * kAct16Bytes + (size_t)cbase * 2;
+          uint8_t* a16 = a.act16_out + (size_t)Pr * kAct16Stride + (size_t)cbase * 2;
 #pragma unroll
           for (int q = 0; q < 4; ++q) {  // 8 channels = 16 bytes of hi and of lo per store
             uint32_t hh[4], ll[4];
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-              __half h0, l0, h1, l1;
-              act16_split(a.next_bn, cbase + 8 * q + 2 * e, val[8 * q + 2 * e], h0, l0, a.num_flags);
-              act16_split(a.next_bn, cbase + 8 * q + 2 * e + 1, val[8 * q + 2 * e + 1], h1, l1, a.num_flags);
-              hh[e] = pack_h2(h0, h1);
-              ll[e] = pack_h2(l0, l1);
+              __half hl[4];  // h0, l0, h1, l1
+#pragma unroll
+              for (int t = 0; t < 2; ++t) {
+                const int ch = cbase + 8 * q + 2 * e + t;
+                // relu(bn(x)) * 16 with the per-channel terms from shared memory: the operations of bn_apply / act16_split
+                float v = __fmul_rn(fmaxf(__fadd_rn(__fmul_rn(__fsub_rn(val[8 * q + 2 * e + t], sh->nb_mean[ch]), sh->nb_inv[ch]), sh->nb_off[ch]), 0.0f), kActScale);
+                if (!(v <= 65504.0f)) {
+                  atomicOr(a.num_flags, kNumActSaturated);
+                  v = 65504.0f;
+                }
+                split_f16(v, hl[2 * t], hl[2 * t + 1]);
+              }
+              hh[e] = pack_h2(hl[0], hl[2]);
+              ll[e] = pack_h2(hl[1], hl[3]);
             }
             *reinterpret_cast<uint4*>(a16 + 16 * q) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
             *reinterpret_cast<uint4*>(a16 + kAct16Bytes / 2 + 16 * q) = make_uint4(ll[0], ll[1], ll[2], ll[3]);
@@ -367,6 +399,82 @@ __global__ void __launch_bounds__(128) dense_kernel(const float* __restrict__ x,
     if (post.scale) acc = bn_apply(post, n, acc);
     if (act == kActRelu) acc = fmaxf(acc, 0.0f);
     y[(size_t)(r0 + r) * N + n] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ the four 1x1 head convolutions, one pass
+// resnet.py:84-124: every head starts with hk.Conv2D(k, kernel_shape=1) -> BatchNorm -> relu on the trunk output (k = 2, 2, 1, 1).  One
+// thread per pixel reads its 64 trunk channels once (applying the trunk's final BatchNorm + relu for v2, :80-82) and produces all six
+// head channels; each is the same FMA chain over ci ascending as dense_kernel, so the results are bit-identical to four dense passes
+// (which read the 64-channel activations four times: 416 us of a 2 ms forward at 4096 boards).
+struct HeadConvArgs {
+  const float* w[4];  // [C][k]
+  const float* b[4];
+  BnDev bn[4];
+  float* out[4];      // [P][k]; nullptr = head not requested
+  int k[4];
+};
+__global__ void __launch_bounds__(256) head_conv_kernel(const float* __restrict__ x, int P, int C, BnDev trunk_bn, HeadConvArgs hc) {
+  extern __shared__ __align__(16) float s_hc[];  // [3][C] trunk BN (inv, mean, offset) | [6][C] weights, output-major
+  float* s_w = s_hc + 3 * C;
+  __shared__ float s_post[4][6];  // per head channel: conv bias, BN inv, mean, offset
+  int col0[4], ncol = 0;
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    col0[h] = ncol;
+    ncol += hc.k[h];
+  }
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    if (trunk_bn.scale) {
+      s_hc[i] = bn_inv(trunk_bn, i);
+      s_hc[C + i] = trunk_bn.mean[i];
+      s_hc[2 * C + i] = trunk_bn.offset[i];
+    }
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+      for (int j = 0; j < hc.k[h]; ++j) s_w[(col0[h] + j) * C + i] = hc.w[h][(size_t)i * hc.k[h] + j];
+  }
+  if (threadIdx.x < 6) {
+    int h = 0;
+    while (h < 3 && (int)threadIdx.x >= col0[h + 1]) ++h;
+    const int j = threadIdx.x - col0[h];
+    if (j < hc.k[h]) {
+      s_post[0][threadIdx.x] = hc.b[h][j];
+      s_post[1][threadIdx.x] = bn_inv(hc.bn[h], j);
+      s_post[2][threadIdx.x] = hc.bn[h].mean[j];
+      s_post[3][threadIdx.x] = hc.bn[h].offset[j];
+    }
+  }
+  __syncthreads();
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= P) return;
+  float acc[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+  const float4* xr = reinterpret_cast<const float4*>(x + (size_t)p * C);
+  for (int q = 0; q < C / 4; ++q) {
+    const float4 v4 = xr[q];
+    float v[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int ci = 4 * q + e;
+      float xv = v[e];
+      if (trunk_bn.scale) xv = fmaxf(__fadd_rn(__fmul_rn(__fsub_rn(xv, s_hc[C + ci]), s_hc[ci]), s_hc[2 * C + ci]), 0.0f);
+#pragma unroll
+      for (int o = 0; o < 6; ++o) acc[o] = __fmaf_rn(xv, s_w[o * C + ci], acc[o]);
+    }
+  }
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    if (!hc.out[h]) continue;
+    for (int j = 0; j < hc.k[h]; ++j) {
+      const int o = col0[h] + j;
+      float r = 0.0f;
+#pragma unroll
+      for (int t = 0; t < 6; ++t)
+        if (t == o) r = acc[t];
+      r = __fadd_rn(r, s_post[0][o]);
+      r = __fadd_rn(__fmul_rn(__fsub_rn(r, s_post[2][o]), s_post[1][o]), s_post[3][o]);  // bn_apply
+      hc.out[h][(size_t)p * hc.k[h] + j] = fmaxf(r, 0.0f);
+    }
   }
 }
 
@@ -413,7 +521,7 @@ static const BnDev kNoBn{nullptr, nullptr, nullptr, nullptr};
 static int launch_conv3x3(const float* in, const uint8_t* obs, int B, int H, int W, int Cin, int Cout, const eaz_conv& c, BnDev pre, BnDev post,
                           const float* residual, int relu_out, float* out, cudaStream_t st, uint8_t* act16_out = nullptr, BnDev next_bn = BnDev{},
                           uint32_t* num_flags = nullptr) {
-  const size_t smem = (size_t)(H + 2) * (W + 2) * Cin * sizeof(float);
+  const size_t smem = ((size_t)(H + 2) * (W + 2) + 3) * Cin * sizeof(float);
   if (smem > 48 * 1024)
     if (cudaError_t e = cudaFuncSetAttribute(conv3x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); e != cudaSuccess)
       return cuda_fail(e, "conv3x3_kernel shared memory");
@@ -424,6 +532,7 @@ static int launch_conv3x3(const float* in, const uint8_t* obs, int B, int H, int
 static int launch_dense(const float* x, int R, int K, int N, const eaz_conv& l, BnDev pre, BnDev post, int act, float* y, cudaStream_t st) {
   int rows = max(1, 128 / N);
   rows = max(rows, 8);
+  while (rows > 8 && ceil_div(R, rows) < 296) rows >>= 1;  // small problems: at least two CTAs per SM
   while (rows > 1 && (size_t)rows * (K | 1) * sizeof(float) > 64 * 1024) rows >>= 1;
   const size_t smem = (size_t)rows * (K | 1) * sizeof(float);
   if (smem > 48 * 1024)
@@ -437,7 +546,7 @@ static int launch_dense(const float* x, int R, int K, int N, const eaz_conv& l, 
 static int check_convnet(const eaz_convnet_params* n) {
   EAZ_CHECK_ARG(n != nullptr, "convnet: NULL parameters");
   EAZ_CHECK_ARG(n->kind == EAZ_CONVNET_RESNET || n->kind == EAZ_CONVNET_MINATAR, "convnet: unknown kind %d", n->kind);
-  EAZ_CHECK_ARG(n->height >= 1 && n->width >= 1 && n->height <= 32 && n->width <= 32 && n->in_channels >= 1, "convnet: bad observation shape");
+  EAZ_CHECK_ARG(n->height >= 1 && n->width >= 1 && n->height <= 32 && n->width <= 32 && n->in_channels >= 1 && n->in_channels <= 256, "convnet: bad observation shape");
   EAZ_CHECK_ARG(n->num_actions >= 1 && n->num_channels >= 4 && n->num_channels % 4 == 0 && 256 % (n->num_channels / 4) == 0 && n->num_channels <= 256,
                 "convnet: num_channels %d must be a multiple of 4 that divides 1024", n->num_channels);
   EAZ_CHECK_ARG(n->hidden >= 1 && n->hidden <= 1024, "convnet: bad hidden width");
@@ -474,7 +583,7 @@ static ConvnetLayout convnet_layout(const eaz_convnet_params* n, int B) {
   if (convnet_tensor(n)) {
     L.total = (L.total + 255) & ~(size_t)255;
     L.act16_off = L.total;
-    L.act16_bytes = ((size_t)B * HW * kAct16Bytes + 255) & ~(size_t)255;
+    L.act16_bytes = ((size_t)B * HW * kAct16Stride + 255) & ~(size_t)255;
     L.wimg_off = L.act16_off + 2 * L.act16_bytes;
     L.wimg_bytes = (size_t)2 * EAZ_CONVNET_MAX_BLOCKS * kConvImgBytes;
     L.zero_off = L.wimg_off + L.wimg_bytes;
@@ -582,13 +691,26 @@ int eaz_convnet_forward(const eaz_convnet_params* net, const uint8_t* observatio
     }
     // ---- heads (:84-124): 1x1 conv (on relu(bn(x1)) for v2, :80-82) -> bn -> relu -> flatten -> linear [-> relu -> linear]
     const BnDev trunk_bn = v2 ? bn_of(net->final_bn) : kNoBn;
+    HeadConvArgs hca{};
+    float* hcbuf[4];
     for (int h = 0; h < 4; ++h) {
       const int k = h < 2 ? 2 : 1;
       float* dst = h == 0 ? exploit_logits : (h == 1 ? explore_logits : nullptr);
-      if (h < 2 && !dst) continue;
-      float* hc = take((size_t)B * HW * k);
-      if (int rc = launch_dense(buf[cur], B * HW, C, k, net->head_conv[h], trunk_bn, bn_of(net->head_bn[h]), kActRelu, hc, st)) return rc;
+      hcbuf[h] = (h < 2 && !dst) ? nullptr : take((size_t)B * HW * k);
+      hca.w[h] = net->head_conv[h].w;
+      hca.b[h] = net->head_conv[h].b;
+      hca.bn[h] = bn_of(net->head_bn[h]);
+      hca.out[h] = hcbuf[h];
+      hca.k[h] = k;
+    }
+    head_conv_kernel<<<ceil_div(B * HW, 256), 256, (size_t)9 * C * sizeof(float), st>>>(buf[cur], B * HW, C, trunk_bn, hca);
+    EAZ_CHECK_LAUNCH("head_conv_kernel");
+    for (int h = 0; h < 4; ++h) {
+      const int k = h < 2 ? 2 : 1;
+      float* hc = hcbuf[h];
+      if (!hc) continue;
       if (h < 2) {
+        float* dst = h == 0 ? exploit_logits : explore_logits;
         if (int rc = launch_dense(hc, B, HW * k, A, net->head_fc[h], kNoBn, kNoBn, kActNone, dst, st)) return rc;
       } else {
         float* hf = take((size_t)B * C);
