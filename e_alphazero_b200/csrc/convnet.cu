@@ -47,7 +47,7 @@ __device__ __forceinline__ void act16_split(const BnDev& bn, int c, float x, __h
 
 // ------------------------------------------------------------------------------------------------ 3x3 convolution, SAME padding
 // in: fp32 [B,H,W,Cin] or (obs != nullptr) bool [B,H,W,Cin]; w: [3,3,Cin,Cout]; out: fp32 [B,H,W,Cout]; Cout % 4 == 0, Cout / 4 | 256
-__global__ void __launch_bounds__(256) conv3x3_kernel(const float* __restrict__ in, const uint8_t* __restrict__ obs, int H, int W, int Cin, int Cout,
+__global__ void __launch_bounds__(256, 4) conv3x3_kernel(const float* __restrict__ in, const uint8_t* __restrict__ obs, int H, int W, int Cin, int Cout,
                                                       const float* __restrict__ w, const float* __restrict__ bias, BnDev pre, BnDev post,
                                                       const float* __restrict__ residual, int relu_out, float* __restrict__ out,
                                                       uint8_t* __restrict__ act16_out, BnDev next_bn, uint32_t* num_flags) {
