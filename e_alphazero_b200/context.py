@@ -140,5 +140,57 @@ class ForwardFn:
         return (ev["exploit_logits"], ev["explore_logits"], ev["value"], ev["ube"], ev["novelty"]), state
 
 
-def get_forward_fn(env: Env, config=None) -> ForwardFn:
-    return ForwardFn(env)
+@dataclass(eq=False)
+class BoardEnvSpec:
+    """What the convolutional evaluators need to know about a pgx env that is not DeepSea / Subleq (context.py:76-82 dispatches on
+    config.env_id): its id, the observation shape [H, W, C] and the number of actions."""
+
+    env_id: str
+    observation_shape: tuple
+    num_actions: int
+
+
+class ConvForwardFn:
+    """forward.apply for EpistemicResidualAZNet (network/resnet.py) / EpistemicMinatarAZNet (network/minatar.py): the same
+    5-tuple as ForwardFn from `eaz_convnet_forward`.  The device copy of the haiku pytrees is cached per (params, state) PAIR with
+    strong references (identity-checked, like as_fc_params); call `params_updated()` after in-place changes of numpy leaves."""
+
+    def __init__(self, env: BoardEnvSpec, config=None, mlp_mode: int = _abi.MLP_EXACT):
+        self.env, self.mlp_mode = env, int(mlp_mode)
+        self.minatar = "minatar" in env.env_id
+        g = lambda k, d: getattr(config, k, d) if config is not None else d
+        self.kw = dict(hash_bits=24, max_u=1.0, novelty_scale=1.0)
+        if self.minatar:  # context.py:52-60
+            self.kw.update(num_channels=g("num_channels", 16), hidden=g("linear_layer_size", 64), max_u=g("max_ube", 1.0),
+                           novelty_scale=g("max_epistemic_variance_reward", 1.0), discount=g("discount", 0.9997))
+        self._cache = None  # (params, state, ConvNetParams)
+
+    def params_updated(self):
+        self._cache = None
+
+    def _net(self, params, state):
+        c = self._cache
+        if c is not None and c[0] is params and c[1] is state:
+            return c[2]
+        H, W, Cc = self.env.observation_shape
+        kind = _abi.CONVNET_MINATAR if self.minatar else _abi.CONVNET_RESNET
+        desc = _abi.convnet_description(params, state, kind, H, W, Cc, self.env.num_actions, **self.kw)
+        net = ops.ConvNetParams(dict(desc, mlp_mode=self.mlp_mode))
+        self._cache = (params, state, net)
+        return net
+
+    def apply(self, params, state, observation, is_training: bool = False, update_hash: bool = False):
+        if is_training or update_hash:
+            raise NotImplementedError("training-mode forward / hash update are learner-side (train.py) and out of scope")
+        ev = self._net(params, state).forward(observation)
+        return (ev["exploit_logits"], ev["explore_logits"], ev["value"], ev["ube"], ev["novelty"]), state
+
+
+def get_forward_fn(env, config=None, mlp_mode: int = _abi.MLP_EXACT):
+    """context.get_forward_fn (context.py:84-106) with the network dispatch of context.get_network (:40-82): the FC network for
+    DeepSea / Subleq, EpistemicMinatarAZNet for MinAtar env ids, EpistemicResidualAZNet for every other pgx env."""
+    if isinstance(env, Env):
+        return ForwardFn(env)
+    if isinstance(env, BoardEnvSpec):
+        return ConvForwardFn(env, config, mlp_mode)
+    raise NotImplementedError("get_forward_fn: pass an e_alphazero_b200.pgx env (DeepSea / Subleq) or a context.BoardEnvSpec")

@@ -56,6 +56,13 @@ constexpr int kBStage = 2 * kBHalf;
 // warps with tcgen05.st and read by tcgen05.mma straight from TMEM: hi halves [256, 384), lo halves [384, 512), 8 columns per chunk
 constexpr int kTmemCols = 512, kTmemAhi = 256, kTmemAlo = 384, kAColsPerChunk = kCK / 2;
 constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 256 B between 8-row groups
+#ifndef EAZ_PS_IDLE_NS
+#define EAZ_PS_IDLE_NS 0
+#endif
+// Sleep between polls of a role that waits for the other phase (0 = spin).  Measured at C2 (ms / step): 0: 1.126, 40 ns: 1.160, 100 ns: 1.148,
+// 300 ns: 1.127 -- mbarrier.try_wait already suspends the polling thread, so the polls do not crowd out the working warps and a sleep
+// only adds wake-up latency to every hand-over.  Kept as a build knob.
+constexpr unsigned kIdleNs = EAZ_PS_IDLE_NS;
 constexpr int kBarL3 = 1, kBarA0 = 2;  // named barriers: layer-3 partial sums; A-ring stage s = kBarA0 + s
 // (activation scale kActScale = 16: mlp.cuh; the W2 images carry a per-matrix power-of-two scale: Args::unscale)
 
@@ -117,6 +124,10 @@ __device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, 
                : "memory");
 }
 __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int) { mbar_wait_warp(bar, parity); }  // (umma.cuh)
+__device__ __forceinline__ void warp_wait_idle(uint64_t* bar, uint32_t parity) {
+  if (kIdleNs) mbar_wait_warp_idle(bar, parity, kIdleNs);
+  else mbar_wait_warp(bar, parity);
+}
 
 __device__ __forceinline__ uint32_t pack_next16(int packed) {  // NodeRec.pad0 (action | child + 1 << 8) -> 16 bits (action | child + 1 << 2)
   return (uint32_t)(packed & 3) | ((uint32_t)(packed >> 8) << 2);
@@ -247,7 +258,10 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
 #pragma unroll 1
       for (int g = 0; g < total; ++g) {
         const int s = g % kStages;
-        if (g >= kStages) mbar_wait(&sh->empty[s], ((g / kStages) & 1) ^ 1);
+        if (g >= kStages) {
+          if (kIdleNs) mbar_wait_idle(&sh->empty[s], ((g / kStages) & 1) ^ 1, kIdleNs);
+          else mbar_wait(&sh->empty[s], ((g / kStages) & 1) ^ 1);
+        }
         mbar_arrive_expect_tx(&sh->full_b[s], (uint32_t)kBStage);
         bulk_g2s(sB + s * kBStage, img + (size_t)(g % kChunks) * kBStage, kBStage, &sh->full_b[s]);
       }
@@ -270,7 +284,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
 #pragma unroll 1
       for (int g = 0; g < total; ++g) {
         const int s = g % kStages, ph = (g / kStages) & 1, c = g % kChunks, it = g / kChunks;
-        mbar_wait(&sh->full_a[c], it & 1);  // (all 32 lanes: uniform control flow)
+        if (c == 0 && kIdleNs) mbar_wait_warp_idle(&sh->full_a[c], it & 1, kIdleNs);  // the whole tree phase passes before chunk 0
+        else mbar_wait(&sh->full_a[c], it & 1);  // (all 32 lanes: uniform control flow)
         mbar_wait(&sh->full_b[s], ph);
         tc_fence_after();
         if (lane == 0) trc.chunk(it, c, 0);
@@ -304,7 +319,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       const uint32_t tq = sh->tmem_base + ((uint32_t)(32 * q) << 16);
 #pragma unroll 1
       for (int it = 0; it < n; ++it) {
-        warp_wait(&sh->cells_full, it & 1, lane);
+        warp_wait_idle(&sh->cells_full, it & 1);
         if (gw == 0 && lane == 0) {
           trc.stamp(it, 0);
           if (it + 1 < n) mbar_arrive_expect_tx(&sh->cells_full, kTile * 4);  // arm the next phase (nobody publishes before this evaluation's outputs)
@@ -476,10 +491,10 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
         const int nout = a.nout[rank];
         int seen = 0;  // novelty bit of the row's cell (fully_connected.py:83-90), fetched while the MMAs run
         if (cg == 0 && a.head_id[rank] == EAZ_HEAD_UBE) {
-          warp_wait(&sh->cells_full, it & 1, lane);
+          warp_wait_idle(&sh->cells_full, it & 1);
           seen = a.ds_seen[sh->cells[row]];
         }
-        warp_wait(&sh->acc_done, it & 1, lane);
+        warp_wait_idle(&sh->acc_done, it & 1);
         tc_fence_after();
         if (tstamp) trc.stamp(it, 2);
         const uint32_t taddr = sh->tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * cg);
@@ -547,7 +562,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       }
 
       // ============================================================== this warp's trees: outputs of simulation `it` -> step `sim`
-      warp_wait(&sh->out_full, it & 1, lane);
+      warp_wait_idle(&sh->out_full, it & 1);
       if (tw == 0 && lane == 0 && it + 1 < n) mbar_arrive_expect_tx(&sh->out_full, out_bytes);  // arm the next phase
       if (tstamp) trc.stamp(it, 4);
       if (lane == 0) trc_all.warp_out_full(it, (int)rank * kTWarps + tw);

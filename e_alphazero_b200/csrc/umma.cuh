@@ -78,6 +78,21 @@ __device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
     if (__any_sync(0xffffffffu, ok != 0)) break;
   }
 }
+// The same waits for roles that are IDLE for microseconds (a network role during the tree phase, a tree warp during the network
+// phase): between polls the warp sleeps, so that it does not take issue slots from the warps of the other phase that share its
+// scheduler (psearch.cuh: about a third of the kernel's 400 M warp instructions were polls).
+__device__ __forceinline__ void mbar_wait_warp_idle(uint64_t* bar, uint32_t parity, unsigned ns) {
+  const bool poller = (threadIdx.x & 31) == 0;
+  while (true) {
+    uint32_t ok = 0;
+    if (poller) ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+    if (__any_sync(0xffffffffu, ok != 0)) break;
+    __nanosleep(ns);
+  }
+}
+__device__ __forceinline__ void mbar_wait_idle(uint64_t* bar, uint32_t parity, unsigned ns) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(ns);
+}
 // One lane of the (converged) warp.  tcgen05.mma issued under `if (elect_one())` from warp-uniform values takes its descriptors from
 // uniform registers; inside an `if (lane == 0)` region the compiler wraps every tcgen05.mma in an ELECT / R2UR.BROADCAST loop
 // (~100 cycles per instruction).

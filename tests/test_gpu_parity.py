@@ -1018,3 +1018,38 @@ def test_convnet_tensor_mode(ops, Hh, W, Cc, A, B, blocks):
     with pytest.raises(ops.EazError, match="TENSOR"):
         ops.ConvNetParams(dict(H.random_convnet(_abi.CONVNET_MINATAR, 10, 10, 4, 6), mlp_mode=_abi.MLP_TENSOR)).forward(torch.zeros((2, 10, 10, 4), dtype=torch.uint8, device="cuda"))
 
+
+@pytest.mark.parametrize("tag,env_id", [("resnet_v2", "othello"), ("minatar", "minatar-breakout")])
+def test_convnet_forward_facade(ops, golden_dir, tag, env_id):
+    """context.get_forward_fn dispatches on the env id like the reference's get_network (context.py:40-82); forward.apply on the haiku
+    pytrees of the golden file returns the reference modules' outputs."""
+    import os
+
+    import torch
+
+    from e_alphazero_b200 import context
+
+    g = np.load(os.path.join(golden_dir, "convnet.npz"))
+    params, state = {}, {}
+    for key in g.files:
+        if key.startswith(f"{tag}_P|") or key.startswith(f"{tag}_S|"):
+            _, mod, name = key.split("|")
+            (params if key.startswith(f"{tag}_P|") else state).setdefault(mod, {})[name] = g[key]
+    bset = np.zeros(1 << 21, np.uint8)
+    bset[g[f"{tag}_set_idx"]] = g[f"{tag}_set_val"]
+    state[str(g[f"{tag}_set_mod"])] = {"binary_set": bset}
+    obs = g[f"{tag}_obs"]
+
+    class Cfg:
+        discount = 0.99
+        num_channels, linear_layer_size, max_ube, max_epistemic_variance_reward = 16, 64, 1.0, 1.0
+
+    fwd = context.get_forward_fn(context.BoardEnvSpec(env_id, obs.shape[1:], H.CONVNET_CASES[tag]["num_actions"]), Cfg())
+    (ex, xp, v, u, nov), _ = fwd.apply(params, state, torch.as_tensor(obs).cuda(), is_training=False)
+    np.testing.assert_allclose(host(ex), g[f"{tag}_exploit"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(host(xp), g[f"{tag}_explore"], rtol=1e-5, atol=2e-5)
+    np.testing.assert_allclose(host(v), g[f"{tag}_value"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_allclose(host(u), g[f"{tag}_ube"], rtol=1e-5, atol=2e-6)
+    np.testing.assert_array_equal(host(nov), g[f"{tag}_novelty"])
+    assert fwd._net(params, state) is fwd._net(params, state)  # cached per pytree pair
+
