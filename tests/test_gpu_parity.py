@@ -814,6 +814,7 @@ def test_facade_param_cache_never_stale(ops):
 FULL_SIZE = {
     "c2": ("deepsea", dict(size=30), 4096, 64, 0.997, 3, 48),
     "c3": ("subleq", dict(word_size=16), 8192, 64, 0.97, 1, 48),
+    "c3_streams3": ("subleq", dict(word_size=16), 8192, 64, 0.97, 3, 32),  # as bench.py runs it: fused transition + 3 sub-batch streams
     # C4: the per-GPU shard of BASELINE config 4 (DeepSea-100, 65 536 envs over 8 GPUs = 8192 per GPU, 128 simulations):
     # 30 MB layer-1 row table per head, two-trees-per-warp tree kernel, 129-node trees
     "c4": ("deepsea", dict(size=100), 8192, 128, 0.997, 3, 48),
