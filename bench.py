@@ -230,7 +230,7 @@ def extra_measure(args, name, dev, world, rank, steps=6, B_override=None, n_over
     envp, netp = synth_params(kind, kw, 0)
     env = ops.deepsea_spec(envp["size"], envp["action_map"], dev) if kind == "deepsea" else ops.subleq_spec(envp["word_size"], True)
     net = ops.FcParams.from_numpy(netp["w"], netp["b"], netp["binary_set"], netp["num_actions"], 24, netp["hash_io"], netp["word_size"], device=dev)
-    streams = 3
+    streams = 1 if (kind == "deepsea" and B > 4096) else 3
     runner = SelfplayRunner(env, net, B, n, gamma, exploration_beta=1.0, directed_exploration=True, mlp_mode=args.mlp_mode, device=dev, seed=200 + rank,
                             use_graph=not args.no_graph, fused_root=not args.no_fused_root, streams=streams, device_noise=True)
     gen = torch.Generator(device=dev).manual_seed(17 + rank)
@@ -565,7 +565,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C3 / C4 / C5-point measurements of the `extra` block")
     ap.add_argument("--streams", type=int, default=0,
-                    help="EAZ_FLAG_STREAMS: search this many sub-batches concurrently on auxiliary streams (0 = 3: measured best for both envs)")
+                    help="EAZ_FLAG_STREAMS: search this many sub-batches concurrently on auxiliary streams (0 = 3, or 1 for DeepSea batches beyond one wave of the persistent kernel: measured best)")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the workload's batch (exploration, not a BASELINE config)")
     ap.add_argument("--sims", type=int, default=0, help="override the workload's simulation count")
     ap.add_argument("--param-refresh", type=int, default=8,
@@ -578,7 +578,7 @@ def main():
         B, n = args.envs_per_gpu or B, args.sims or n
         desc += f" [overridden: {B} envs/GPU, {n} simulations]"
     if args.streams <= 0:
-        args.streams = 3
+        args.streams = 1 if (kind == "deepsea" and B > 4096) else 3  # (C4: one stream + the two-CTAs-per-SM network kernel, mlp_gather.cu)
     if args.impl == "reference":
         run_reference(args, kind, kw, B, n, gamma, desc)
     else:

@@ -26,6 +26,7 @@ struct MlpSource {
   const int* tile_done;
   int tree_epoch;
   int* mlp_done;
+  int many_trees;  // the caller-visible batch is large (kFlagManyTrees): other sub-batch streams run beside this launch
 };
 
 struct MlpOutputs {

@@ -28,7 +28,7 @@ constexpr int kTM = 128;                  // rows per CTA
 constexpr int kH = 256;
 constexpr int kCK = 32;                   // K (halves) per chunk
 constexpr int kChunks = kH / kCK;         // 8
-constexpr int kStages = 4;
+constexpr int kStagesMax = 4;  // ring depth: template parameter of the kernel (4: one CTA per SM; 2: two CTAs per SM)
 constexpr int kAHalf = kTM * kCK * 2;     // 8 KB: hi or lo tile of one A chunk
 constexpr int kAStage = 2 * kAHalf;
 constexpr int kBHalf = kH * kCK * 2;      // 16 KB: hi or lo tile of one W2 chunk
@@ -38,13 +38,13 @@ constexpr int kOutMax = 4;
 // (kActScale = 16, mlp.cuh; the W2 image carries a per-matrix power-of-two scale, tile_weights.cu)
 
 struct Smem {
-  uint64_t full_a[kStages], full_b[kStages], empty[kStages], acc_done;
+  uint64_t full_a[kStagesMax], full_b[kStagesMax], empty[kStagesMax], acc_done;
   uint32_t tmem_base;
   alignas(16) float b2[kH];
   alignas(16) float w3t[kOutMax][kH];  // layer-3 weights, output-major: four consecutive k per 16-byte load
   alignas(16) float part[kTM][kOutMax];  // partial sums of column group 1 (warps 4-7)
 };
-constexpr size_t kSmemBytes = (size_t)kStages * (kAStage + kBStage) + sizeof(Smem) + 1024;
+constexpr size_t smem_bytes(int stages) { return (size_t)stages * (kAStage + kBStage) + sizeof(Smem) + 1024; }
 }  // namespace gk
 using namespace gk;
 
@@ -73,6 +73,7 @@ struct GatherHeads {
 // Optional timeline (eaz_debug_set_gather_trace): CTA (0,0,0) records clock64() at its milestones.
 static unsigned long long* g_gather_trace = nullptr;
 
+template <int kStages>
 __global__ void __launch_bounds__(320, 2) mlp_gather_kernel(NetDesc net, EnvDesc env, MlpSource src, TensorWeights tw, int B, GatherHeads heads,
                                                             MlpOutputs out, unsigned long long* tl, unsigned long long* trace) {
   const bool tr = trace && blockIdx.x == 0 && blockIdx.y == 0;
@@ -345,14 +346,23 @@ int launch_mlp_gather(const NetDesc& net, const EnvDesc& env, const MlpSource& s
   for (int h = 0; h < 4; ++h)
     if (heads_mask & (1 << h)) hl.head[hl.n++] = h;
   if (hl.n == 0 || B == 0) return 0;
-  static bool attr_set = false;  // idempotent; a race only repeats the call
+  // Ring depth: 4 stages (197 KB: one CTA per SM) when the launch fits the machine in one wave, 2 stages (101 KB: two CTAs per SM, 256 TMEM
+  // columns each) when there are more (tile, head) units than SMs -- BASELINE C4: 64 tiles x 3 heads = 192 CTAs would otherwise run as
+  // 148 + 44.  Measured at C4 (ms / step, same box): 4 stages 5.17 (one stream) / 4.97 (3 sub-batch streams of 66 CTAs), 2 stages 4.86 / 5.05.
+  static const int force = getenv("EAZ_GATHER_STAGES") ? atoi(getenv("EAZ_GATHER_STAGES")) : 0;  // measurement knob
+  const int units = ceil_div(B, kTM) * hl.n;
+  const bool two = force ? force == 2 : units > 148;
+  static bool attr_set = false;  // idempotent; a race only repeats the calls
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(mlp_gather_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+    cudaError_t e = cudaFuncSetAttribute(mlp_gather_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(4));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(mlp_gather_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(2));
     if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(mlp_gather_kernel)");
     attr_set = true;
   }
-  cudaError_t le = launch_pdl(mlp_gather_kernel, dim3(ceil_div(B, kTM), hl.n), dim3(320), kSmemBytes, stream, net, env, src, tw, B, hl, out, g_timeline,
-                              g_gather_trace);
+  cudaError_t le = two ? launch_pdl(mlp_gather_kernel<2>, dim3(ceil_div(B, kTM), hl.n), dim3(320), smem_bytes(2), stream, net, env, src, tw, B, hl, out, g_timeline,
+                                    g_gather_trace)
+                       : launch_pdl(mlp_gather_kernel<4>, dim3(ceil_div(B, kTM), hl.n), dim3(320), smem_bytes(4), stream, net, env, src, tw, B, hl, out, g_timeline,
+                                    g_gather_trace);
   if (le != cudaSuccess) return cuda_fail(le, "mlp_gather_kernel launch");
   return 0;
 }

@@ -835,6 +835,7 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
   const int lhead = exploration ? EAZ_HEAD_EXPLORE : EAZ_HEAD_EXPLOIT;  // context.py:132
   const int mask = (1 << EAZ_HEAD_VALUE) | (1 << EAZ_HEAD_UBE) | (1 << lhead);
   MlpSource src{nullptr, t.states, t.leaf, env.kind == EAZ_ENV_DEEPSEA ? t.ds_seen : nullptr, env.kind == EAZ_ENV_DEEPSEA ? t.cell : nullptr};
+  src.many_trees = (sp.flags & kFlagManyTrees) ? 1 : 0;
   MlpOutputs mo{{nullptr, nullptr}, t.net_value, t.net_ube, nullptr};
   mo.logits[lhead - EAZ_HEAD_EXPLOIT] = t.net_logits;
   const float *root_logits = in->prior_logits, *root_value = in->value, *root_var = in->value_epistemic_variance;
