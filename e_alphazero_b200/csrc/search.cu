@@ -894,7 +894,8 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     stage2_bytes = (size_t)8 * Stage2<G>::words(chase_cap) * sizeof(uint32_t);
     // issue-bound regime only (measured: C2 = 4096 trees is 3 % faster with one tree per warp, 8192 trees 4 % and 65536 trees 12 %
     // faster with two): the caller-visible batch decides, not the sub-batch of one stream
-    two_per_warp = !one_per_warp && (sp.flags & kFlagManyTrees) && chase_cap > 0 && stage2_bytes <= 48 * 1024 && !flags;
+    two_per_warp = !one_per_warp && (sp.flags & kFlagManyTrees) && chase_cap > 0 && stage2_bytes <= 48 * 1024 && !flags &&
+                   !(sp.flags & EAZ_FLAG_PUCT);  // (the PUCT selection is staged in the one-tree-per-warp kernel)
   }
   // Subleq: the transition of the pending expansion runs inside the tree kernel (tree_step.cuh: subleq_expand_fused) for batches up to
   // kSqFusedMaxTrees, as the separate subleq_tree_step_kernel launch above that

@@ -470,7 +470,10 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
   uint32_t* const s_next = s_misc + SG::kMiscWords;  // cached selection per node
   uint32_t* const s_state = s_next + chase_cap;      // DeepSea: compact state per node
   if constexpr (J == 1) {
-    if (in_batch && do_backward && chase_cap > sim + 1 && !(sp.flags & EAZ_FLAG_PUCT)) {  // (PUCT selection: DIRECT path)
+    // Gumbel and PUCT selection alike refresh from the staged records; PUCT only for small action counts: its trees are deep, and with
+    // 16 lanes per node the staging area holds 8 nodes -- most Subleq steps then fall back to DIRECT after paying for the staging
+    // (measured, 4096 x 64 DeepSea-30: 1.29 ms staged vs 1.45 DIRECT; 8192 x 64 Subleq-16: 7.60 vs 6.34)
+    if (in_batch && do_backward && chase_cap > sim + 1 && (!(sp.flags & EAZ_FLAG_PUCT) || G <= 4)) {
       leaf = t.leaf[b];
       L = t.path_len[b];
       const unsigned lslot = (unsigned)leaf * uB + ub;
@@ -707,8 +710,20 @@ __global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp,
           inval = s_root[32 + lane] != 0u;
           considered_visit = (int)s_misc[5];
         }
-        int child;
-        const int act = select_action_staged<G>(sp, e, valid[0], raw, raw_var, prior_p, beta, is_root, g2, inval, considered_visit, lane, gl, &child);
+        int child, act;
+        if (sp.flags & EAZ_FLAG_PUCT) {
+          // muzero_action_selection (puct_select, search.cu) on the same staged + patched edge records; the node's own statistics after
+          // this backward: visits + 1 / new mean / new variance of the path level's owner lane, or the fresh leaf's (1, value, var)
+          const int nvis_l = __shfl_sync(0xffffffffu, nvis, src);
+          const float pv_l = __shfl_sync(0xffffffffu, pv, src), pvar_l = __shfl_sync(0xffffffffu, pvar, src);
+          const int n_vis = lev < L ? nvis_l + 1 : 1;
+          const float n_val = lev < L ? pv_l : value, n_var = lev < L ? pvar_l : var;
+          const bool inv1[1] = {r == 0 && is_root && gl < t.A && s_root[32 + lane] != 0u};
+          act = puct_select<G, 1>(sp, e, valid, n_vis, n_val, n_var, beta, is_root || (sp.flags & EAZ_FLAG_BETA_INTERIOR) != 0, ub, (unsigned)node, inv1, gl);
+          child = __shfl_sync(0xffffffffu, e.ci[0], (lane & ~(G - 1)) + (act & (G - 1)));
+        } else {
+          act = select_action_staged<G>(sp, e, valid[0], raw, raw_var, prior_p, beta, is_root, g2, inval, considered_visit, lane, gl, &child);
+        }
         if (act_on && gl == 0) {
           const int packed = pack_next(act, child);
           t.nodes[(unsigned)node * uB + ub].pad0 = packed;
