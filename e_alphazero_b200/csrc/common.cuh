@@ -177,22 +177,47 @@ struct SubleqVec {
   int8_t v[8];
 };
 // [task 0..5][test 0..2]; the sixth row is the last lax.switch branch (MULTIPLICATION).
-static __constant__ SubleqVec c_sq_in[6][3] = {
-    {{7, {1, 2, 3, 4, 5, 6, 7, 0}}, {8, {5, 4, 4, 5, 1, 2, 3, 1}}, {8, {1, 1, 6, 2, 4, 4, 5, 3}}},
-    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}},
-    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}},
-    {{6, {1, 1, 5, 4, 0, -3, 0, 0}}, {6, {2, 3, 0, 0, -1, -2, 0, 0}}, {8, {1, 2, 3, 4, 4, 3, 2, 1}}},
-    {{6, {1, 1, 5, 4, 0, -3, 0, 0}}, {6, {2, 3, 0, 0, -1, -2, 0, 0}}, {8, {1, 2, 3, 4, 4, 3, 2, 1}}},
-    {{6, {1, 2, 2, 3, -7, 4, 0, 0}}, {6, {-1, -5, 5, 2, 0, 1, 0, 0}}, {6, {0, 0, 1, 1, -3, 3, 0, 0}}},
+#define EAZ_SQ_IN_TABLE { \
+    {{7, {1, 2, 3, 4, 5, 6, 7, 0}}, {8, {5, 4, 4, 5, 1, 2, 3, 1}}, {8, {1, 1, 6, 2, 4, 4, 5, 3}}}, \
+    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}}, \
+    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}}, \
+    {{6, {1, 1, 5, 4, 0, -3, 0, 0}}, {6, {2, 3, 0, 0, -1, -2, 0, 0}}, {8, {1, 2, 3, 4, 4, 3, 2, 1}}}, \
+    {{6, {1, 1, 5, 4, 0, -3, 0, 0}}, {6, {2, 3, 0, 0, -1, -2, 0, 0}}, {8, {1, 2, 3, 4, 4, 3, 2, 1}}}, \
+    {{6, {1, 2, 2, 3, -7, 4, 0, 0}}, {6, {-1, -5, 5, 2, 0, 1, 0, 0}}, {6, {0, 0, 1, 1, -3, 3, 0, 0}}}, \
+}
+#define EAZ_SQ_OUT_TABLE { \
+    {{7, {-1, -2, -3, -4, -5, -6, -7, 0}}, {8, {-5, -4, -4, -5, -1, -2, -3, -1}}, {8, {-1, -1, -6, -2, -4, -4, -5, -3}}}, \
+    {{8, {4, 3, 2, 1, 0, -1, -2, -3}}, {7, {-1, -2, -3, -4, -5, -6, -7, 0}}, {5, {0, 1, -2, 3, -4, 0, 0, 0}}}, \
+    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}}, \
+    {{3, {0, 1, 3, 0, 0, 0, 0, 0}}, {3, {-1, 0, 1, 0, 0, 0, 0, 0}}, {4, {-1, -1, 1, 1, 0, 0, 0, 0}}}, \
+    {{3, {2, 9, -3, 0, 0, 0, 0, 0}}, {3, {5, 0, -3, 0, 0, 0, 0, 0}}, {4, {3, 7, 7, 3, 0, 0, 0, 0}}}, \
+    {{3, {2, 6, -28, 0, 0, 0, 0, 0}}, {3, {5, 10, 0, 0, 0, 0, 0, 0}}, {3, {0, 1, -9, 0, 0, 0, 0, 0}}}, \
+}
+static __constant__ SubleqVec c_sq_in[6][3] = EAZ_SQ_IN_TABLE;
+static __constant__ SubleqVec c_sq_out[6][3] = EAZ_SQ_OUT_TABLE;
+// The same vectors for word size 16, reduced mod 16 and packed one byte per element (sq_pack_vec's format) at COMPILE time:
+// subleq_simulate16 reads two 64-bit constants instead of packing 16 elements (a modulo each) per call.
+struct SqPacked16 {
+  unsigned long long in[6][3], out[6][3];
 };
-static __constant__ SubleqVec c_sq_out[6][3] = {
-    {{7, {-1, -2, -3, -4, -5, -6, -7, 0}}, {8, {-5, -4, -4, -5, -1, -2, -3, -1}}, {8, {-1, -1, -6, -2, -4, -4, -5, -3}}},
-    {{8, {4, 3, 2, 1, 0, -1, -2, -3}}, {7, {-1, -2, -3, -4, -5, -6, -7, 0}}, {5, {0, 1, -2, 3, -4, 0, 0, 0}}},
-    {{8, {-4, -3, -2, -1, 0, 1, 2, 3}}, {7, {1, 2, 3, 4, 5, 6, 7, 0}}, {5, {0, -1, 2, -3, 4, 0, 0, 0}}},
-    {{3, {0, 1, 3, 0, 0, 0, 0, 0}}, {3, {-1, 0, 1, 0, 0, 0, 0, 0}}, {4, {-1, -1, 1, 1, 0, 0, 0, 0}}},
-    {{3, {2, 9, -3, 0, 0, 0, 0, 0}}, {3, {5, 0, -3, 0, 0, 0, 0, 0}}, {4, {3, 7, 7, 3, 0, 0, 0, 0}}},
-    {{3, {2, 6, -28, 0, 0, 0, 0, 0}}, {3, {5, 10, 0, 0, 0, 0, 0, 0}}, {3, {0, 1, -9, 0, 0, 0, 0, 0}}},
-};
+constexpr unsigned long long sq_pack16_ce(const SubleqVec& v) {
+  unsigned long long p = 0ull;
+  for (int i = 0; i < 8; ++i)
+    if (i < v.len) p |= (unsigned long long)(unsigned)(((int)v.v[i] % 16 + 16) % 16) << (8 * i);
+  return p;
+}
+constexpr SqPacked16 sq_make_packed16() {
+  constexpr SubleqVec tin[6][3] = EAZ_SQ_IN_TABLE;
+  constexpr SubleqVec tout[6][3] = EAZ_SQ_OUT_TABLE;
+  SqPacked16 p{};
+  for (int r = 0; r < 6; ++r)
+    for (int k = 0; k < 3; ++k) {
+      p.in[r][k] = sq_pack16_ce(tin[r][k]);
+      p.out[r][k] = sq_pack16_ce(tout[r][k]);
+    }
+  return p;
+}
+static __constant__ SqPacked16 c_sq16 = sq_make_packed16();
 
 __host__ __device__ inline int floormod(int x, int m) {
   int r = x % m;
@@ -372,6 +397,124 @@ __device__ __forceinline__ void subleq_simulate(int ws, uint8_t* mem, uint8_t* s
   r.correct = (!err) && !bad && out_cur == out_len;  // :394
 }
 
+// ---- word size 16 (the BASELINE Subleq configs C3 / C5): the whole machine in registers.
+// Memory is 16 words of 4 bits = ONE 64-bit register (nibble i = mem[i]); a fetch is a shift, a store is a mask-and-insert, and the
+// loop detector's snapshot is a second register compared as a whole (M == S) -- no shared memory, no `diff` counter, and the snapshot
+// itself is free, so the tight loop takes the snapshots too.  The dependence chain of a common cycle is ~14 integer operations
+// (fetch shift -> clamp -> operand shift -> subtract -> insert) against two shared-memory round trips + ~10 operations above.  Same
+// cycle semantics, statement for statement (subleq.py:156-395); any snapshot schedule is exact (see CYCLE DETECTION above).
+__host__ __device__ __forceinline__ unsigned long long sq_pack_nibbles16(const uint32_t* w4) {  // 16 bytes (each < 16) -> 16 nibbles
+  unsigned long long m = 0ull;
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t w = w4[i];
+    const uint32_t n = (w & 0xFu) | ((w >> 4) & 0xF0u) | ((w >> 8) & 0xF00u) | ((w >> 12) & 0xF000u);
+    m |= (unsigned long long)n << (16 * i);
+  }
+  return m;
+}
+template <bool kDetect>
+__device__ __forceinline__ void subleq_simulate16(unsigned long long M, int trow, int k, SubleqSim& r) {
+  constexpr int ws = 16, AMAX = ws - 4, AIN = ws - 3, AOUT = ws - 2;
+  constexpr unsigned half1 = (unsigned)((ws + 1) >> 1) - 1u;
+  const int in_len = c_sq_in[trow][k].len, out_len = c_sq_out[trow][k].len;
+  const unsigned long long tin = c_sq16.in[trow][k], tout = c_sq16.out[trow][k];  // == sq_pack_vec(c_sq_in / c_sq_out[trow][k], 16)
+  unsigned long long outp = 0ull, S = M;  // S: Brent's snapshot (initially the start state)
+  int in_cur = 0, out_cur = 0, cur = 0, bytes = 0, cycles = 0, err = 0, bad = 0;
+  int lam = 0, pw = 1;
+  uint32_t io_meta = 0u, snap_meta = 0u;
+  bool hit = false, oob = false;
+  uint32_t f = (uint32_t)M;  // the three words at the program counter: nibbles 0..2
+  while (true) {
+    uint32_t a4, b4, am4, bm4;  // operand addresses, already times 4 (= bit offsets into M)
+    int ma, mb;
+    while (true) {  // consecutive COMMON cycles (both operands plain memory cells)
+      a4 = (f << 2) & 0x3Cu;
+      b4 = (f >> 2) & 0x3Cu;
+      am4 = min(a4, (uint32_t)(4 * AMAX));
+      bm4 = min(b4, (uint32_t)(4 * AMAX));
+      ma = (int)((uint32_t)(M >> am4) & 15u);
+      mb = (int)((uint32_t)(M >> bm4) & 15u);
+      if (!(max(a4, b4) <= (uint32_t)(4 * AMAX) && !oob && !hit && cycles < EAZ_SUBLEQ_MAX_CYCLES)) break;
+      cycles += 1;
+      const int c = (int)((f >> 8) & 15u);
+      const int seq = cur + 3;  // <= 16 (a cycle only runs at cur <= 13)
+      const int value = (ma - mb) & 15;  // floor-mod 16 of a difference of two words
+      M = (M & ~(15ull << am4)) | ((unsigned long long)(unsigned)value << am4);
+      // both candidate fetches go out as soon as the store has landed; the jump test (:329) picks one.  An out-of-range fetch
+      // (program counter >= 14) is never used (oob), so the shift count is only kept in range.
+      const uint32_t f_jump = (uint32_t)(M >> (4 * c)), f_seq = (uint32_t)(M >> (4 * min(seq, 15)));
+      const bool jump = (unsigned)(value - 1) >= half1;
+      f = jump ? f_jump : f_seq;
+      const int cur_n = jump ? c : seq;
+      bytes = max(bytes, seq);  // :311
+      cur = cur_n;
+      oob = cur_n + 2 >= ws;
+      if (kDetect) {
+        const uint32_t meta = (uint32_t)cur_n | io_meta;
+        hit = M == S && meta == snap_meta;
+        if (++lam == pw) {  // (a hit leaves the loop before the new snapshot matters)
+          S = M;
+          snap_meta = meta;
+          lam = 0;
+          pw <<= 1;
+        }
+      }
+    }
+    if (hit || cycles >= EAZ_SUBLEQ_MAX_CYCLES) break;
+    // ---- the general cycle: an operand is IN / OUT / HALT, or the program counter ran out of range
+    cycles += 1;
+    const uint32_t a = a4 >> 2, b = b4 >> 2;
+    const int c = (int)((f >> 8) & 15u);
+    const bool live = !oob;
+    const bool have_in = in_cur < in_len;
+    const int in0 = have_in ? (int)((unsigned)(tin >> (8 * in_cur)) & 0xffu) : 0;
+    const bool a_mem = a <= (uint32_t)AMAX, b_mem = b <= (uint32_t)AMAX, a_in = a == (uint32_t)AIN, b_in = b == (uint32_t)AIN;
+    const int va = a_mem ? ma : (a_in ? in0 : 0);
+    const int vb = b_mem ? mb : (b_in ? in0 : 0);
+    const int value = (va - vb) & 15;
+    if (live && a_mem) M = (M & ~(15ull << am4)) | ((unsigned long long)(unsigned)value << am4);
+    const int cur_n = live ? (((unsigned)(value - 1) >= half1) ? c : cur + 3) : cur;
+    const bool uses_in = a_in || b_in;
+    const bool to_out = live && a == (uint32_t)AOUT;
+    const bool out_ok = to_out && out_cur < 8;
+    const bool last_ok = !out_ok || (out_cur < out_len && value == (int)((unsigned)(tout >> (8 * out_cur)) & 0xffu));
+    if (out_ok) {
+      outp |= (unsigned long long)(unsigned)value << (8 * out_cur);
+      out_cur += 1;
+    }
+    bad |= (out_ok && !last_ok) ? 1 : 0;
+    in_cur += (live && uses_in && have_in) ? 1 : 0;
+    io_meta = ((uint32_t)in_cur << 16) | ((uint32_t)out_cur << 20);
+    const bool halt = live && !bad && out_cur == out_len;
+    err = (oob || (live && uses_in && !have_in) || (to_out && !out_ok) || (out_ok && !last_ok)) ? 1 : 0;
+    bytes = live ? max(bytes, cur + 3) : bytes;
+    if (err || halt) break;
+    if (kDetect) {
+      const uint32_t meta = (uint32_t)cur_n | io_meta;
+      hit = M == S && meta == snap_meta;
+      if (hit) break;
+      if (++lam == pw) {
+        S = M;
+        snap_meta = meta;
+        lam = 0;
+        pw <<= 1;
+      }
+    }
+    f = (uint32_t)(M >> (4 * min(cur_n, 15)));
+    cur = cur_n;
+    oob = cur_n + 2 >= ws;
+  }
+  if (hit && !err) cycles = EAZ_SUBLEQ_MAX_CYCLES;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    r.in[i] = (in_cur + i < in_len) ? (int)((tin >> (8 * (in_cur + i))) & 0xffull) : ws;
+    r.out[i] = i < out_cur ? (int)((outp >> (8 * i)) & 0xffull) : ws;
+  }
+  r.bytes_used = bytes;
+  r.cycles = cycles;
+  r.correct = (!err) && !bad && out_cur == out_len;
+}
+
 __device__ __forceinline__ float subleq_reward(int reward_fn, int solved, int bytes_used) {
   if (reward_fn == EAZ_SUBLEQ_REWARD_LOWEST_BYTES) return __fdiv_rn((float)solved, (float)(1 + bytes_used));  // :540-542
   return (float)solved;                                                                                      // :535-537
@@ -476,17 +619,21 @@ inline cudaError_t sq_prepare_launch(K kernel, int ws, size_t* dyn_out) {
 __device__ __forceinline__ void sq_run_tests_block(SqShared& sh, uint8_t* dyn, int ws) {
   const int e = threadIdx.x / 3, k = threadIdx.x % 3;
   if (sh.run[e]) {
-    const int stride = sq_img_stride(ws);
-    uint8_t* img = dyn + (size_t)threadIdx.x * stride;
-    uint8_t* snap = dyn + (size_t)(3 * EAZ_SQ_EPB + threadIdx.x) * stride;
     const uint32_t* base = reinterpret_cast<const uint32_t*>(sh.base[e]);
-    for (int i = 0; i < (ws + 3) >> 2; ++i) {
-      const uint32_t w = base[i];
-      reinterpret_cast<uint32_t*>(img)[i] = w;
-      reinterpret_cast<uint32_t*>(snap)[i] = w;  // the detector's first snapshot: the start state
-    }
     SubleqSim r;
-    subleq_simulate<true>(ws, img, snap, sh.trow[e], k, r);
+    if (ws == 16) {  // register-resident machine (no per-test image)
+      subleq_simulate16<true>(sq_pack_nibbles16(base), sh.trow[e], k, r);
+    } else {
+      const int stride = sq_img_stride(ws);
+      uint8_t* img = dyn + (size_t)threadIdx.x * stride;
+      uint8_t* snap = dyn + (size_t)(3 * EAZ_SQ_EPB + threadIdx.x) * stride;
+      for (int i = 0; i < (ws + 3) >> 2; ++i) {
+        const uint32_t w = base[i];
+        reinterpret_cast<uint32_t*>(img)[i] = w;
+        reinterpret_cast<uint32_t*>(snap)[i] = w;  // the detector's first snapshot: the start state
+      }
+      subleq_simulate<true>(ws, img, snap, sh.trow[e], k, r);
+    }
     sh.correct[e][k] = r.correct;
     sh.bytes[e][k] = r.bytes_used;
     if (k == 0) {

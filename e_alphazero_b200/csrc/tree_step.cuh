@@ -190,16 +190,20 @@ __device__ __forceinline__ void subleq_expand_fused(const Tree& t, const EnvDesc
     __syncwarp();
     SubleqSim r;
     if (lane < 3) {
-      const int stride = sq_img_stride(ws);
-      uint8_t* img = imgs + lane * stride;
-      uint8_t* snap = imgs + (3 + lane) * stride;
       const uint32_t* base = reinterpret_cast<const uint32_t*>(st + EAZ_SQ_HDR);
-      for (int i = 0; i < (ws + 3) >> 2; ++i) {
-        const uint32_t w = base[i];
-        reinterpret_cast<uint32_t*>(img)[i] = w;
-        reinterpret_cast<uint32_t*>(snap)[i] = w;
+      if (ws == 16) {  // register-resident machine (common.cuh)
+        subleq_simulate16<true>(sq_pack_nibbles16(base), sq_task_row(st[34]), lane, r);
+      } else {
+        const int stride = sq_img_stride(ws);
+        uint8_t* img = imgs + lane * stride;
+        uint8_t* snap = imgs + (3 + lane) * stride;
+        for (int i = 0; i < (ws + 3) >> 2; ++i) {
+          const uint32_t w = base[i];
+          reinterpret_cast<uint32_t*>(img)[i] = w;
+          reinterpret_cast<uint32_t*>(snap)[i] = w;
+        }
+        subleq_simulate<true>(ws, img, snap, sq_task_row(st[34]), lane, r);
       }
-      subleq_simulate<true>(ws, img, snap, sq_task_row(st[34]), lane, r);
       res[lane] = r.correct;
       res[3 + lane] = r.bytes_used;
     }
@@ -437,7 +441,7 @@ struct Stage {
 };
 
 template <int G, int J>
-__global__ void __launch_bounds__(128) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
+__global__ void __launch_bounds__(128, (G == 16 && J == 1) ? 8 : 1) tree_step_kernel(Tree t, SearchParams sp, EnvDesc env, int sim, int do_backward, int do_select,
                                                          const float* __restrict__ beta_in, const uint8_t* __restrict__ invalid,
                                                          unsigned long long* tl, long long* trace, int chase_cap, int* tile_done,
                                                          const int* mlp_done, int mlp_target, int sq_fused) {

@@ -1,4 +1,5 @@
 """The SHIPPED Subleq interpreter source (csrc/common.cuh: subleq_simulate with the exact loop shortcut and the tight common-cycle loop)
+-- and subleq_simulate16, the register-resident machine used for word size 16 --
 compiled for the host and held to the oracle's plain MAX_CYCLE_COUNT loop (subleq.py:156-395) on programs built to spin, count and do
 IO.  The function is ordinary C++ apart from two shared-memory byte accessors, which the harness replaces by array accesses; nothing of
 the oracle is linked into it.  (The GPU build of the same text is tested in test_gpu_parity.py::test_subleq_cycle_detection_exact.)"""
@@ -40,7 +41,12 @@ extern "C" void host_simulate(int ws, const uint8_t* program, int trow, int k, i
   memcpy(mem, program, ws);
   memcpy(snap, program, ws);
   SubleqSim r;
-  if (detect) subleq_simulate<true>(ws, mem, snap, trow, k, r);
+  if (detect >= 2) {  // the register-resident word-size-16 machine
+    uint32_t w4[4];
+    memcpy(w4, program, 16);
+    if (detect == 3) subleq_simulate16<true>(sq_pack_nibbles16(w4), trow, k, r);
+    else subleq_simulate16<false>(sq_pack_nibbles16(w4), trow, k, r);
+  } else if (detect) subleq_simulate<true>(ws, mem, snap, trow, k, r);
   else subleq_simulate<false>(ws, mem, snap, trow, k, r);
   for (int i = 0; i < 8; ++i) { in_after[i] = r.in[i]; out_after[i] = r.out[i]; }
   bcc[0] = r.bytes_used; bcc[1] = r.cycles; bcc[2] = r.correct;
@@ -97,7 +103,7 @@ def test_shipped_interpreter_equals_plain_loop(host_interp, ws, n):
         k = int(rng.integers(0, 3))
         tin, tout = O.subleq_test_cases(task, ws)
         exp = O.subleq_simulate(ws, progs[i].astype(np.int32), tin[k], tout[k])
-        for detect in (1, 0):
+        for detect in ((1, 0, 3, 2) if ws == 16 else (1, 0)):  # 3 / 2: subleq_simulate16 with / without the loop shortcut
             host_interp.host_simulate(ws, progs[i].ctypes.data_as(C.c_void_p), task - 1, k, detect, ia, oa, bcc)
             got = (list(ia), list(oa), bcc[0], bcc[1], bool(bcc[2]))
             want = (exp["input_after"].tolist(), exp["output_after"].tolist(), exp["bytes_used"], exp["cycles_used"], exp["correct"])
