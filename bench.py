@@ -396,38 +396,66 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         ms_total = float(t.item())
     value = world * B * args.steps / (ms_total * 1e-3)
 
-    # ---- e2e: host buffers in, host results out, copies inside the timed region (rank-local, max over ranks)
+    # ---- e2e: host buffers in, host results out, copies inside the timed region (rank-local, max over ranks).
+    # A graph runner keeps its state fields in one device arena and the search outputs in another (ops.alloc_arena), so a host caller
+    # moves a step's inputs with ONE pinned copy and reads states + results back with two (SelfplayRunner.host_arenas);
+    # without the graph the fields are copied one by one.
     fields = ops.state_fields(env)
-    host_in = {k: states[k].detach().cpu().pin_memory() for k in fields}
-    host_out = {k: torch.empty_like(host_in[k]).pin_memory() for k in fields}
     res_names = ("action", "root_value", "root_epistemic_std", "value_prediction", "ube_prediction", "q_values_epistemic_variance")
-    h2d = sum(v.numel() * v.element_size() for v in host_in.values())
     e2e_ms, d2h = 0.0, 0
-    dstates = runner.static_states() if runner.use_graph else {k: torch.empty_like(states[k]) for k in fields}
-    host_res = None
-    for i in range(args.steps + 2):
-        flush.zero_()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if i >= 2 and (i - 2) % args.param_refresh == 0:
-            runner.params_updated()
-        a.record()
-        for k in fields:
-            dstates[k].copy_(host_in[k], non_blocking=True)
-        dstates, out = one_step(dstates)
-        for k in fields:
-            host_out[k].copy_(dstates[k], non_blocking=True)
-        res = [getattr(out, nme) for nme in res_names]
-        if host_res is None:
-            host_res = [torch.empty_like(r, device="cpu").pin_memory() for r in res]
-            d2h = sum(v.numel() * v.element_size() for v in host_out.values()) + sum(r.numel() * r.element_size() for r in res)
-        for hr, r in zip(host_res, res):
-            hr.copy_(r, non_blocking=True)
-        join_gathers()
-        b.record()
+    if runner.use_graph and runner.fused_root:  # (with a separate root forward its predictions live outside the output arena)
+        dstates = runner.static_states()
+        hs_a, hv_a, host_res_flat, host_res = runner.host_arenas()
+        hs_b, hv_b, _, _ = runner.host_arenas()
+        hs_a.copy_(runner.static_flat)
         torch.cuda.synchronize()
-        if i >= 2:
-            e2e_ms += a.elapsed_time(b)
-        host_in, host_out = host_out, host_in
+        h2d = hs_a.numel()
+        d2h = hs_b.numel() + host_res_flat.numel()
+        for i in range(args.steps + 2):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if i >= 2 and (i - 2) % args.param_refresh == 0:
+                runner.params_updated()
+            a.record()
+            runner.static_flat.copy_(hs_a, non_blocking=True)
+            dstates, out = one_step(dstates)
+            hs_b.copy_(runner.static_flat, non_blocking=True)
+            host_res_flat.copy_(runner.plan.out_flat, non_blocking=True)  # action, root value / std, predictions, q variances, visit statistics
+            join_gathers()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                e2e_ms += a.elapsed_time(b)
+            hs_a, hs_b = hs_b, hs_a
+    else:
+        host_in = {k: states[k].detach().cpu().pin_memory() for k in fields}
+        host_out = {k: torch.empty_like(host_in[k]).pin_memory() for k in fields}
+        h2d = sum(v.numel() * v.element_size() for v in host_in.values())
+        dstates = runner.static_states() if runner.use_graph else {k: torch.empty_like(states[k]) for k in fields}
+        host_res = None
+        for i in range(args.steps + 2):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if i >= 2 and (i - 2) % args.param_refresh == 0:
+                runner.params_updated()
+            a.record()
+            for k in fields:
+                dstates[k].copy_(host_in[k], non_blocking=True)
+            dstates, out = one_step(dstates)
+            for k in fields:
+                host_out[k].copy_(dstates[k], non_blocking=True)
+            res = [getattr(out, nme) for nme in res_names]
+            if host_res is None:
+                host_res = [torch.empty_like(r, device="cpu").pin_memory() for r in res]
+                d2h = sum(v.numel() * v.element_size() for v in host_out.values()) + sum(r.numel() * r.element_size() for r in res)
+            for hr, r in zip(host_res, res):
+                hr.copy_(r, non_blocking=True)
+            join_gathers()
+            b.record()
+            torch.cuda.synchronize()
+            if i >= 2:
+                e2e_ms += a.elapsed_time(b)
+            host_in, host_out = host_out, host_in
     if world > 1:
         t = torch.tensor([e2e_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -528,7 +556,9 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
                       "multi_gpu": (f"envs sharded per rank, params broadcast once, per-step trajectory records packed into a [{args.param_refresh},B,4] scan "
                                     "buffer and all-gathered once per scan on a side stream (main.py:383-385)") if world > 1 else "single GPU"},
             "simulations_per_s": value * n, "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps,
+                    "copies": ("1 pinned H2D copy of the state arena, 2 D2H copies (state arena, search-output arena) per step" if (not args.no_graph and not args.no_fused_root)
+                               else "one copy per state field / result tensor")},
             "gpu_launches": n_full * runner.launches_per_step + (args.steps - n_full) * runner.launches_per_step_reuse + args.steps, "roofline": roofline,
             "cpu_baseline": cpu, "extra": extra}
     emit(line)

@@ -415,11 +415,35 @@ class ConvNetParams:
 
 
 # --------------------------------------------------------------------------- search
-def alloc_search_outputs(B, N, A, S, want_tree, device) -> dict:
-    torch = require_cuda()
+def alloc_arena(specs, device="cuda", pinned=False):
+    """One flat uint8 allocation holding every tensor of `specs` = [(name, shape, torch dtype)] at 256-byte aligned offsets;
+    returns (flat, {name: view}).  A host caller moves ALL of them with one copy of `flat` (a pinned host arena built from the
+    same specs has the same layout) instead of one small cudaMemcpy per tensor."""
+    import math
+
+    import torch
+
+    offs, total = [], 0
+    for _, shape, dt in specs:
+        nbytes = int(math.prod(shape)) * torch.empty((), dtype=dt).element_size()
+        offs.append((total, nbytes))
+        total += (nbytes + 255) // 256 * 256
+    flat = torch.zeros(max(total, 256), dtype=torch.uint8, device=device)
+    if pinned:
+        flat = flat.pin_memory()
+    views = {name: flat[off : off + nb].view(dt).view(shape) for (name, shape, dt), (off, nb) in zip(specs, offs)}
+    return flat, views
+
+
+def search_output_specs(B, N, A, S, want_tree):
     shp = {"B": (B,), "BA": (B, A), "BN": (B, N), "BNA": (B, N, A), "BNS": (B, N, S)}
     fields = _abi.SUMMARY_FIELDS + (_abi.TREE_FIELDS if want_tree else []) + _abi.ROOT_FIELDS
-    return {name: torch.empty(shp[kind], dtype=_dt()[dt], device=device) for name, dt, kind in fields}
+    return [(name, shp[kind], _dt()[dt]) for name, dt, kind in fields]
+
+
+def alloc_search_outputs(B, N, A, S, want_tree, device) -> dict:
+    require_cuda()
+    return alloc_arena(search_output_specs(B, N, A, S, want_tree), device)[1]
 
 
 @dataclass
@@ -433,6 +457,8 @@ class SearchPlan:
     device: str = "cuda"
     workspace: object = None
     out: dict = field(default_factory=dict)
+    out_flat: object = None
+    out_specs: object = None
     num_launches: int = 0
     num_launches_reuse: int = 0
 
@@ -447,7 +473,9 @@ class SearchPlan:
         self._ws_ptr = C.c_void_p(self.workspace.data_ptr() + off)
         self._ws_bytes = C.c_size_t(nbytes)
         B, N, A = self.cfg.batch, self.cfg.num_simulations + 1, self.env.num_actions
-        self.out = alloc_search_outputs(B, N, A, self.env.compact_bytes, self.want_tree, self.device)
+        # all outputs in one arena: `out_flat` moves them to the host with one copy (alloc_arena)
+        self.out_specs = search_output_specs(B, N, A, self.env.compact_bytes, self.want_tree)
+        self.out_flat, self.out = alloc_arena(self.out_specs, self.device)
         self.num_launches = load().eaz_search_num_launches(C.byref(self.cfg), C.byref(e))
         cfg_reuse = _abi.EazSearchConfig.from_buffer_copy(self.cfg)
         cfg_reuse.flags |= _abi.FLAG_REUSE_PREPARED

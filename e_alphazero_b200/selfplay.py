@@ -90,7 +90,11 @@ class SelfplayRunner:
         torch = require_cuda()
         subleq = self.env.kind == _abi.ENV_SUBLEQ
         if self._static is None:
-            st = {k: v.clone() for k, v in states.items()}
+            # the graph's state buffers live in ONE arena (ops.alloc_arena): a host caller uploads / downloads all fields with one copy
+            self.state_specs = [(k, tuple(v.shape), v.dtype) for k, v in states.items()]
+            self.static_flat, st = ops.alloc_arena(self.state_specs, self.device)
+            for k, v in states.items():
+                st[k].copy_(v)
             sg = torch.zeros((self.B, self.A), dtype=torch.float32, device=self.device)
             stt = torch.ones(self.B, dtype=torch.int32, device=self.device) if subleq else None
             self._step_eager({k: v.clone() for k, v in st.items()}, self.draw_gumbel(), self._draw_tasks() if subleq else None,
@@ -130,6 +134,16 @@ class SelfplayRunner:
     def static_states(self):
         """The graph's own state buffers (step them in place to avoid the copies in/out)."""
         return self._static[0] if self._static else None
+
+    def host_arenas(self):
+        """Pinned host mirrors of the two device arenas of a graph runner -- (states_flat, states_views, out_flat, out_views) with the
+        device layouts, so that a host caller moves a whole step's inputs / results with ONE copy each way per arena:
+        `runner.static_flat.copy_(states_flat, non_blocking=True)` ... step ... `out_flat.copy_(runner.plan.out_flat, non_blocking=True)`."""
+        if self._static is None:
+            raise ops.EazError("host_arenas(): run one graph step first (the state arena is created by it)")
+        sf, sv = ops.alloc_arena(self.state_specs, "cpu", pinned=True)
+        of, ov = ops.alloc_arena(self.plan.out_specs, "cpu", pinned=True)
+        return sf, sv, of, ov
 
     def _step_eager(self, states: dict, gumbel=None, task_ids=None, reuse_prepared=None):
         torch = require_cuda()

@@ -508,6 +508,53 @@ def test_selfplay_runner_graph_equals_eager(ops, kind, kw, B):
         H.assert_same_bits(runs["eager"][1][k], runs["graph"][1][k], k)
 
 
+@pytest.mark.parametrize("kind,kw,B", [("deepsea", dict(size=10), 200), ("subleq", dict(word_size=16), 48)])
+def test_selfplay_runner_host_arenas(ops, kind, kw, B):
+    """A host caller of a graph runner uploads all state fields with ONE copy of the state arena and reads states / search outputs back with
+    one copy per arena (SelfplayRunner.host_arenas, ops.alloc_arena): identical to a runner whose states stay on the device."""
+    import torch
+
+    from e_alphazero_b200.selfplay import SelfplayRunner
+
+    env = H.make_env(kind, seed=3, **kw)
+    net = H.make_net(env, seed=4, fill=0.5)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    tasks = torch.ones(B, dtype=torch.int32, device="cuda") if kind == "subleq" else None
+    runs = {}
+    for mode in ("device", "host"):
+        r = SelfplayRunner(denv, dnet, B, 12, 0.97, exploration_beta=1.0, directed_exploration=True, mlp_mode=_abi.MLP_TENSOR, use_graph=True,
+                           fused_root=True, seed=1)
+        st = ops.env_init(denv, B, task_ids=tasks)
+        gen = torch.Generator(device="cuda").manual_seed(9)
+        rec, arenas = [], None
+        for step in range(4):
+            u = torch.rand((B, env.num_actions), device="cuda", generator=gen).clamp_(1e-20, 1.0 - 1e-7)
+            g = (-(-u.log()).log()).contiguous()
+            if mode == "host" and step > 0:  # the previous step's states come back from the host with one copy
+                r.static_flat.copy_(arenas[0], non_blocking=True)
+                st = r.static_states()
+            st, out = r.step(st, gumbel=g, task_ids=tasks)
+            if mode == "host":
+                if arenas is None:
+                    arenas = r.host_arenas()
+                    assert arenas[0].is_pinned() and arenas[0].numel() == r.static_flat.numel() and arenas[2].numel() == r.plan.out_flat.numel()
+                sf, sv, of, ov = arenas
+                sf.copy_(r.static_flat, non_blocking=True)
+                of.copy_(r.plan.out_flat, non_blocking=True)
+                torch.cuda.synchronize()
+                rec.append(({k: sv[k].numpy().copy() for k in sv}, ov["action"].numpy().copy(), ov["value"].numpy().copy(), ov["root_value"].numpy().copy()))
+                r.static_flat.fill_(0xAB)  # the device copy is gone: only the upload above can restore it
+            else:
+                rec.append(({k: host(v).copy() for k, v in st.items()}, host(out.action).copy(), host(out.root_value).copy(), host(out.value_prediction).copy()))
+        runs[mode] = rec
+    for (sa, aa, va, pa), (sb, ab, vb, pb) in zip(runs["device"], runs["host"]):
+        for k in sa:
+            H.assert_same_bits(sa[k], sb[k].reshape(sa[k].shape), k)
+        H.assert_same_bits(aa, ab, "action")
+        H.assert_same_bits(va, vb, "value")
+        H.assert_same_bits(pa, pb, "root_value")
+
+
 # ----------------------------------------------------------------------------- reanalyze (reanalyze.py:52-131)
 @pytest.mark.parametrize("B,A", [(1, 2), (257, 2), (100, 16), (33, 40), (9, 256)])
 def test_reanalyze_targets_bit_exact(ops, B, A):
