@@ -493,20 +493,27 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
         if persistent:
             tensor_kernel = "ds_search_kernel"
         total_ms = sum(v[0] for v in prof.values())
-        dominant = "tree" if persistent else ("network" if mlp_ms >= tree_ms else "tree")
         tree_gbs = (tree_bytes + io_bytes) / (tree_ms * 1e-3) / 1e9
         mlp_tfs = flops_fwd * B * n / (mlp_ms * 1e-3) / 1e12
+        # speed-of-light floors of one search: the roof that binds is the one with the larger floor.  The persistent kernel does the
+        # tree work AND the network in one launch, so both floors refer to the same duration; otherwise the class that takes longer.
+        hbm_floor_us = (tree_bytes + io_bytes) / (hbm_peak * 1e9) * 1e6
+        tensor_floor_us = flops_fwd * B * n / (tf_peak * 1e12) * 1e6
+        if persistent:
+            dominant = "network" if tensor_floor_us >= hbm_floor_us else "tree"
+        else:
+            dominant = "network" if mlp_ms >= tree_ms else "tree"
         tree_obj = {"bound": "hbm", "achieved": tree_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": tree_gbs / hbm_peak, "traffic": None,
                     "kernels": ("ds_search_kernel (persistent: all simulations of a 128-tree tile in one 4-CTA cluster -- tree steps, DeepSea transition AND "
                                 "the tcgen05 network evaluation; its whole duration is charged to the tree bytes)") if persistent else
                                ("tree_step_kernel (expand + backward + action refresh + descent)" + (" + subleq_tree_step_kernel" if kind == "subleq" else "")),
                     "algorithmic_bytes_per_search": tree_bytes + io_bytes, "ms_per_search": tree_ms,
                     "avg_launch_us": 1e3 * tree_ms / max(prof["select"][1] + prof["expand_backward"][1] + prof["env_step"][1], 1),
-                    "edge_traversals": V, "peak_source": which}
+                    "edge_traversals": V, "peak_source": which, "floor_us_per_search": hbm_floor_us}
         mlp_obj = {"bound": "tensor", "achieved": mlp_tfs, "peak": tf_peak, "unit": "TFLOP/s", "frac": mlp_tfs / tf_peak, "traffic": None,
                    "kernels": "mlp_exact_kernel (fp32 FMA chains, bit-exact mode)" if args.mlp_mode == 0 else f"{tensor_kernel} (tcgen05)",
                    "flops_per_search": flops_fwd * B * n, "ms_per_search": mlp_ms, "avg_launch_us": 1e3 * mlp_ms / max(prof["network"][1], 1),
-                   "peak_source": which}
+                   "peak_source": which, "floor_us_per_search": tensor_floor_us}
         try:  # DRAM traffic per launch from the committed ncu --set full captures (profiles/r2_traffic.json, r1_traffic.json)
             traffic = {}
             for name in ("r1_traffic.json", "r2_traffic.json"):
@@ -523,6 +530,10 @@ def run_b200(args, kind, kw, B, n, gamma, desc):
                                ": the events serialise the PDL chain and the sub-batch streams, so these durations are upper bounds -- in the timed region the "
                                "tree kernel stages its data under the network kernel and sub-batches overlap (value / ms_per_step is the overlapped time)"))
         roofline["dominant"] = dominant
+        if persistent:
+            roofline["note"] = ("one launch runs the tree steps and the network of all simulations; a simulation is a serial chain network -> backward -> "
+                                "refresh -> descent per 128-tree tile (profiles/r2_summary.md 1.1), so the kernel is latency-bound: the tensor roof "
+                                "(larger floor) is reported here, the HBM roof of the tree bytes under `other`")
         roofline["share_of_search_time"] = (mlp_ms if dominant == "network" else tree_ms) / total_ms
         roofline["other"] = tree_obj if dominant == "network" else mlp_obj
         roofline["per_class_ms"] = {k: round(v[0], 4) for k, v in prof.items()}

@@ -36,12 +36,20 @@ constexpr int kCtas = 4;              // CTAs per cluster
 constexpr int kSlots = kTile / kCtas; // trees per CTA
 constexpr int kHeads = 3;             // CTAs 0..2 run one head each
 // Warp roles, aligned to warpgroups (4 warps) because the register file is re-split per warpgroup with setmaxnreg: the kernel starts
-// with 72 registers per thread (65536 / 896); the gather warps, which hold a whole A chunk (16 x 16 bytes per thread) in registers, then
-// grow to kRegsGather, paid for by the control warpgroup shrinking (the tree warps ran no faster with 88 than with 72).
+// with 72 registers per thread (65536 / 896); the tree warps and the gather warps (which hold a batch of A chunks, 4 x 64 bytes per
+// thread, in registers) then grow to 80, paid for by the control warpgroup shrinking to 24 (16 x 32 x 80 + 8 x 32 x 80 + 4 x 32 x 24
+// = 64512 <= 65536).  At 72 the tree warps' step spilled ~28 registers to local memory (ptxas: 112 bytes of spill stores) and, with
+// 200 KB of the SM's 256 KB configured as shared memory, those lines kept falling out of the remaining L1 onto the per-simulation
+// critical path: 80 registers alone took C2 from 1.129 to 1.050 ms / step (profiles/r2_summary.md 1.4).
 constexpr int kTWarps = 16, kGWarps = 8;
 constexpr int kWarpTree0 = 0, kWarpGather0 = kTWarps, kWarpMma = kTWarps + kGWarps, kWarpCopy = kWarpMma + 1;
 constexpr int kThreads = (kTWarps + kGWarps + 4) * 32;  // 896: 4 tree warpgroups, 2 gather warpgroups, 1 control warpgroup (MMA, copy, 2 idle)
-constexpr int kRegsTree = 72, kRegsGather = 88, kRegsCtrl = 32;  // the increase (8 warps x 16) must fit what the control warpgroup releases (4 x 40): the pool is per CTA
+#ifndef EAZ_PS_REGS_TREE
+#define EAZ_PS_REGS_TREE 80
+#define EAZ_PS_REGS_GATHER 80
+#define EAZ_PS_REGS_CTRL 24
+#endif
+constexpr int kRegsTree = EAZ_PS_REGS_TREE, kRegsGather = EAZ_PS_REGS_GATHER, kRegsCtrl = EAZ_PS_REGS_CTRL;  // (the pool is per CTA: the sum over warps must stay <= 65536)
 template <int N>
 __device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -49,7 +57,12 @@ __device__ __forceinline__ void regs_dec() { asm volatile("setmaxnreg.dec.sync.a
 constexpr int kH = 256;
 constexpr int kCK = 16;               // K (halves) per chunk = one tcgen05.mma kind::f16 K-step
 constexpr int kChunks = kH / kCK;     // 16 per evaluation
-constexpr int kStages = 6;            // W2 chunk ring (the A operand lives in tensor memory: no A ring)
+#ifndef EAZ_PS_STAGES
+#define EAZ_PS_STAGES 5
+#endif
+// W2 chunk ring (the A operand lives in tensor memory: no A ring).  Measured at C2 with the 80-register split (ms / step): 3 stages 1.052,
+// 4: 1.051, 5: 1.036, 6: 1.050 -- a sixth stage takes the shared-memory configuration from 196 to 228 KB, i.e. 32 KB out of the L1.
+constexpr int kStages = EAZ_PS_STAGES;
 constexpr int kBHalf = kH * kCK * 2;     // 8 KB: hi or lo tile of a W2 chunk
 constexpr int kBStage = 2 * kBHalf;
 // tensor memory (512 columns x 128 lanes): D = relu-input accumulator [0, 256); A operand of the whole K = 256, written by the gather
@@ -129,6 +142,19 @@ __device__ __forceinline__ void warp_wait_idle(uint64_t* bar, uint32_t parity) {
   else mbar_wait_warp(bar, parity);
 }
 
+#ifndef EAZ_PS_H1_NOALLOC
+#define EAZ_PS_H1_NOALLOC 0
+#endif
+// layer-1 row loads of the gather warps (read-only table, 1 KB per row and head)
+__device__ __forceinline__ uint4 ld_h1(const uint4* p) {
+#if EAZ_PS_H1_NOALLOC
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+#else
+  return __ldg(p);
+#endif
+}
 __device__ __forceinline__ uint32_t pack_next16(int packed) {  // NodeRec.pad0 (action | child + 1 << 8) -> 16 bits (action | child + 1 << 2)
   return (uint32_t)(packed & 3) | ((uint32_t)(packed >> 8) << 2);
 }
@@ -331,10 +357,10 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
             const int c = 2 * (4 * batch + k) + half;
-            v[k][0] = __ldg(src + 2 * c);
-            v[k][1] = __ldg(src + 2 * c + 1);
-            v[k][2] = __ldg(src + 2 * c + (2 * kH) / 16);
-            v[k][3] = __ldg(src + 2 * c + (2 * kH) / 16 + 1);
+            v[k][0] = ld_h1(src + 2 * c);
+            v[k][1] = ld_h1(src + 2 * c + 1);
+            v[k][2] = ld_h1(src + 2 * c + (2 * kH) / 16);
+            v[k][3] = ld_h1(src + 2 * c + (2 * kH) / 16 + 1);
           }
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
@@ -355,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
     }
   } else {
     // ================================================================ tree warps: two trees each (16 lanes per tree)
-    // (the tree warps keep the launch allocation of 72)
+    if (kRegsTree > 72) regs_inc<kRegsTree>();  // (the launch allocation is 72)
     const int tw = warp - kWarpTree0;
     const int hl = lane & (kW - 1), hbase = lane & kW, sub = lane >> 4;
     const int slot = 2 * tw + sub;
