@@ -36,19 +36,26 @@ constexpr int kCtas = 4;              // CTAs per cluster
 constexpr int kSlots = kTile / kCtas; // trees per CTA
 constexpr int kHeads = 3;             // CTAs 0..2 run one head each
 // Warp roles, aligned to warpgroups (4 warps) because the register file is re-split per warpgroup with setmaxnreg: the kernel starts
-// with 72 registers per thread (65536 / 896); the tree warps and the gather warps (which hold a batch of A chunks, 4 x 64 bytes per
-// thread, in registers) then grow to 80, paid for by the control warpgroup shrinking to 24 (16 x 32 x 80 + 8 x 32 x 80 + 4 x 32 x 24
-// = 64512 <= 65536).  At 72 the tree warps' step spilled ~28 registers to local memory (ptxas: 112 bytes of spill stores) and, with
-// 200 KB of the SM's 256 KB configured as shared memory, those lines kept falling out of the remaining L1 onto the per-simulation
-// critical path: 80 registers alone took C2 from 1.129 to 1.050 ms / step (profiles/r2_summary.md 1.4).
+// with 72 registers per thread (65536 / 896); the tree warps then grow to 96, the gather warps (one A chunk = 64 bytes per thread and
+// round trip in registers) shrink to 48 and the control warpgroup to 24 (16 x 32 x 96 + 8 x 32 x 48 + 4 x 32 x 24 = 64512 <= 65536).
+// REGISTER SPILLS WERE THE KERNEL'S LARGEST SINGLE COST: at 72 registers the tree step spilled ~28 values (ptxas: 112 bytes of spill
+// stores) and, with ~200 KB of the SM's 256 KB configured as shared memory, those lines kept falling out of the remaining L1 onto the
+// per-simulation critical path.  Measured at C2 (ms / step): 72 / 88 / 32 registers (tree / gather / control) 1.129; 80 / 80 / 24: 1.050
+// (36 bytes still spilled); 96 / 48 / 24 with a two-chunk gather batch: 0.981 (16 bytes); with a one-chunk batch: 0.961 (ptxas: no spills).
+// ptxas's allocation under setmaxnreg is not monotonic in the limits (88 / 64 / 24 spilled MORE than 80 / 80 / 24), so the split was
+// chosen by compiling the candidates and counting spill bytes (-Xptxas -v), then measuring (profiles/r2_summary.md 1.4).
 constexpr int kTWarps = 16, kGWarps = 8;
 constexpr int kWarpTree0 = 0, kWarpGather0 = kTWarps, kWarpMma = kTWarps + kGWarps, kWarpCopy = kWarpMma + 1;
 constexpr int kThreads = (kTWarps + kGWarps + 4) * 32;  // 896: 4 tree warpgroups, 2 gather warpgroups, 1 control warpgroup (MMA, copy, 2 idle)
 #ifndef EAZ_PS_REGS_TREE
-#define EAZ_PS_REGS_TREE 80
-#define EAZ_PS_REGS_GATHER 80
+#define EAZ_PS_REGS_TREE 96
+#define EAZ_PS_REGS_GATHER 48
 #define EAZ_PS_REGS_CTRL 24
 #endif
+#ifndef EAZ_PS_GATHER_BATCH
+#define EAZ_PS_GATHER_BATCH 1
+#endif
+constexpr int kGB = EAZ_PS_GATHER_BATCH;  // A chunks a gather warp holds in registers per round trip (4 x 16 bytes per chunk and thread)
 constexpr int kRegsTree = EAZ_PS_REGS_TREE, kRegsGather = EAZ_PS_REGS_GATHER, kRegsCtrl = EAZ_PS_REGS_CTRL;  // (the pool is per CTA: the sum over warps must stay <= 65536)
 template <int N>
 __device__ __forceinline__ void regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -155,6 +162,15 @@ __device__ __forceinline__ uint4 ld_h1(const uint4* p) {
   return __ldg(p);
 #endif
 }
+// A value the compiler may not re-derive (ptxas folds a plain `mov`; a value that went through a warp shuffle -- every lane reads its
+// own -- is not recomputable): shared-window addresses for the inner loops.
+__device__ __forceinline__ uint32_t opaque_u32(uint32_t v) { return __shfl_sync(0xffffffffu, v, threadIdx.x & 31); }
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t pack_next16(int packed) {  // NodeRec.pad0 (action | child + 1 << 8) -> 16 bits (action | child + 1 << 2)
   return (uint32_t)(packed & 3) | ((uint32_t)(packed >> 8) << 2);
 }
@@ -337,7 +353,8 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
     // of ring writes -- i.e. >= 470 cycles against 384 cycles of tensor work; measured 630.)  The whole K = 256 of a row fits beside
     // the accumulator, so there is no A ring and no "stage free" wait either.  Warp g serves the 32 rows of TMEM quarter g % 4 and the
     // chunks of parity g / 4, four chunks per batch: one MEMBAR-carrying hand-over per batch instead of per chunk.
-    regs_inc<kRegsGather>();
+    if (kRegsGather >= 72) regs_inc<kRegsGather>();
+    else regs_dec<kRegsGather>();
     if (head_cta) {
       const int gw = warp - kWarpGather0;
       const int q = warp & 3, half = gw >> 2;
@@ -352,19 +369,19 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
         }
         const uint4* const src = reinterpret_cast<const uint4*>(table + (size_t)sh->cells[32 * q + lane] * (4 * kH));  // [hi 512 B | lo 512 B]
 #pragma unroll 1
-        for (int batch = 0; batch < 2; ++batch) {
-          uint4 v[4][4];  // [chunk of the batch][hi0, hi1, lo0, lo1]
+        for (int batch = 0; batch < 8 / kGB; ++batch) {
+          uint4 v[kGB][4];  // [chunk of the batch][hi0, hi1, lo0, lo1]
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = 2 * (4 * batch + k) + half;
+          for (int k = 0; k < kGB; ++k) {
+            const int c = 2 * (kGB * batch + k) + half;
             v[k][0] = ld_h1(src + 2 * c);
             v[k][1] = ld_h1(src + 2 * c + 1);
             v[k][2] = ld_h1(src + 2 * c + (2 * kH) / 16);
             v[k][3] = ld_h1(src + 2 * c + (2 * kH) / 16 + 1);
           }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int c = 2 * (4 * batch + k) + half;
+          for (int k = 0; k < kGB; ++k) {
+            const int c = 2 * (kGB * batch + k) + half;
             tmem_st8(tq + (uint32_t)(kTmemAhi + c * kAColsPerChunk), v[k][0], v[k][1]);
             tmem_st8(tq + (uint32_t)(kTmemAlo + c * kAColsPerChunk), v[k][2], v[k][3]);
           }
@@ -373,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
           __syncwarp();
           if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mbar_arrive(&sh->full_a[2 * (4 * batch + k) + half]);
+            for (int k = 0; k < kGB; ++k) mbar_arrive(&sh->full_a[2 * (kGB * batch + k) + half]);
           }
         }
         if (gw == 0 && lane == 0) trc.stamp(it, 1);
@@ -770,19 +787,28 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
 
       // ---- 4. simulate: follow the cached selections (all 16 lanes of a tree run the same chase), then the DeepSea transition
       {
+        // (32-bit shared addresses taken through a shuffle + loop-invariant operands in registers: written with the generic pointers,
+        // every level re-derived the shared window base -- S2UR SR_CgaCtaId -- and re-read B / max_depth / the path pointer from the
+        // constant bank, ~290 cycles per level on the critical path; C2 0.961 -> 0.947 ms / step)
         int node = 0, depth = 0, action = 0, child = -1;
         bool active = in_batch;
+        const int max_depth = sp.max_depth;
+        int2* path_p = t.path + ub;
+        const uint32_t next_sa = opaque_u32(smem_u32(s_next));
+        uint32_t back_p = opaque_u32(smem_u32(s_back));
         while (__any_sync(0xffffffffu, active)) {
           if (active) {
-            const int nx = (int)s_next[node];
+            const int nx = (int)lds_u16(next_sa + 2u * (uint32_t)node);
             action = nx & 3;
             child = (nx >> 2) - 1;
             if (hl == 0) {
-              t.path[(unsigned)depth * uB + ub] = make_int2(node, action);
-              if (depth < 32) s_back[depth] = (uint32_t)node | ((uint32_t)action << 16);
+              *path_p = make_int2(node, action);
+              if (depth < 32) sts_u32(back_p, (uint32_t)node | ((uint32_t)action << 16));
             }
+            path_p += uB;
+            back_p += 4u;
             depth += 1;
-            if (child < 0 || depth >= sp.max_depth) active = false;
+            if (child < 0 || depth >= max_depth) active = false;
             else node = child;
           }
         }
