@@ -507,9 +507,10 @@ static bool persistent_eligible(int B, int N, int A, int flags, const EnvDesc& e
   int dev = 0, max_optin = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) return false;
   if (ps::smem_bytes(ncap, env.size) > (size_t)max_optin) return false;  // trees too large for the shared-memory caches
-  // One wave only: a tile's chain (network -> tree -> network ...) is latency-bound, so a second wave of clusters doubles the search
-  // time, while the per-simulation launch chain fills the whole machine with every kernel (measured at DeepSea-100 x 8192 trees =
-  // 64 tiles on 33 co-resident clusters: 5.2 ms persistent vs 4.5 ms chain; at 4096 trees = 32 tiles: 1.20 vs 1.29 ms).
+  // At most two waves of clusters: a tile's chain (network -> tree -> network ...) is latency-bound, so every further wave adds a whole
+  // search time, while the per-simulation launch chain fills the machine with every kernel.  Measured at DeepSea-100 x 8192 trees x 128
+  // simulations (C4: 64 tiles on 37 co-resident clusters, two waves): 3.99 ms persistent vs 4.6 - 4.9 ms chain (before the kernel's
+  // spills were removed: 5.2 vs 4.5); at 4096 trees = 32 tiles: 0.83 vs 1.29 ms.  Larger batches stay on the chain (unmeasured beyond).
   static int max_clusters[32] = {0};  // per device, queried once (idempotent; a race only repeats the query)
   if (dev >= 0 && dev < 32 && max_clusters[dev] == 0) {
     cudaLaunchConfig_t cfg{};
@@ -532,7 +533,7 @@ static bool persistent_eligible(int B, int N, int A, int flags, const EnvDesc& e
     max_clusters[dev] = nc;
   }
   static const bool any_waves = getenv("EAZ_PERSISTENT_WAVES") != nullptr;  // measurement knob: allow more tiles than co-resident clusters
-  if (!any_waves && (dev < 0 || dev >= 32 || ceil_div(B, ps::kTile) > max_clusters[dev])) return false;
+  if (!any_waves && (dev < 0 || dev >= 32 || ceil_div(B, ps::kTile) > 2 * max_clusters[dev])) return false;
   if (ncap_out) *ncap_out = ncap;
   return true;
 }
