@@ -3,6 +3,7 @@
 // variant, and the lane-group reductions whose order is the contract with the
 // CPU oracle (oracle/eaz_oracle.c: orc_tree_sum).
 #pragma once
+#include <cstdlib>
 
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -79,8 +80,9 @@ static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 b
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
+  static const int no_pdl = getenv("EAZ_NO_PDL") != nullptr;  // measurement / debugging knob: plain stream order (no early launch)
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);

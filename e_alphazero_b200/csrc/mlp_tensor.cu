@@ -285,7 +285,12 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       state_staged = true;
     }
     if (tr && threadIdx.x == 0) trace[6] = clock64();
-    if (cached_bits) {  // this row's whole observation as a bit-string in shared memory (Subleq._observe, subleq.py:679-707)
+    // ONE thread per row builds the row's bit-string (producer group 0; thread r and thread 128 + r serve the same row).  Both groups used
+    // to build it redundantly, which is harmless for the paths that store whole words but RACED in the one-hot path below: it zeroes the
+    // row's words and then ORs bits in, so the two threads' read-modify-writes of one word could interleave and drop a bit (A sets bit
+    // r1, B zeroes the word, A reads 0, B sets r1, A writes r2: r1 is gone) -- rarely, and only for non-binary encodings: a few rows of
+    // one head's outputs off by ~3e-2 in up to 15 % of the searches on some boxes (profiles/stress_tensor_subleq.py).
+    if (cached_bits && warp < 4) {  // this row's whole observation as a bit-string in shared memory (Subleq._observe, subleq.py:679-707)
       const int w = env.obs_cols, ws = env.ws;
       if (state_staged && env.binary && ws == 16 && w == 5) {
         // subleq-16 (the reference's own experiment size): 48 rows x 5 bits, and for v in [0, 16] the 5-bit pattern of
@@ -349,7 +354,8 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
       }
     }
     if (tr && threadIdx.x == 0) trace[7] = clock64();
-    if (state_staged) asm volatile("bar.sync 1, 256;" ::: "memory");  // every worker is done with its staged record: A stage 0 may be overwritten
+    // every worker is done with its staged record (A stage 0 may be overwritten) and group 0's bit-strings are visible to group 1
+    if (state_staged || cached_bits) asm volatile("bar.sync 1, 256;" ::: "memory");
     if (tr && threadIdx.x == 0) trace[776] = clock64();
     const uint32_t lane_base = (uint32_t)((warp & 3) * 32) << 16;
     const int grp = warp >> 2;  // two producer groups: group g produces chunks t with t % 2 == g

@@ -1,6 +1,6 @@
 """Stress aid: repeats one TENSOR-mode Subleq search and checks every node's network outputs against the fp32 oracle network on the
 node's own stored state (the (a) half of tests/test_gpu_parity.py::test_search_tensor_mode), reporting WHICH nodes differ.
-Usage (on a B200): python profiles/stress_tensor_subleq.py [reps] [word_size] [binary] [B] [n]"""
+Usage (on a B200): [EAZ_STRESS_POISON=171] python profiles/stress_tensor_subleq.py [reps] [word_size] [binary] [B] [n]"""
 import os
 import sys
 
@@ -24,7 +24,11 @@ denv, dnet = H.device_env(env), H.device_net(net)
 cfg = _abi.default_search_config(mlp_mode=_abi.MLP_TENSOR, num_simulations=n, discount=0.97)
 A = env.num_actions
 bad_runs = 0
+poison = int(os.environ.get("EAZ_STRESS_POISON", "-1"))  # byte pattern written over the allocator's free memory before every search
 for rep in range(reps):
+    if poison >= 0:  # whatever the search reads without having written it is then garbage on every box
+        x = torch.empty(1 << 30, dtype=torch.uint8, device="cuda").fill_(poison)
+        del x
     got = {k: v.cpu().numpy() for k, v in ops.search(cfg, denv, dnet, H.device_root(env, denv, root), want_tree=True).items()}
     emb = got["embeddings"][:, 1:].reshape(B * n, -1)
     st = H.uncompact(env, emb)
@@ -69,6 +73,29 @@ for rep in range(reps):
                         best.append((float(np.abs((alt - alt.max()) - gs).max()), f"chunk {c} <- {nm} chunk {c2}"))
             best.sort()
             print("   best hypotheses:", best[:4])
+            # was another state evaluated?  distance of the GPU row to the expected rows of every node of the batch (and the roots)
+            d_all = np.abs(lg - gs[None, :]).max(1)
+            j = int(np.argmin(d_all))
+            print("   nearest expected row among all nodes:", (j // n, j % n + 1), float(d_all[j]), "| own", float(d_all[i]))
+            root_emb = got["embeddings"][:, 0]
+            evr = O.mlp_forward_states(net, env, H.uncompact(env, root_emb))["exploit_logits"]
+            evr = evr - evr.max(1, keepdims=True)
+            dr = np.abs(evr - gs[None, :]).max(1)
+            print("   nearest root row:", int(np.argmin(dr)), float(dr.min()))
+            # the same state with one memory word / the step count changed
+            base = {k: v[i : i + 1].copy() for k, v in st.items()}
+            cand = []
+            for w in range(ws):
+                for val in range(ws):
+                    c2 = {k: v.copy() for k, v in base.items()}
+                    c2["memory"][0, w] = val
+                    cand.append((w, val, c2))
+            allc = {k: np.concatenate([c[2][k] for c in cand]) for k in base}
+            evc = O.mlp_forward_states(net, env, allc)["exploit_logits"]
+            evc = evc - evc.max(1, keepdims=True)
+            dc = np.abs(evc - gs[None, :]).max(1)
+            jj = int(np.argmin(dc))
+            print("   nearest one-word variant: memory[%d] = %d" % (cand[jj][0], cand[jj][1]), float(dc[jj]))
             same_state = [int(j) for j in range(B * n) if (emb[j] == emb[i]).all()]
             print("   nodes with the same state:", [(j // n, j % n + 1, float(dl[j])) for j in same_state[:10]])
 print(f"{bad_runs} of {reps} runs had mismatching nodes")
