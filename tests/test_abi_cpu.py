@@ -125,3 +125,29 @@ def test_xla_ffi_shim_builds_and_validates(lib):
                  hash_bits=24, hash_io=1, max_u=1.0, novelty_scale=1.0)
     rc, msg = X.call(shim, "EazSearch", args, rets, attrs)
     assert rc == 3 and "word_size" in msg
+
+
+def test_alloc_arena_layout_on_cpu():
+    """ops.alloc_arena: every tensor is a typed view of ONE flat allocation at 256-byte aligned offsets, and an arena built from the
+    same specs anywhere (e.g. pinned host memory) has the same layout -- one copy of `flat` moves all of them."""
+    import torch
+
+    from e_alphazero_b200 import ops
+
+    specs = [("a", (5,), torch.int32), ("b", (5, 3), torch.float32), ("c", (7,), torch.uint8), ("d", (2, 2, 2), torch.float32)]
+    flat, views = ops.alloc_arena(specs, device="cpu")
+    flat2, views2 = ops.alloc_arena(specs, device="cpu")
+    assert flat.dtype == torch.uint8 and flat.numel() == flat2.numel() == 4 * 256
+    base = flat.data_ptr()
+    offs = [views[n].data_ptr() - base for n, _, _ in specs]
+    assert offs == [0, 256, 512, 768] and all(o % 256 == 0 for o in offs)
+    for name, shape, dt in specs:
+        assert tuple(views[name].shape) == shape and views[name].dtype == dt and views[name].is_contiguous()
+    views["b"].copy_(torch.arange(15, dtype=torch.float32).reshape(5, 3))
+    views["c"].fill_(7)
+    flat2.copy_(flat)  # ONE copy moves every tensor
+    assert torch.equal(views2["b"], views["b"]) and torch.equal(views2["c"], views["c"]) and int(views2["a"].abs().sum()) == 0
+    # the search-output arena of a plan is built from specs that name every summary / root field once
+    sp = ops.search_output_specs(B=4, N=9, A=2, S=4, want_tree=True)
+    names = [n for n, _, _ in sp]
+    assert len(names) == len(set(names)) and {"action", "value", "root_value", "children_prior_logits"} <= set(names)
