@@ -355,6 +355,32 @@ def test_search_tensor_mode(ops, kind, kw, B, cfg_kw, root_kw):
     assert_tree_equal(exp, got)
 
 
+def test_tensor_mode_one_hot_subleq_repeated(ops):
+    """Regression: with the NON-binary (one-hot) Subleq encoding the tensor-core network kernel's two producer groups used to build a row's
+    observation bit-string concurrently (zero the words, then OR bits in), and on some boxes ~15 % of the searches evaluated a few rows with
+    one input bit dropped (logits off by ~3e-2).  60 searches, every node's network outputs against the fp32 oracle each time."""
+    env = H.make_env("subleq", seed=11, word_size=20, binary=False)
+    net = H.make_net(env, seed=12, fill=0.5)
+    B, n = 40, 16
+    root = H.make_root(env, net, B, seed=13, beta_max=0.0)
+    denv, dnet = H.device_env(env), H.device_net(net)
+    cfg = _abi.default_search_config(mlp_mode=_abi.MLP_TENSOR, num_simulations=n, discount=0.97)
+    cfg.batch = B
+    plan = ops.SearchPlan(cfg, denv, dnet, want_tree=True)
+    droot = H.device_root(env, denv, root)
+    A = env.num_actions
+    for rep in range(60):
+        got = {k: host(v) for k, v in plan.run(droot).items() if k in ("embeddings", "children_prior_logits", "raw_values", "raw_values_epistemic_variance")}
+        st = H.uncompact(env, got["embeddings"][:, 1:].reshape(B * n, -1))
+        ev = O.mlp_forward_states(net, env, st)
+        lg = ev["exploit_logits"] - ev["exploit_logits"].max(1, keepdims=True)
+        term = st["terminated"].astype(bool)
+        np.testing.assert_allclose(got["children_prior_logits"][:, 1:].reshape(B * n, A), lg, rtol=1e-5, atol=2e-6, err_msg=f"search {rep}")
+        np.testing.assert_allclose(got["raw_values"][:, 1:].reshape(-1), np.where(term, 0, ev["value"]), rtol=1e-5, atol=2e-6, err_msg=f"search {rep}")
+        np.testing.assert_allclose(got["raw_values_epistemic_variance"][:, 1:].reshape(-1), np.where(term, 0, ev["ube"]), rtol=1e-5, atol=2e-6,
+                                   err_msg=f"search {rep}")
+
+
 def _wide_range_net(env, seed, w_big):
     """Sparse network with |w| up to `w_big` in layers 2 / 3 (two non-zeros per output column), small dense layer 1."""
     net = H.make_net(env, seed=seed, fill=0.5)
