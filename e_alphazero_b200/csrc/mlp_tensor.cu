@@ -14,8 +14,7 @@
 // contiguous block fetched with a single 1-D bulk async copy (UBLKCP) that signals an mbarrier.
 // Warp roles: warps 0-7 = two producer groups (thread == row; group g produces chunks t % 2 == g, prefetching its
 // next chunk's operands before storing the current one) that also run the epilogue, warp 8 issues the MMAs,
-// warp 9 issues the weight copies.  4-stage mbarrier pipeline of K=32 chunks: A 16 KB + B 32 KB per stage, so
-// three weight copies and three A chunks are in flight behind the MMAs of the current chunk.
+// warp 9 issues the weight copies.  mbarrier pipeline of K=32 chunks, A 16 KB + B 32 KB per stage (kStages below).
 //
 // Accuracy: <= ~1e-6 relative to the fp32 EXACT contract (tests: 1e-5); NOT bit-identical to it, so search
 // parity in this mode is proven by replaying the GPU's per-node network outputs through the oracle.
@@ -29,7 +28,14 @@ int launch_weight_scales(const NetDesc& net, int heads_mask, NumStatus* ns, cuda
 
 constexpr int kTM = 128;                       // rows per CTA
 constexpr int kCK = 32;                        // K elements (fp16) per pipeline stage: 64 B per row
-constexpr int kStages = 4;
+#ifndef EAZ_MT_STAGES
+#define EAZ_MT_STAGES 2
+#endif
+// Pipeline stages (A 16 KB + B 32 KB each).  TWO, measured: with four a CTA holds 205 KB of shared memory and owns its SM, so under the
+// sub-batch streams (EAZ_FLAG_STREAMS) the tree kernel's blocks of another sub-batch cannot use the issue slots the ten network warps
+// leave idle; with two (109 KB) four tree blocks -- or the next network CTA's prologue -- fit beside it.  C3 (3 streams) 4.72 -> 4.50 ms
+// per step (three stages: 4.62), one stream 5.39 -> 5.38; C5 16 384 x 128: 102 -> 107 M simulations/s, 65 536 x 128: 106 -> 108.
+constexpr int kStages = EAZ_MT_STAGES;
 constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 8-row group stride inside a chunk tile (512 B)
 constexpr int kAHalf = kTM * kCK * 2;          // one of hi / lo
 constexpr int kAStage = 2 * kAHalf;
@@ -242,7 +248,7 @@ __global__ void __launch_bounds__(320, 1) mlp_tensor_kernel(NetDesc net, EnvDesc
         const uint32_t blo_off = (uint32_t)(npad * kCK * 2) >> 4, alo_off = (uint32_t)kAHalf >> 4;
 #pragma unroll 1
         for (int c = 0; c < nchunks; ++c, ++t) {
-          const int s = t & (kStages - 1), ph = (t / kStages) & 1;
+          const int s = t % kStages, ph = (t / kStages) & 1;
           mbar_wait(&sh->full_b[s], ph);
           mbar_wait(&sh->full_a[s], ph);
           tc_fence_after();
