@@ -639,6 +639,80 @@ __global__ void __launch_bounds__(3 * EAZ_SQ_EPB) subleq_tree_step_kernel(Tree t
   t.reward[b] = reward;
 }
 
+// The same transition for word size 16 (C3 / C5 above kSqFusedMaxTrees): the machine runs in registers (common.cuh: subleq_simulate16), so a
+// block needs neither the 264-byte program rows nor the per-test images -- 8 KB of shared memory for 64 envs instead of 38 KB for 32, and
+// ten 192-thread blocks per SM instead of six 96-thread ones (the dense kernel above ran at 7-8 % of the SM's warp slots).
+constexpr int kSq16Epb = 64;
+__global__ void __launch_bounds__(3 * kSq16Epb) subleq16_tree_step_kernel(Tree t, EnvDesc env) {
+  constexpr int kRec = EAZ_SQ_HDR + 16;  // compact state record: header + 16 memory bytes
+  __shared__ __align__(8) uint8_t rec[kSq16Epb][kRec];
+  __shared__ unsigned long long s_mem[kSq16Epb];
+  __shared__ int kind[kSq16Epb], trow[kSq16Epb];  // kind: 0 absorbing, 1 terminate now, 2 execute
+  __shared__ int correct[kSq16Epb][3], bytes_used[kSq16Epb][3];
+  __shared__ int16_t in_after[kSq16Epb][8], out_after[kSq16Epb][8];
+  const int e = threadIdx.x / 3, k = threadIdx.x % 3;
+  const int b = blockIdx.x * kSq16Epb + e;
+  if (k == 0) {
+    int kd = -1;
+    if (b < t.B) {
+      const uint2* ps = reinterpret_cast<const uint2*>(t.states + ((size_t)t.parent[b] * t.B + b) * kRec);
+#pragma unroll
+      for (int i = 0; i < kRec / 8; ++i) reinterpret_cast<uint2*>(rec[e])[i] = ps[i];
+      uint16_t* h = reinterpret_cast<uint16_t*>(rec[e]);
+      const int flags = rec[e][35];
+      if (flags & (EAZ_SQ_FLAG_TERM | EAZ_SQ_FLAG_TRUNC)) {
+        kd = 0;
+      } else {
+        const int step = h[16] + 1;  // _step_count incremented before _step
+        h[16] = (uint16_t)step;
+        if (step >= 16 - 3 || (flags & EAZ_SQ_FLAG_SOLVED)) {  // subleq.py:671-673
+          kd = 1;
+          rec[e][35] = (uint8_t)(flags | EAZ_SQ_FLAG_TERM);
+        } else {
+          rec[e][EAZ_SQ_HDR + step - 1] = (uint8_t)t.action[b];  // :654
+          trow[e] = sq_task_row(rec[e][34]);
+          s_mem[e] = sq_pack_nibbles16(reinterpret_cast<const uint32_t*>(rec[e] + EAZ_SQ_HDR));
+          kd = 2;
+        }
+      }
+    }
+    kind[e] = kd;
+  }
+  __syncthreads();
+  if (kind[e] == 2) {  // run_tests (subleq.py:504-532): thread k interprets test case k
+    SubleqSim r;
+    subleq_simulate16<true>(s_mem[e], trow[e], k, r);
+    correct[e][k] = r.correct;
+    bytes_used[e][k] = r.bytes_used;
+    if (k == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        in_after[e][i] = (int16_t)r.in[i];
+        out_after[e][i] = (int16_t)r.out[i];
+      }
+    }
+  }
+  __syncthreads();
+  if (k != 0 || b >= t.B) return;
+  float reward = 0.0f;
+  if (kind[e] == 2) {
+    const int solved = correct[e][0] & correct[e][1] & correct[e][2];
+    const int bytes = max(bytes_used[e][0], max(bytes_used[e][1], bytes_used[e][2]));
+    reward = subleq_reward(env.reward_fn, solved, bytes);
+    uint16_t* h = reinterpret_cast<uint16_t*>(rec[e]);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      h[i] = (uint16_t)in_after[e][i];
+      h[8 + i] = (uint16_t)out_after[e][i];
+    }
+    rec[e][35] = (uint8_t)((rec[e][35] & ~EAZ_SQ_FLAG_SOLVED) | (solved ? EAZ_SQ_FLAG_SOLVED : 0));
+  }
+  uint2* cs = reinterpret_cast<uint2*>(t.states + ((size_t)t.leaf[b] * t.B + b) * kRec);
+#pragma unroll
+  for (int i = 0; i < kRec / 8; ++i) cs[i] = reinterpret_cast<const uint2*>(rec[e])[i];
+  t.reward[b] = reward;
+}
+
 // ------------------------------------------------------------------ policy output (A.1 step 4) + epistemic_summary (A.7)
 struct SummaryOut {
   int32_t* action;
@@ -921,9 +995,14 @@ static int run_search(const Tree& t, const SearchParams& sp, const EnvDesc& env,
     if (sim == sp.n) break;
     if (env.kind == EAZ_ENV_SUBLEQ && !sq_fused) {
       ProfScope ps(CLS_ENV, st);
-      size_t dyn = 0;
-      if (cudaError_t e = sq_prepare_launch(subleq_tree_step_kernel, env.ws, &dyn); e != cudaSuccess) return cuda_fail(e, "subleq_tree_step_kernel attribute");
-      subleq_tree_step_kernel<<<ceil_div(t.B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, dyn, st>>>(t, env);
+      static const bool generic_sq = getenv("EAZ_SUBLEQ_GENERIC") != nullptr;  // measurement knob: the any-word-size kernel for ws = 16 too
+      if (env.ws == 16 && t.S == EAZ_SQ_HDR + 16 && !generic_sq) {
+        subleq16_tree_step_kernel<<<ceil_div(t.B, kSq16Epb), 3 * kSq16Epb, 0, st>>>(t, env);
+      } else {
+        size_t dyn = 0;
+        if (cudaError_t e = sq_prepare_launch(subleq_tree_step_kernel, env.ws, &dyn); e != cudaSuccess) return cuda_fail(e, "subleq_tree_step_kernel attribute");
+        subleq_tree_step_kernel<<<ceil_div(t.B, EAZ_SQ_EPB), 3 * EAZ_SQ_EPB, dyn, st>>>(t, env);
+      }
       EAZ_CHECK_LAUNCH("subleq_tree_step_kernel");
     }
     {
