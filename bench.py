@@ -606,7 +606,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the short C3 / C4 / C5-point measurements of the `extra` block")
     ap.add_argument("--streams", type=int, default=0,
-                    help="EAZ_FLAG_STREAMS: search this many sub-batches concurrently on auxiliary streams (0 = 3, or 1 for DeepSea batches beyond one wave of the persistent kernel: measured best)")
+                    help="EAZ_FLAG_STREAMS: search this many sub-batches concurrently on auxiliary streams (0 = 3, or 1 for DeepSea batches beyond one wave of clusters: C4 then runs as ONE persistent launch over two waves)")
     ap.add_argument("--envs-per-gpu", type=int, default=0, help="override the workload's batch (exploration, not a BASELINE config)")
     ap.add_argument("--sims", type=int, default=0, help="override the workload's simulation count")
     ap.add_argument("--param-refresh", type=int, default=8,
@@ -619,7 +619,7 @@ def main():
         B, n = args.envs_per_gpu or B, args.sims or n
         desc += f" [overridden: {B} envs/GPU, {n} simulations]"
     if args.streams <= 0:
-        args.streams = 1 if (kind == "deepsea" and B > 4096) else 3  # (C4: one stream + the two-CTAs-per-SM network kernel, mlp_gather.cu)
+        args.streams = 1 if (kind == "deepsea" and B > 4096) else 3  # (C4: one persistent launch, two waves of clusters: psearch.cuh)
     if args.impl == "reference":
         run_reference(args, kind, kw, B, n, gamma, desc)
     else:

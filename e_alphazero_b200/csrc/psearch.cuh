@@ -8,7 +8,7 @@
 //     keep, per tree and for the whole search, the cached selection and the compact env state of EVERY node in shared memory (the
 //     pointer-chase descent never leaves the SM), plus a staging area with the node / edge records of the current path;
 //   * CTAs 0..2 additionally run ONE NETWORK HEAD each (value, UBE, policy) for all 128 rows of the tile: 8 gather warps copy the
-//     pre-activated fp16 hi/lo layer-1 rows (mlp_gather.cu: h1 table) of the 128 leaf cells into a 4-stage ring, one warp streams the
+//     pre-activated fp16 hi/lo layer-1 rows (mlp_gather.cu: h1 table) of the 128 leaf cells straight into tensor memory, one warp streams the
 //     W2 chunk images with 1-D bulk async copies (the ring runs ahead across simulations: the weights never change), one elected
 //     thread issues tcgen05.mma kind::f16 (M=128, N=256, K=16, 3 split-precision products per chunk) into a TMEM accumulator that
 //     stays allocated for the whole search; layer 3 (<= 2 outputs) runs on the CUDA cores of the 16 tree warps straight out of TMEM;
