@@ -77,11 +77,11 @@ constexpr int kBStage = 2 * kBHalf;
 constexpr int kTmemCols = 512, kTmemAhi = 256, kTmemAlo = 384, kAColsPerChunk = kCK / 2;
 constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 256 B between 8-row groups
 #ifndef EAZ_PS_IDLE_NS
-#define EAZ_PS_IDLE_NS 0
+#define EAZ_PS_IDLE_NS 300
 #endif
-// Sleep between polls of a role that waits for the other phase (0 = spin).  Measured at C2 (ms / step): 0: 1.126, 40 ns: 1.160, 100 ns: 1.148,
-// 300 ns: 1.127 -- mbarrier.try_wait already suspends the polling thread, so the polls do not crowd out the working warps and a sleep
-// only adds wake-up latency to every hand-over.  Kept as a build knob.
+// Sleep between polls of a role that waits for the other phase (0 = spin).  While the tree step still spilled registers the polls did
+// not matter (ms / step at C2: 0: 1.126, 40 ns: 1.160, 100 ns: 1.148, 300 ns: 1.127); with the spills gone the waiting roles' polls
+// are what competes with the tree warps for issue slots: 0: 0.945, 100 ns: 0.952, 300 ns: 0.931, 500 ns: 0.932, 1000 ns: 0.959.
 constexpr unsigned kIdleNs = EAZ_PS_IDLE_NS;
 constexpr int kBarL3 = 1, kBarA0 = 2;  // named barriers: layer-3 partial sums; A-ring stage s = kBarA0 + s
 // (activation scale kActScale = 16: mlp.cuh; the W2 images carry a per-matrix power-of-two scale: Args::unscale)
