@@ -83,6 +83,18 @@ constexpr int kSBO = (kCK * 2 / 16) * kCoreBytes;  // 256 B between 8-row groups
 // not matter (ms / step at C2: 0: 1.126, 40 ns: 1.160, 100 ns: 1.148, 300 ns: 1.127); with the spills gone the waiting roles' polls
 // are what competes with the tree warps for issue slots: 0: 0.945, 100 ns: 0.952, 300 ns: 0.931, 500 ns: 0.932, 1000 ns: 0.959.
 constexpr unsigned kIdleNs = EAZ_PS_IDLE_NS;
+#ifndef EAZ_PS_IDLE_OUT_NS
+#define EAZ_PS_IDLE_OUT_NS EAZ_PS_IDLE_NS
+#endif
+#ifndef EAZ_PS_IDLE_ACC_NS
+#define EAZ_PS_IDLE_ACC_NS EAZ_PS_IDLE_NS
+#endif
+// The tree warps' two waits inside the network phase can poll at their own pace: acc_done (the MMAs are still running, the gather warps
+// are done) and out_full (after layer 3: a short wait for the slowest head's st.async, nobody else needs the issue slots).
+#ifndef EAZ_PS_IDLE_CELLS_NS
+#define EAZ_PS_IDLE_CELLS_NS EAZ_PS_IDLE_NS
+#endif
+constexpr unsigned kIdleOutNs = EAZ_PS_IDLE_OUT_NS, kIdleAccNs = EAZ_PS_IDLE_ACC_NS, kIdleCellsNs = EAZ_PS_IDLE_CELLS_NS;  // (cells: the gather warps)
 constexpr int kBarL3 = 1, kBarA0 = 2;  // named barriers: layer-3 partial sums; A-ring stage s = kBarA0 + s
 // (activation scale kActScale = 16: mlp.cuh; the W2 images carry a per-matrix power-of-two scale: Args::unscale)
 
@@ -144,8 +156,9 @@ __device__ __forceinline__ void st_async_u32(uint32_t cluster_addr, uint32_t v, 
                : "memory");
 }
 __device__ __forceinline__ void warp_wait(uint64_t* bar, uint32_t parity, int) { mbar_wait_warp(bar, parity); }  // (umma.cuh)
+template <unsigned kNs = kIdleNs>
 __device__ __forceinline__ void warp_wait_idle(uint64_t* bar, uint32_t parity) {
-  if (kIdleNs) mbar_wait_warp_idle(bar, parity, kIdleNs);
+  if (kNs) mbar_wait_warp_idle(bar, parity, kNs);
   else mbar_wait_warp(bar, parity);
 }
 
@@ -362,7 +375,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       const uint32_t tq = sh->tmem_base + ((uint32_t)(32 * q) << 16);
 #pragma unroll 1
       for (int it = 0; it < n; ++it) {
-        warp_wait_idle(&sh->cells_full, it & 1);
+        warp_wait_idle<kIdleCellsNs>(&sh->cells_full, it & 1);
         if (gw == 0 && lane == 0) {
           trc.stamp(it, 0);
           if (it + 1 < n) mbar_arrive_expect_tx(&sh->cells_full, kTile * 4);  // arm the next phase (nobody publishes before this evaluation's outputs)
@@ -537,7 +550,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
           warp_wait_idle(&sh->cells_full, it & 1);
           seen = a.ds_seen[sh->cells[row]];
         }
-        warp_wait_idle(&sh->acc_done, it & 1);
+        warp_wait_idle<kIdleAccNs>(&sh->acc_done, it & 1);
         tc_fence_after();
         if (tstamp) trc.stamp(it, 2);
         const uint32_t taddr = sh->tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(64 * cg);
@@ -605,7 +618,7 @@ __global__ void __launch_bounds__(kThreads, 1) ds_search_kernel(const __grid_con
       }
 
       // ============================================================== this warp's trees: outputs of simulation `it` -> step `sim`
-      warp_wait_idle(&sh->out_full, it & 1);
+      warp_wait_idle<kIdleOutNs>(&sh->out_full, it & 1);
       if (tw == 0 && lane == 0 && it + 1 < n) mbar_arrive_expect_tx(&sh->out_full, out_bytes);  // arm the next phase
       if (tstamp) trc.stamp(it, 4);
       if (lane == 0) trc_all.warp_out_full(it, (int)rank * kTWarps + tw);
